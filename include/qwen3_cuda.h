@@ -1,0 +1,147 @@
+/*
+ * qwen3_cuda.h -- C ABI of libqwen3cuda, the B200 (sm_100a) drop-in for qwen3-rs's quantized
+ * forward pass.
+ *
+ * This is the boundary a Rust `qwen3-cuda` crate binds with `extern "C"`
+ * to implement qwen3-inference's
+ *
+ *     pub trait Transformer {                                  // models/mod.rs:13-18
+ *         fn forward(&mut self, token: usize, pos: usize) -> &[f32];
+ *         fn get_config(&self) -> &ModelConfig;
+ *     }
+ *
+ * and `TransformerBuilder::new(path).with_ctx_length(opt).build()` (models/mod.rs:40-74).
+ * Plain pointers and sizes only; no exceptions cross the boundary.  Every entry point returns
+ * 0 on success and a negative Q3_E* code on failure, with a message in q3_last_error().
+ * A handle is owned by one caller thread at a time (the reference takes `&mut self`).
+ * All file:line citations are relative to the reference repository root.
+ */
+#ifndef QWEN3_CUDA_H
+#define QWEN3_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define Q3_OK 0
+#define Q3_EINVAL (-1)   /* bad argument (reference: panic on slice index / assert)        */
+#define Q3_EIO (-2)      /* cannot open / map the checkpoint (models/mod.rs:56-59)          */
+#define Q3_EFORMAT (-3)  /* bad magic / version / dims / short file (configuration.rs:116-146, utils.rs:21-26) */
+#define Q3_ECUDA (-4)    /* CUDA runtime error                                              */
+#define Q3_EUNSUPPORTED (-5) /* shape outside what the kernels cover (e.g. head_dim != 128) */
+#define Q3_ECOMM (-6)    /* tensor-parallel communicator error                              */
+
+/* POD mirror of ModelConfig (configuration.rs:18-30), same field meaning.  seq_len already has
+ * the context-length override applied (models/mod.rs:65-67). */
+typedef struct q3_config {
+    int32_t architecture_id;
+    int32_t dim;
+    int32_t hidden_dim;
+    int32_t n_layers;
+    int32_t n_heads;
+    int32_t n_kv_heads;
+    int32_t head_dim;
+    int32_t seq_len;
+    int32_t vocab_size;
+    int32_t group_size;
+    int32_t shared_classifier;
+} q3_config;
+
+typedef struct q3_handle q3_handle;
+
+/* ---- construction: TransformerBuilder (models/mod.rs:40-74) --------------------------------
+ * Opens and validates the checkpoint (configuration.rs:77-146), uploads it once to HBM
+ * (re-laid-out for the kernels), zero-fills the device KV cache (qwen3.rs:439-440) and uploads
+ * the host-computed RoPE table (layers.rs:161-171).  ctx_len <= 0 keeps the file's seq_len.
+ * device: CUDA ordinal. */
+int q3_create(const char *checkpoint_path, int ctx_len, int device, q3_handle **out);
+
+/* Tensor-parallel member: rank `tp_rank` of `tp_size` (one process per GPU).  Attention heads
+ * and FFN columns are sharded; the exchange after o_proj / down_proj runs over
+ * NVLink peer memory.  After creating every rank call q3_tp_export / q3_tp_connect. */
+int q3_create_tp(const char *checkpoint_path, int ctx_len, int device, int tp_rank, int tp_size,
+                 q3_handle **out);
+/* Size in bytes of the opaque per-rank blob (CUDA IPC handles of the exchange buffers). */
+size_t q3_tp_blob_size(void);
+int q3_tp_export(q3_handle *h, void *blob_out);
+/* blobs: tp_size blobs, rank-major (all-gathered by the host, e.g. torch.distributed). */
+int q3_tp_connect(q3_handle *h, const void *blobs);
+
+void q3_destroy(q3_handle *h);
+
+/* ---- Transformer::get_config (models/mod.rs:17) ------------------------------------------- */
+const q3_config *q3_get_config(const q3_handle *h);
+
+/* ---- Transformer::forward (models/mod.rs:15, qwen3.rs:62-79) -------------------------------
+ * Runs one decode step on the device and copies the vocab_size logits to logits_host (the
+ * reference returns a borrow of its own logits that the caller copies, generation.rs:159-160).
+ * logits_host == NULL leaves them on the device (see q3_logits_device).
+ * token >= vocab_size or pos >= seq_len -> Q3_EINVAL (the reference panics). */
+int q3_forward(q3_handle *h, int token, int pos, float *logits_host);
+
+/* Extension: forward + device-side greedy argmax with the reference's
+ * tie rule (sampler.rs:57-59: last index among equal maxima).  Only 4 bytes cross PCIe. */
+int q3_forward_argmax(q3_handle *h, int token, int pos, int *next_token);
+
+/* Extension: n greedy steps entirely on the device (token feedback stays in HBM); tokens_out
+ * receives the n sampled tokens.  Equivalent to n q3_forward_argmax calls starting at
+ * (first_token, pos0). */
+int q3_decode_greedy(q3_handle *h, int first_token, int pos0, int n, int *tokens_out);
+
+/* Extension: batched prefill of n tokens at positions pos0..pos0+n-1.  Leaves
+ * the KV cache as n sequential forwards would (within float tolerance) and returns the logits
+ * of the last token (NULL to skip). */
+int q3_prefill(q3_handle *h, const int *tokens, int n, int pos0, float *last_logits_host);
+
+/* Zero the KV cache (a freshly built reference transformer, qwen3.rs:439-440). */
+int q3_reset(q3_handle *h);
+
+/* Device pointer to the logits of the last forward (vocab_size f32, valid until the next call). */
+const float *q3_logits_device(const q3_handle *h);
+
+/* Copy KV cache rows [pos0, pos0+n) of one layer to the host, layout [n][n_kv_heads*head_dim]
+ * (the reference's cache layout, layers.rs:329-331), or overwrite them from the host. */
+int q3_kv_read(q3_handle *h, int layer, int pos0, int n, float *k_host, float *v_host);
+int q3_kv_write(q3_handle *h, int layer, int pos0, int n, const float *k_host, const float *v_host);
+
+/* Run layers [layer0, layer1) of one decode step on a caller-supplied residual stream x
+ * (dim f32, host), in place -- the production kernels, teacher-forced for layer-level parity
+ * tests.  With run_head != 0 also final norm + lm_head into logits_host. */
+int q3_forward_layers(q3_handle *h, int pos, int layer0, int layer1, float *x_host, int run_head,
+                      float *logits_host);
+
+/* Which execution path q3_forward uses: 0 = multi-kernel CUDA graph, 1 = persistent
+ * single-launch decode kernel.  Default: the fastest available. */
+int q3_set_decode_path(q3_handle *h, int path);
+
+/* Timing helper for benchmarks: runs `steps` decode steps at positions pos0.. (greedy token
+ * feedback on the device) with inputs already resident, timed with CUDA events on the launch
+ * stream; returns total milliseconds. */
+int q3_bench_decode(q3_handle *h, int first_token, int pos0, int steps, float *ms_out);
+/* Number of kernel launches one decode step issues on the current path. */
+int q3_launches_per_step(const q3_handle *h);
+
+/* ---- operator-level entry points (host buffers in/out; used by the parity tests) -----------
+ * Each runs the same device code the forward pass uses. */
+/* tensor.rs:91-119 quantize */
+int q3_op_quantize(int device, const float *x, int n, int gs, int8_t *q_out, float *s_out);
+/* tensor.rs:23-62 matmul: out[d] from x (int8[n] + f32[n/gs]) and row-major w (int8[d*n] +
+ * f32[d*n/gs]).  group_dots_out (optional, int32[d*(n/gs)]) receives the per-group integer
+ * dot products the kernel accumulated. */
+int q3_op_matmul(int device, const int8_t *xq, const float *xs, const int8_t *wq, const float *ws,
+                 int n, int d, int gs, float *out, int32_t *group_dots_out);
+/* layers.rs:109-119 RMSNorm::forward */
+int q3_op_rmsnorm(int device, const float *x, const float *w, int n, float *out);
+/* qwen3-export model_exporter.rs:104-161 quantize_q80 on the device. */
+int q3_op_quantize_q80(int device, const float *w, size_t n, int gs, int8_t *q_out, float *s_out);
+
+const char *q3_last_error(void);
+const char *q3_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QWEN3_CUDA_H */

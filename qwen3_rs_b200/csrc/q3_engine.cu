@@ -1,0 +1,805 @@
+// q3_engine.cu -- host side of libqwen3cuda: checkpoint loader, HBM layout, decode graph and
+// the extern "C" API declared in include/qwen3_cuda.h.
+//
+// Mirrors the reference's construction path: TransformerBuilder::build (models/mod.rs:55-73) ->
+// read_config (configuration.rs:77-146) -> load_weights (qwen3.rs:199-277) ->
+// TransformerBlockBuffers::new (qwen3.rs:412-445), then Qwen3Transformer::forward (qwen3.rs:62-79).
+#include "../../include/qwen3_cuda.h"
+#include "q3_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <string>
+#include <vector>
+
+using namespace q3;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(Q3_ECUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                        cudaGetErrorString(e_));                                                        \
+    } while (0)
+
+extern "C" const char *q3_last_error(void) { return g_err; }
+extern "C" const char *q3_version(void) { return "qwen3cuda 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct DevQT { // device QuantizedTensor: row-major int8 [rows][K] + f32 scales [rows][K/gs]
+    int8_t *q = nullptr;
+    float *s = nullptr;
+    int rows = 0, K = 0;
+};
+
+struct LayerDev {
+    DevQT qkv; // rows: [AH_l q | KV_l k | KV_l v]            (layers.rs:334-336 fused)
+    DevQT wo;  // [dim][AH_l]
+    DevQT w13; // rows interleaved (gate_j, up_j), j < H_l      (layers.rs:468-469 fused)
+    DevQT w2;  // [dim][H_l]
+    float *rms_att = nullptr, *rms_ffn = nullptr, *q_ln = nullptr, *k_ln = nullptr;
+};
+
+struct q3_handle {
+    q3_config cfg{};
+    int device = 0;
+    int tp_rank = 0, tp_size = 1;
+    int n_heads_l = 0, n_kv_l = 0, AH_l = 0, KV_l = 0, H_l = 0, kv_mul = 1;
+    int num_sms = 148;
+    std::vector<LayerDev> layers;
+    DevQT embed, wcls;
+    float *rms_final = nullptr;
+    float *rope = nullptr; // [seq_len][64][2]
+    // activations
+    float *x = nullptr, *xb = nullptr, *q = nullptr, *hb = nullptr, *logits = nullptr, *attn_part = nullptr;
+    int8_t *xq = nullptr, *hq = nullptr;
+    float *xs = nullptr, *hs = nullptr;
+    float *kc = nullptr, *vc = nullptr; // [L][seq_len][KV_l]
+    int *d_tokpos = nullptr;            // [0]=token [1]=pos [2]=argmax out [3]=history idx
+    int *d_history = nullptr;
+    int history_cap = 0;
+    float *h_logits = nullptr; // pinned
+    int *h_small = nullptr;    // pinned scratch
+    cudaStream_t stream = nullptr;
+    cudaGraphExec_t g_fwd = nullptr, g_greedy = nullptr;
+    int decode_path = 0;
+    int launches_per_step = 0;
+    size_t dev_bytes = 0;
+    std::vector<void *> allocs;
+};
+
+static int dmalloc(q3_handle *h, void **p, size_t bytes) {
+    CK(cudaMalloc(p, bytes ? bytes : 16));
+    h->allocs.push_back(*p);
+    h->dev_bytes += bytes;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// checkpoint (configuration.rs, utils.rs)
+// ------------------------------------------------------------------------------------------
+struct HostQT {
+    const int8_t *q;
+    const float *s;
+};
+struct Ckpt {
+    uint8_t *map = nullptr;
+    size_t len = 0, off = 0;
+    q3_config cfg{};
+    const float *rms_att, *rms_ffn, *rms_final, *q_ln, *k_ln;
+    HostQT embed, wcls;
+    std::vector<HostQT> wq, wk, wv, wo, w1, w2, w3;
+    ~Ckpt() {
+        if (map) munmap(map, len);
+    }
+    const void *take(size_t bytes) { // utils.rs:21-49
+        if (off + bytes > len) return nullptr;
+        const void *p = map + off;
+        off += bytes;
+        return p;
+    }
+};
+
+static int open_ckpt(const char *path, int ctx_len, Ckpt &c) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(Q3_EIO, "Failed to open checkpoint: %s", path);
+    struct stat st;
+    fstat(fd, &st);
+    c.len = (size_t)st.st_size;
+    void *m = mmap(nullptr, c.len ? c.len : 1, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return fail(Q3_EIO, "Failed to create memory mapping");
+    c.map = (uint8_t *)m;
+    const int32_t *hd = (const int32_t *)c.take(13 * 4);
+    if (!hd) return fail(Q3_EFORMAT, "Insufficient data for config: need 52 bytes, got %zu", c.len);
+    if (hd[0] != 0x616a6331)
+        return fail(Q3_EFORMAT, "Invalid checkpoint magic number: expected 0x616a6331, got %#x", hd[0]);
+    if (hd[1] != 1) return fail(Q3_EFORMAT, "Unsupported checkpoint version: expected 1, got %d", hd[1]);
+    const char *names[8] = {"architecture_id", "dim", "n_layers", "n_heads", "n_kv_heads", "vocab_size", "seq_len", "head_dim"};
+    int32_t vals[8] = {hd[2], hd[3], hd[5], hd[6], hd[7], hd[8], hd[9], hd[10]};
+    for (int i = 0; i < 8; i++)
+        if (vals[i] <= 0) return fail(Q3_EFORMAT, "Invalid %s: must be positive, got %d", names[i], vals[i]);
+    if (!c.take(256 - 52)) return fail(Q3_EFORMAT, "Cannot skip %d bytes: insufficient data", 256 - 52);
+    q3_config &cf = c.cfg;
+    cf.architecture_id = hd[2]; cf.dim = hd[3]; cf.hidden_dim = hd[4]; cf.n_layers = hd[5];
+    cf.n_heads = hd[6]; cf.n_kv_heads = hd[7]; cf.vocab_size = hd[8]; cf.seq_len = hd[9];
+    cf.head_dim = hd[10]; cf.shared_classifier = hd[11] != 0; cf.group_size = hd[12];
+    if (ctx_len > 0 && ctx_len < cf.seq_len) cf.seq_len = ctx_len; // models/mod.rs:65-67
+    if (cf.architecture_id != 1) return fail(Q3_EFORMAT, "Unknown architecture_id: %d", cf.architecture_id);
+    if (cf.hidden_dim <= 0 || cf.group_size <= 0) return fail(Q3_EFORMAT, "Invalid hidden_dim/group_size");
+
+    const int L = cf.n_layers, dim = cf.dim, hdm = cf.head_dim, gs = cf.group_size;
+    const size_t AH = (size_t)cf.n_heads * hdm, KV = (size_t)cf.n_kv_heads * hdm, H = cf.hidden_dim, V = cf.vocab_size;
+#define TAKE_F32(dst, n, what)                                                         \
+    if (!((dst) = (const float *)c.take((size_t)(n) * 4)))                             \
+        return fail(Q3_EFORMAT, "Failed to read %s: Insufficient data", what);
+    TAKE_F32(c.rms_att, (size_t)L * dim, "attention normalization weights");
+    TAKE_F32(c.rms_ffn, (size_t)L * dim, "FFN normalization weights");
+    TAKE_F32(c.rms_final, dim, "final normalization weights");
+    TAKE_F32(c.q_ln, (size_t)L * hdm, "query layer norm weights");
+    TAKE_F32(c.k_ln, (size_t)L * hdm, "key layer norm weights");
+    auto take_qts = [&](std::vector<HostQT> &v, int n, size_t size_each, const char *what) -> int {
+        v.resize(n);
+        for (int i = 0; i < n; i++) { // models/mod.rs:89-108
+            v[i].q = (const int8_t *)c.take(size_each);
+            v[i].s = (const float *)c.take(size_each / gs * 4);
+            if (!v[i].q || !v[i].s)
+                return fail(Q3_EFORMAT, "Failed to read quantized tensor %d data (%s): Insufficient data", i, what);
+        }
+        return 0;
+    };
+    std::vector<HostQT> one;
+    int rc;
+    if ((rc = take_qts(one, 1, V * dim, "token embedding"))) return rc;
+    c.embed = one[0];
+    if ((rc = take_qts(c.wq, L, (size_t)dim * AH, "wq"))) return rc;
+    if ((rc = take_qts(c.wk, L, (size_t)dim * KV, "wk"))) return rc;
+    if ((rc = take_qts(c.wv, L, (size_t)dim * KV, "wv"))) return rc;
+    if ((rc = take_qts(c.wo, L, AH * dim, "wo"))) return rc;
+    if ((rc = take_qts(c.w1, L, (size_t)dim * H, "w1"))) return rc;
+    if ((rc = take_qts(c.w2, L, H * dim, "w2"))) return rc;
+    if ((rc = take_qts(c.w3, L, (size_t)dim * H, "w3"))) return rc;
+    if (cf.shared_classifier) c.wcls = c.embed;
+    else {
+        if ((rc = take_qts(one, 1, (size_t)dim * V, "classifier"))) return rc;
+        c.wcls = one[0];
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// upload helpers
+// ------------------------------------------------------------------------------------------
+struct Stager { // pinned staging buffer for re-laid-out tensors
+    uint8_t *buf = nullptr;
+    size_t cap = 0;
+    ~Stager() {
+        if (buf) cudaFreeHost(buf);
+    }
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        if (buf) cudaFreeHost(buf);
+        buf = nullptr;
+        cap = 0;
+        CK(cudaMallocHost((void **)&buf, n));
+        cap = n;
+        return 0;
+    }
+};
+
+// Allocate a device tensor of `rows` x K and fill it from row pieces: piece i copies
+// rows[i] rows starting at source row src_row0[i] of src[i], columns [col0, col0+K) of a
+// source matrix with srcK columns (col slicing = row-parallel TP shard of Wo / W2).
+struct RowPiece {
+    HostQT src;
+    int src_row0, nrows, srcK;
+};
+static int upload_rows(q3_handle *h, Stager &st, DevQT &dst, const std::vector<RowPiece> &pieces, int K, int col0,
+                       int gs, bool interleave2 = false) {
+    int rows = 0;
+    for (auto &p : pieces) rows += p.nrows;
+    dst.rows = rows;
+    dst.K = K;
+    const int ng = K / gs;
+    size_t qbytes = (size_t)rows * K, sbytes = (size_t)rows * ng * 4;
+    int rc;
+    if ((rc = dmalloc(h, (void **)&dst.q, qbytes))) return rc;
+    if ((rc = dmalloc(h, (void **)&dst.s, sbytes))) return rc;
+    if ((rc = st.ensure(qbytes + sbytes))) return rc;
+    int8_t *hq = (int8_t *)st.buf;
+    float *hs = (float *)(st.buf + qbytes);
+    if (interleave2) { // two pieces of equal size, rows alternate (gate_j, up_j)
+        const RowPiece &a = pieces[0], &b = pieces[1];
+        for (int j = 0; j < a.nrows; j++) {
+            const RowPiece *pp[2] = {&a, &b};
+            for (int t = 0; t < 2; t++) {
+                size_t sr = (size_t)pp[t]->src_row0 + j;
+                memcpy(hq + (size_t)(2 * j + t) * K, pp[t]->src.q + sr * pp[t]->srcK + col0, K);
+                memcpy(hs + (size_t)(2 * j + t) * ng, pp[t]->src.s + sr * (pp[t]->srcK / gs) + col0 / gs, (size_t)ng * 4);
+            }
+        }
+    } else {
+        size_t r = 0;
+        for (auto &p : pieces) {
+            if (p.srcK == K && col0 == 0) {
+                memcpy(hq + r * K, p.src.q + (size_t)p.src_row0 * K, (size_t)p.nrows * K);
+                memcpy(hs + r * ng, p.src.s + (size_t)p.src_row0 * ng, (size_t)p.nrows * ng * 4);
+            } else {
+                for (int j = 0; j < p.nrows; j++) {
+                    size_t sr = (size_t)p.src_row0 + j;
+                    memcpy(hq + (r + j) * K, p.src.q + sr * p.srcK + col0, K);
+                    memcpy(hs + (r + j) * ng, p.src.s + sr * (p.srcK / gs) + col0 / gs, (size_t)ng * 4);
+                }
+            }
+            r += p.nrows;
+        }
+    }
+    CK(cudaMemcpy(dst.q, hq, qbytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dst.s, hs, sbytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+static int upload_f32(q3_handle *h, float **dst, const float *src, size_t n) {
+    int rc;
+    if ((rc = dmalloc(h, (void **)dst, n * 4))) return rc;
+    CK(cudaMemcpy(*dst, src, n * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel launch sequence (qwen3.rs:62-79, 131-176)
+// ------------------------------------------------------------------------------------------
+#define GS_DISPATCH(gs, CALL)                \
+    switch (gs) {                            \
+    case 32: { constexpr int GS = 32; CALL; } break;   \
+    case 64: { constexpr int GS = 64; CALL; } break;   \
+    case 128: { constexpr int GS = 128; CALL; } break; \
+    default: break;                          \
+    }
+
+template <int GS, int EPI>
+static void launch_gemv_t(const q3_handle *h, GemvArgs a, cudaStream_t s) {
+    int npairs = a.rows / 2;
+    int grid = (npairs + 7) / 8;
+    int cap = h->num_sms * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    size_t smem = (size_t)a.K + (size_t)(a.K / GS) * 4;
+    k_gemv<GS, EPI><<<grid, 256, smem, s>>>(a);
+}
+template <int EPI>
+static void launch_gemv(const q3_handle *h, const GemvArgs &a, cudaStream_t s) {
+    GS_DISPATCH(h->cfg.group_size, (launch_gemv_t<GS, EPI>(h, a, s)));
+}
+
+static int launch_norm_quant(const q3_handle *h, const NormQuantArgs &a, cudaStream_t s) {
+    GS_DISPATCH(h->cfg.group_size, (k_rmsnorm_quant<GS><<<1, 1024, 0, s>>>(a)));
+    return 1;
+}
+
+// One transformer block.  Returns the number of kernel launches.
+static int launch_layer(q3_handle *h, int l, bool first_from_embed, cudaStream_t s) {
+    const q3_config &c = h->cfg;
+    const LayerDev &W = h->layers[l];
+    const int gs = c.group_size, dim = c.dim;
+    const int *d_token = h->d_tokpos, *d_pos = h->d_tokpos + 1;
+    float *kc_l = h->kc + (size_t)l * c.seq_len * h->KV_l;
+    float *vc_l = h->vc + (size_t)l * c.seq_len * h->KV_l;
+    int n = 0;
+    // attn_norm + quantize (qwen3.rs:134-136); layer 0 also gathers the embedding row (qwen3.rs:64)
+    NormQuantArgs na{};
+    na.x = h->x; na.w = W.rms_att; na.q = h->xq; na.s = h->xs; na.n = dim;
+    if (first_from_embed) { na.embed_q = h->embed.q; na.embed_s = h->embed.s; na.token = d_token; }
+    n += launch_norm_quant(h, na, s);
+    // q, k, v projections (layers.rs:334-336)
+    GemvArgs g{};
+    g.wq = W.qkv.q; g.ws = W.qkv.s; g.xq = h->xq; g.xs = h->xs; g.K = dim; g.rows = W.qkv.rows;
+    g.q = h->q; g.kc = kc_l; g.vc = vc_l; g.AH = h->AH_l; g.KV = h->KV_l; g.pos = d_pos;
+    launch_gemv<EPI_QKV>(h, g, s); n++;
+    // QK-norm + RoPE (layers.rs:339-340)
+    int nh = h->n_heads_l + h->n_kv_l;
+    k_qknorm_rope<<<(nh + 3) / 4, 128, 0, s>>>(h->q, kc_l, W.q_ln, W.k_ln, h->rope, d_pos, h->n_heads_l, h->n_kv_l, h->KV_l);
+    n++;
+    // attention (layers.rs:343) + quantize (qwen3.rs:152)
+    dim3 ag(h->n_kv_l, ATTN_MAX_SPLITS);
+    switch (h->kv_mul) {
+    case 1: k_attn_partial<1><<<ag, 128, 0, s>>>(h->q, kc_l, vc_l, h->attn_part, d_pos, h->KV_l, h->n_heads_l); break;
+    case 2: k_attn_partial<2><<<ag, 128, 0, s>>>(h->q, kc_l, vc_l, h->attn_part, d_pos, h->KV_l, h->n_heads_l); break;
+    case 4: k_attn_partial<4><<<ag, 128, 0, s>>>(h->q, kc_l, vc_l, h->attn_part, d_pos, h->KV_l, h->n_heads_l); break;
+    case 8: k_attn_partial<8><<<ag, 128, 0, s>>>(h->q, kc_l, vc_l, h->attn_part, d_pos, h->KV_l, h->n_heads_l); break;
+    }
+    n++;
+    GS_DISPATCH(gs, (k_attn_combine_quant<GS><<<h->n_heads_l, 128, 0, s>>>(h->attn_part, d_pos, h->xb, h->xq, h->xs)));
+    n++;
+    // o_proj + residual (qwen3.rs:153-156)
+    GemvArgs o{};
+    o.wq = W.wo.q; o.ws = W.wo.s; o.xq = h->xq; o.xs = h->xs; o.K = h->AH_l; o.rows = dim; o.out = h->x;
+    launch_gemv<EPI_RESID>(h, o, s); n++;
+    // ffn_norm + quantize (qwen3.rs:159-161)
+    NormQuantArgs nf{};
+    nf.x = h->x; nf.w = W.rms_ffn; nf.q = h->xq; nf.s = h->xs; nf.n = dim;
+    n += launch_norm_quant(h, nf, s);
+    // gate/up + SwiGLU (layers.rs:468-475)
+    GemvArgs gu{};
+    gu.wq = W.w13.q; gu.ws = W.w13.s; gu.xq = h->xq; gu.xs = h->xs; gu.K = dim; gu.rows = W.w13.rows; gu.out = h->hb;
+    launch_gemv<EPI_SWIGLU>(h, gu, s); n++;
+    // quantize(hb) (layers.rs:478)
+    {
+        int n4 = h->H_l / 4, grid = (n4 + 255) / 256;
+        GS_DISPATCH(gs, (k_quantize<GS><<<grid, 256, 0, s>>>(h->hb, h->H_l, h->hq, h->hs)));
+        n++;
+    }
+    // down + residual (layers.rs:479, qwen3.rs:175)
+    GemvArgs dn{};
+    dn.wq = W.w2.q; dn.ws = W.w2.s; dn.xq = h->hq; dn.xs = h->hs; dn.K = h->H_l; dn.rows = dim; dn.out = h->x;
+    launch_gemv<EPI_RESID>(h, dn, s); n++;
+    return n;
+}
+
+// final norm (in place) + quantize + lm_head (qwen3.rs:72-76)
+static int launch_head(q3_handle *h, cudaStream_t s) {
+    const q3_config &c = h->cfg;
+    NormQuantArgs na{};
+    na.x = h->x; na.w = h->rms_final; na.q = h->xq; na.s = h->xs; na.n = c.dim; na.write_normed = 1;
+    int n = launch_norm_quant(h, na, s);
+    GemvArgs g{};
+    g.wq = h->wcls.q; g.ws = h->wcls.s; g.xq = h->xq; g.xs = h->xs; g.K = c.dim; g.rows = c.vocab_size; g.out = h->logits;
+    launch_gemv<EPI_STORE>(h, g, s); n++;
+    return n;
+}
+
+static int launch_argmax(q3_handle *h, bool feedback, cudaStream_t s) {
+    int *tp = h->d_tokpos;
+    k_argmax<<<1, 1024, 0, s>>>(h->logits, h->cfg.vocab_size, tp + 2, feedback ? tp : nullptr, feedback ? tp + 1 : nullptr,
+                                feedback ? h->d_history : nullptr, tp + 3);
+    return 1;
+}
+
+static int launch_step(q3_handle *h, bool argmax, bool feedback, cudaStream_t s) {
+    int n = 0;
+    for (int l = 0; l < h->cfg.n_layers; l++) n += launch_layer(h, l, l == 0, s);
+    n += launch_head(h, s);
+    if (argmax) n += launch_argmax(h, feedback, s);
+    return n;
+}
+
+static int build_graphs(q3_handle *h) {
+    for (int which = 0; which < 2; which++) {
+        cudaGraph_t g;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int n = launch_step(h, which == 1, which == 1, h->stream);
+        cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+        if (e != cudaSuccess) return fail(Q3_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        CK(cudaGraphInstantiate(which ? &h->g_greedy : &h->g_fwd, g, 0));
+        CK(cudaGraphDestroy(g));
+        if (which == 1) h->launches_per_step = n;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// construction
+// ------------------------------------------------------------------------------------------
+static int create_impl(const char *path, int ctx_len, int device, int tp_rank, int tp_size, q3_handle **out) {
+    if (!path || !out) return fail(Q3_EINVAL, "null argument");
+    if (tp_size < 1 || tp_rank < 0 || tp_rank >= tp_size) return fail(Q3_EINVAL, "bad tp rank/size %d/%d", tp_rank, tp_size);
+    *out = nullptr;
+    Ckpt ck;
+    int rc = open_ckpt(path, ctx_len, ck);
+    if (rc) return rc;
+    const q3_config &c = ck.cfg;
+    const int gs = c.group_size;
+    if (c.head_dim != HEAD_DIM) return fail(Q3_EUNSUPPORTED, "head_dim %d unsupported (kernels are built for 128)", c.head_dim);
+    if (gs != 32 && gs != 64 && gs != 128) return fail(Q3_EUNSUPPORTED, "group_size %d unsupported (32/64/128)", gs);
+    if (c.n_heads % c.n_kv_heads) return fail(Q3_EUNSUPPORTED, "n_heads %% n_kv_heads != 0");
+    int kv_mul = c.n_heads / c.n_kv_heads;
+    if (kv_mul != 1 && kv_mul != 2 && kv_mul != 4 && kv_mul != 8) return fail(Q3_EUNSUPPORTED, "GQA factor %d unsupported", kv_mul);
+    if (c.dim % 128 || c.hidden_dim % 128) return fail(Q3_EUNSUPPORTED, "dim/hidden_dim must be multiples of 128");
+    if (c.dim > 16384 || c.hidden_dim > 65536) return fail(Q3_EUNSUPPORTED, "dim/hidden_dim too large");
+    if (c.n_kv_heads % tp_size || (c.hidden_dim / tp_size) % gs || c.hidden_dim % tp_size)
+        return fail(Q3_EUNSUPPORTED, "tp_size %d does not divide kv heads / hidden groups", tp_size);
+    if (c.vocab_size % 2) return fail(Q3_EUNSUPPORTED, "odd vocab_size");
+
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(Q3_EINVAL, "device %d out of range (%d visible)", device, ndev);
+    CK(cudaSetDevice(device));
+    q3_handle *h = new q3_handle();
+    h->cfg = c;
+    h->device = device;
+    h->tp_rank = tp_rank;
+    h->tp_size = tp_size;
+    h->kv_mul = kv_mul;
+    h->n_heads_l = c.n_heads / tp_size;
+    h->n_kv_l = c.n_kv_heads / tp_size;
+    h->AH_l = h->n_heads_l * HEAD_DIM;
+    h->KV_l = h->n_kv_l * HEAD_DIM;
+    h->H_l = c.hidden_dim / tp_size;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    h->num_sms = prop.multiProcessorCount;
+
+    auto guard_fail = [&](int code) {
+        q3_destroy(h);
+        return code;
+    };
+#define TRY(x)                         \
+    do {                               \
+        int rc_ = (x);                 \
+        if (rc_) return guard_fail(rc_); \
+    } while (0)
+#define CKH(call)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return guard_fail(fail(Q3_ECUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, \
+                                   __LINE__, cudaGetErrorString(e_)));                                    \
+    } while (0)
+
+    CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const int L = c.n_layers, dim = c.dim, H = c.hidden_dim;
+    const int AH = c.n_heads * HEAD_DIM;
+    Stager st;
+    h->layers.resize(L);
+    const int r = tp_rank;
+    for (int l = 0; l < L; l++) {
+        LayerDev &W = h->layers[l];
+        // column-parallel: this rank's q heads / kv heads (rows of the [out,in] matrices)
+        TRY(upload_rows(h, st, W.qkv,
+                        {{ck.wq[l], r * h->AH_l, h->AH_l, dim}, {ck.wk[l], r * h->KV_l, h->KV_l, dim}, {ck.wv[l], r * h->KV_l, h->KV_l, dim}},
+                        dim, 0, gs));
+        // row-parallel: all rows, this rank's input columns
+        TRY(upload_rows(h, st, W.wo, {{ck.wo[l], 0, dim, AH}}, h->AH_l, r * h->AH_l, gs));
+        TRY(upload_rows(h, st, W.w13, {{ck.w1[l], r * h->H_l, h->H_l, dim}, {ck.w3[l], r * h->H_l, h->H_l, dim}}, dim, 0, gs, true));
+        TRY(upload_rows(h, st, W.w2, {{ck.w2[l], 0, dim, H}}, h->H_l, r * h->H_l, gs));
+        TRY(upload_f32(h, &W.rms_att, ck.rms_att + (size_t)l * dim, dim));
+        TRY(upload_f32(h, &W.rms_ffn, ck.rms_ffn + (size_t)l * dim, dim));
+        TRY(upload_f32(h, &W.q_ln, ck.q_ln + (size_t)l * HEAD_DIM, HEAD_DIM));
+        TRY(upload_f32(h, &W.k_ln, ck.k_ln + (size_t)l * HEAD_DIM, HEAD_DIM));
+    }
+    // embedding table stays int8 and is dequantised per row on the fly (bit-identical to the
+    // reference's load-time dequantize, tensor.rs:72-80: a single multiply per element)
+    TRY(upload_rows(h, st, h->embed, {{ck.embed, 0, c.vocab_size, dim}}, dim, 0, gs));
+    if (c.shared_classifier) h->wcls = h->embed;
+    else TRY(upload_rows(h, st, h->wcls, {{ck.wcls, 0, c.vocab_size, dim}}, dim, 0, gs));
+    TRY(upload_f32(h, &h->rms_final, ck.rms_final, dim));
+
+    // RoPE table on the host with glibc powf/cosf/sinf (layers.rs:161-171), one row per position
+    {
+        size_t n = (size_t)c.seq_len * HEAD_DIM;
+        std::vector<float> tab(n);
+        const int half = HEAD_DIM / 2;
+        std::vector<float> freq(half);
+        for (int i = 0; i < half; i++) freq[i] = powf(1e6f, -((float)i) / (float)half);
+        for (int p = 0; p < c.seq_len; p++)
+            for (int i = 0; i < half; i++) {
+                float ang = (float)p * freq[i];
+                tab[(size_t)p * HEAD_DIM + 2 * i] = cosf(ang);
+                tab[(size_t)p * HEAD_DIM + 2 * i + 1] = sinf(ang);
+            }
+        TRY(upload_f32(h, &h->rope, tab.data(), n));
+    }
+    // buffers (qwen3.rs:420-444)
+    const int maxd = (h->AH_l > dim ? h->AH_l : dim);
+    TRY(dmalloc(h, (void **)&h->x, (size_t)dim * 4));
+    TRY(dmalloc(h, (void **)&h->xb, (size_t)maxd * 4));
+    TRY(dmalloc(h, (void **)&h->q, (size_t)h->AH_l * 4));
+    TRY(dmalloc(h, (void **)&h->hb, (size_t)h->H_l * 4));
+    TRY(dmalloc(h, (void **)&h->logits, (size_t)c.vocab_size * 4));
+    TRY(dmalloc(h, (void **)&h->xq, (size_t)maxd));
+    TRY(dmalloc(h, (void **)&h->xs, (size_t)(maxd / gs + 1) * 4));
+    TRY(dmalloc(h, (void **)&h->hq, (size_t)h->H_l));
+    TRY(dmalloc(h, (void **)&h->hs, (size_t)(h->H_l / gs + 1) * 4));
+    TRY(dmalloc(h, (void **)&h->attn_part, (size_t)h->n_heads_l * ATTN_MAX_SPLITS * ATTN_PART_STRIDE * 4));
+    size_t kvn = (size_t)L * c.seq_len * h->KV_l;
+    TRY(dmalloc(h, (void **)&h->kc, kvn * 4));
+    TRY(dmalloc(h, (void **)&h->vc, kvn * 4));
+    CKH(cudaMemset(h->kc, 0, kvn * 4)); // vec![0.0; ..] (qwen3.rs:439-440)
+    CKH(cudaMemset(h->vc, 0, kvn * 4));
+    h->history_cap = c.seq_len + 8;
+    TRY(dmalloc(h, (void **)&h->d_tokpos, 16 * 4));
+    TRY(dmalloc(h, (void **)&h->d_history, (size_t)h->history_cap * 4));
+    CKH(cudaMemset(h->d_tokpos, 0, 16 * 4));
+    CKH(cudaMemset(h->x, 0, (size_t)dim * 4));
+    CKH(cudaMallocHost((void **)&h->h_logits, (size_t)c.vocab_size * 4));
+    CKH(cudaMallocHost((void **)&h->h_small, 64 * 4));
+    CKH(cudaDeviceSynchronize());
+    TRY(build_graphs(h));
+    *out = h;
+    return Q3_OK;
+}
+
+extern "C" int q3_create(const char *path, int ctx_len, int device, q3_handle **out) {
+    return create_impl(path, ctx_len, device, 0, 1, out);
+}
+extern "C" int q3_create_tp(const char *path, int ctx_len, int device, int tp_rank, int tp_size, q3_handle **out) {
+    if (tp_size != 1) return fail(Q3_EUNSUPPORTED, "tensor parallel path not built yet");
+    return create_impl(path, ctx_len, device, tp_rank, tp_size, out);
+}
+extern "C" size_t q3_tp_blob_size(void) { return 256; }
+extern "C" int q3_tp_export(q3_handle *, void *) { return fail(Q3_EUNSUPPORTED, "tensor parallel path not built yet"); }
+extern "C" int q3_tp_connect(q3_handle *, const void *) { return fail(Q3_EUNSUPPORTED, "tensor parallel path not built yet"); }
+
+extern "C" void q3_destroy(q3_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->g_fwd) cudaGraphExecDestroy(h->g_fwd);
+    if (h->g_greedy) cudaGraphExecDestroy(h->g_greedy);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->h_logits) cudaFreeHost(h->h_logits);
+    if (h->h_small) cudaFreeHost(h->h_small);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const q3_config *q3_get_config(const q3_handle *h) { return h ? &h->cfg : nullptr; }
+extern "C" const float *q3_logits_device(const q3_handle *h) { return h ? h->logits : nullptr; }
+extern "C" int q3_launches_per_step(const q3_handle *h) { return h ? h->launches_per_step : 0; }
+extern "C" int q3_set_decode_path(q3_handle *h, int path) {
+    if (!h) return fail(Q3_EINVAL, "null handle");
+    if (path != 0) return fail(Q3_EUNSUPPORTED, "decode path %d not available", path);
+    h->decode_path = path;
+    return Q3_OK;
+}
+
+static int check_tok_pos(const q3_handle *h, int token, int pos) {
+    if (!h) return fail(Q3_EINVAL, "null handle");
+    if (token < 0 || token >= h->cfg.vocab_size)
+        return fail(Q3_EINVAL, "index out of bounds: token %d >= vocab_size %d", token, h->cfg.vocab_size);
+    if (pos < 0 || pos >= h->cfg.seq_len)
+        return fail(Q3_EINVAL, "index out of bounds: pos %d >= seq_len %d", pos, h->cfg.seq_len);
+    return 0;
+}
+
+static int set_tok_pos(q3_handle *h, int token, int pos) {
+    h->h_small[0] = token;
+    h->h_small[1] = pos;
+    h->h_small[2] = 0;
+    h->h_small[3] = 0;
+    CK(cudaMemcpyAsync(h->d_tokpos, h->h_small, 16, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+extern "C" int q3_forward(q3_handle *h, int token, int pos, float *logits_host) {
+    int rc = check_tok_pos(h, token, pos);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    if ((rc = set_tok_pos(h, token, pos))) return rc;
+    CK(cudaGraphLaunch(h->g_fwd, h->stream));
+    if (logits_host) {
+        CK(cudaMemcpyAsync(h->h_logits, h->logits, (size_t)h->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        memcpy(logits_host, h->h_logits, (size_t)h->cfg.vocab_size * 4);
+    } else {
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return Q3_OK;
+}
+
+extern "C" int q3_forward_argmax(q3_handle *h, int token, int pos, int *next_token) {
+    int rc = check_tok_pos(h, token, pos);
+    if (rc) return rc;
+    if (!next_token) return fail(Q3_EINVAL, "null next_token");
+    CK(cudaSetDevice(h->device));
+    if ((rc = set_tok_pos(h, token, pos))) return rc;
+    CK(cudaGraphLaunch(h->g_greedy, h->stream));
+    CK(cudaMemcpyAsync(h->h_small + 8, h->d_tokpos + 2, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *next_token = h->h_small[8];
+    return Q3_OK;
+}
+
+extern "C" int q3_decode_greedy(q3_handle *h, int first_token, int pos0, int n, int *tokens_out) {
+    int rc = check_tok_pos(h, first_token, pos0);
+    if (rc) return rc;
+    if (n < 0 || pos0 + n > h->cfg.seq_len) return fail(Q3_EINVAL, "pos0 + n = %d exceeds seq_len %d", pos0 + n, h->cfg.seq_len);
+    if (n > h->history_cap) return fail(Q3_EINVAL, "n too large");
+    CK(cudaSetDevice(h->device));
+    if ((rc = set_tok_pos(h, first_token, pos0))) return rc;
+    for (int i = 0; i < n; i++) CK(cudaGraphLaunch(h->g_greedy, h->stream));
+    if (tokens_out && n > 0) {
+        CK(cudaMemcpyAsync(tokens_out, h->d_history, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return Q3_OK;
+}
+
+extern "C" int q3_bench_decode(q3_handle *h, int first_token, int pos0, int steps, float *ms_out) {
+    int rc = check_tok_pos(h, first_token, pos0);
+    if (rc) return rc;
+    if (steps < 1 || pos0 + steps > h->cfg.seq_len) return fail(Q3_EINVAL, "pos0 + steps exceeds seq_len");
+    CK(cudaSetDevice(h->device));
+    if ((rc = set_tok_pos(h, first_token, pos0))) return rc;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(e0, h->stream));
+    for (int i = 0; i < steps; i++) CK(cudaGraphLaunch(h->g_greedy, h->stream));
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_out) *ms_out = ms;
+    return Q3_OK;
+}
+
+extern "C" int q3_prefill(q3_handle *h, const int *tokens, int n, int pos0, float *last_logits_host) {
+    // Sequential on-device decode steps until the batched tcgen05 path lands: same results as n
+    // forwards by construction.
+    if (!h || !tokens || n <= 0) return fail(Q3_EINVAL, "bad prefill arguments");
+    for (int i = 0; i < n; i++) {
+        int rc = q3_forward(h, tokens[i], pos0 + i, i == n - 1 ? last_logits_host : nullptr);
+        if (rc) return rc;
+    }
+    return Q3_OK;
+}
+
+extern "C" int q3_reset(q3_handle *h) {
+    if (!h) return fail(Q3_EINVAL, "null handle");
+    CK(cudaSetDevice(h->device));
+    size_t kvn = (size_t)h->cfg.n_layers * h->cfg.seq_len * h->KV_l;
+    CK(cudaMemsetAsync(h->kc, 0, kvn * 4, h->stream));
+    CK(cudaMemsetAsync(h->vc, 0, kvn * 4, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return Q3_OK;
+}
+
+static int kv_rw(q3_handle *h, int layer, int pos0, int n, float *k, float *v, bool write) {
+    if (!h) return fail(Q3_EINVAL, "null handle");
+    if (layer < 0 || layer >= h->cfg.n_layers || pos0 < 0 || n < 0 || pos0 + n > h->cfg.seq_len)
+        return fail(Q3_EINVAL, "kv range out of bounds");
+    CK(cudaSetDevice(h->device));
+    size_t off = ((size_t)layer * h->cfg.seq_len + pos0) * h->KV_l, bytes = (size_t)n * h->KV_l * 4;
+    cudaMemcpyKind kind = write ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    CK(cudaStreamSynchronize(h->stream));
+    if (k) CK(write ? cudaMemcpy(h->kc + off, k, bytes, kind) : cudaMemcpy(k, h->kc + off, bytes, kind));
+    if (v) CK(write ? cudaMemcpy(h->vc + off, v, bytes, kind) : cudaMemcpy(v, h->vc + off, bytes, kind));
+    return Q3_OK;
+}
+extern "C" int q3_kv_read(q3_handle *h, int layer, int pos0, int n, float *k, float *v) {
+    return kv_rw(h, layer, pos0, n, k, v, false);
+}
+extern "C" int q3_kv_write(q3_handle *h, int layer, int pos0, int n, const float *k, const float *v) {
+    return kv_rw(h, layer, pos0, n, (float *)k, (float *)v, true);
+}
+
+extern "C" int q3_forward_layers(q3_handle *h, int pos, int layer0, int layer1, float *x_host, int run_head,
+                                 float *logits_host) {
+    if (!h || !x_host) return fail(Q3_EINVAL, "null argument");
+    if (pos < 0 || pos >= h->cfg.seq_len) return fail(Q3_EINVAL, "index out of bounds: pos %d", pos);
+    if (layer0 < 0 || layer1 > h->cfg.n_layers || layer0 > layer1) return fail(Q3_EINVAL, "bad layer range");
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = set_tok_pos(h, 0, pos))) return rc;
+    CK(cudaMemcpyAsync(h->x, x_host, (size_t)h->cfg.dim * 4, cudaMemcpyHostToDevice, h->stream));
+    for (int l = layer0; l < layer1; l++) launch_layer(h, l, false, h->stream);
+    CK(cudaMemcpyAsync(x_host, h->x, (size_t)h->cfg.dim * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (run_head) {
+        launch_head(h, h->stream);
+        if (logits_host)
+            CK(cudaMemcpyAsync(logits_host, h->logits, (size_t)h->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return Q3_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// operator-level entry points
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t n) { CK(cudaMalloc(&p, n ? n : 16)); return 0; }
+    template <class T> T *as() { return (T *)p; }
+};
+static int op_prologue(int device, int gs) {
+    CK(cudaSetDevice(device));
+    if (gs != 32 && gs != 64 && gs != 128) return fail(Q3_EUNSUPPORTED, "group_size %d unsupported (32/64/128)", gs);
+    return 0;
+}
+
+extern "C" int q3_op_quantize(int device, const float *x, int n, int gs, int8_t *q_out, float *s_out) {
+    int rc = op_prologue(device, gs);
+    if (rc) return rc;
+    if (n < 0 || n % gs) return fail(Q3_EINVAL, "n must be a multiple of group_size");
+    if (n == 0) return Q3_OK;
+    DevBuf dx, dq, ds;
+    if ((rc = dx.alloc((size_t)n * 4)) || (rc = dq.alloc(n)) || (rc = ds.alloc((size_t)n / gs * 4))) return rc;
+    CK(cudaMemcpy(dx.p, x, (size_t)n * 4, cudaMemcpyHostToDevice));
+    int grid = (n / 4 + 255) / 256;
+    GS_DISPATCH(gs, (k_quantize<GS><<<grid, 256>>>(dx.as<float>(), n, dq.as<int8_t>(), ds.as<float>())));
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(q_out, dq.p, n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(s_out, ds.p, (size_t)n / gs * 4, cudaMemcpyDeviceToHost));
+    return Q3_OK;
+}
+
+extern "C" int q3_op_matmul(int device, const int8_t *xq, const float *xs, const int8_t *wq, const float *ws, int n,
+                            int d, int gs, float *out, int32_t *group_dots_out) {
+    int rc = op_prologue(device, gs);
+    if (rc) return rc;
+    if (n <= 0 || d < 0 || n % gs || n % 16 || d % 2) return fail(Q3_EINVAL, "need n %% gs == 0, n %% 16 == 0, d even");
+    if (d == 0) return Q3_OK;
+    const int ng = n / gs;
+    DevBuf dxq, dxs, dwq, dws, dout, ddots;
+    if ((rc = dxq.alloc(n)) || (rc = dxs.alloc((size_t)ng * 4)) || (rc = dwq.alloc((size_t)d * n)) ||
+        (rc = dws.alloc((size_t)d * ng * 4)) || (rc = dout.alloc((size_t)d * 4)))
+        return rc;
+    if (group_dots_out && (rc = ddots.alloc((size_t)d * ng * 4))) return rc;
+    CK(cudaMemcpy(dxq.p, xq, n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dxs.p, xs, (size_t)ng * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dwq.p, wq, (size_t)d * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dws.p, ws, (size_t)d * ng * 4, cudaMemcpyHostToDevice));
+    GemvArgs a{};
+    a.wq = dwq.as<int8_t>(); a.ws = dws.as<float>(); a.xq = dxq.as<int8_t>(); a.xs = dxs.as<float>();
+    a.K = n; a.rows = d; a.out = dout.as<float>(); a.dots = group_dots_out ? ddots.as<int32_t>() : nullptr;
+    q3_handle fake;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    fake.num_sms = prop.multiProcessorCount;
+    fake.cfg.group_size = gs;
+    launch_gemv<EPI_STORE>(&fake, a, 0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout.p, (size_t)d * 4, cudaMemcpyDeviceToHost));
+    if (group_dots_out) CK(cudaMemcpy(group_dots_out, ddots.p, (size_t)d * ng * 4, cudaMemcpyDeviceToHost));
+    return Q3_OK;
+}
+
+extern "C" int q3_op_rmsnorm(int device, const float *x, const float *w, int n, float *out) {
+    CK(cudaSetDevice(device));
+    if (n <= 0) return fail(Q3_EINVAL, "n must be positive");
+    DevBuf dx, dw, dout;
+    int rc;
+    if ((rc = dx.alloc((size_t)n * 4)) || (rc = dw.alloc((size_t)n * 4)) || (rc = dout.alloc((size_t)n * 4))) return rc;
+    CK(cudaMemcpy(dx.p, x, (size_t)n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dw.p, w, (size_t)n * 4, cudaMemcpyHostToDevice));
+    k_rmsnorm<<<1, 1024>>>(dx.as<float>(), dw.as<float>(), dout.as<float>(), n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return Q3_OK;
+}
+
+extern "C" int q3_op_quantize_q80(int device, const float *w, size_t n, int gs, int8_t *q_out, float *s_out) {
+    int rc = op_prologue(device, gs);
+    if (rc) return rc;
+    if (n % gs) return fail(Q3_EINVAL, "Weight length is not a multiple of group_size");
+    if (n == 0) return Q3_OK;
+    DevBuf dw, dq, ds;
+    if ((rc = dw.alloc(n * 4)) || (rc = dq.alloc(n)) || (rc = ds.alloc(n / gs * 4))) return rc;
+    CK(cudaMemcpy(dw.p, w, n * 4, cudaMemcpyHostToDevice));
+    size_t blocks = (n / 4 + 255) / 256;
+    int grid = (int)(blocks > 148 * 16 ? 148 * 16 : blocks);
+    GS_DISPATCH(gs, (k_quantize_q80<GS><<<grid, 256>>>(dw.as<float>(), n, dq.as<int8_t>(), ds.as<float>())));
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(q_out, dq.p, n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(s_out, ds.p, n / gs * 4, cudaMemcpyDeviceToHost));
+    return Q3_OK;
+}

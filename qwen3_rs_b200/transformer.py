@@ -1,0 +1,266 @@
+"""Host-side mirror of qwen3-inference's model interface over libqwen3cuda's C ABI.
+
+Same names, argument meaning and error behaviour as the reference (models/mod.rs):
+
+    TransformerBuilder::new(path).with_ctx_length(opt).build() -> Transformers   (:40-74)
+    Transformer::forward(token, pos) -> &[f32]                                   (:15)
+    Transformer::get_config() -> &ModelConfig                                    (:17)
+
+The forward pass runs only in the CUDA library: there is NO CPU fallback -- if the library or a
+GPU is missing, construction raises.  numpy arrays returned by forward() are copies of the
+logits (the reference hands out a borrow that generate_next_token copies, generation.rs:159-160).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import build as _build
+
+
+class Q3Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[q3 error {code}] {msg}")
+        self.code = code
+        self.message = msg
+
+
+class _Cfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "architecture_id", "dim", "hidden_dim", "n_layers", "n_heads", "n_kv_heads", "head_dim", "seq_len",
+        "vocab_size", "group_size", "shared_classifier")]
+
+
+@dataclass(frozen=True)
+class ModelConfig:
+    """configuration.rs:18-30."""
+    architecture_id: int
+    dim: int
+    hidden_dim: int
+    n_layers: int
+    n_heads: int
+    n_kv_heads: int
+    head_dim: int
+    seq_len: int
+    vocab_size: int
+    group_size: int
+    shared_classifier: bool
+
+
+_lib = None
+
+# every symbol include/qwen3_cuda.h declares: (restype, argtypes)
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_pp = C.POINTER(C.c_void_p)
+ABI = {
+    "q3_create": (_i, [C.c_char_p, _i, _i, _pp]),
+    "q3_create_tp": (_i, [C.c_char_p, _i, _i, _i, _i, _pp]),
+    "q3_tp_blob_size": (_sz, []),
+    "q3_tp_export": (_i, [_vp, _vp]),
+    "q3_tp_connect": (_i, [_vp, _vp]),
+    "q3_destroy": (None, [_vp]),
+    "q3_get_config": (C.POINTER(_Cfg), [_vp]),
+    "q3_forward": (_i, [_vp, _i, _i, _vp]),
+    "q3_forward_argmax": (_i, [_vp, _i, _i, C.POINTER(_i)]),
+    "q3_decode_greedy": (_i, [_vp, _i, _i, _i, _vp]),
+    "q3_prefill": (_i, [_vp, _vp, _i, _i, _vp]),
+    "q3_reset": (_i, [_vp]),
+    "q3_logits_device": (_vp, [_vp]),
+    "q3_kv_read": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "q3_kv_write": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "q3_forward_layers": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
+    "q3_set_decode_path": (_i, [_vp, _i]),
+    "q3_bench_decode": (_i, [_vp, _i, _i, _i, C.POINTER(_f)]),
+    "q3_launches_per_step": (_i, [_vp]),
+    "q3_op_quantize": (_i, [_i, _vp, _i, _i, _vp, _vp]),
+    "q3_op_matmul": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "q3_op_rmsnorm": (_i, [_i, _vp, _vp, _i, _vp]),
+    "q3_op_quantize_q80": (_i, [_i, _vp, _sz, _i, _vp, _vp]),
+    "q3_last_error": (C.c_char_p, []),
+    "q3_version": (C.c_char_p, []),
+}
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load_library():
+    """dlopen libqwen3cuda.so (building it first if nvcc is present and it is stale)."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB
+        if not os.path.exists(path):
+            path = _build.build()
+        L = C.CDLL(path)
+        for name, (res, args) in ABI.items():
+            fn = getattr(L, name)  # AttributeError == missing export: fail loudly
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise Q3Error(rc, load_library().q3_last_error().decode(errors="replace"))
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Transformer:
+    """Device-resident Qwen3 transformer (the `Transformers::Qwen3` variant, models/mod.rs:20-37)."""
+
+    def __init__(self, handle: int):
+        self._h = handle
+        c = load_library().q3_get_config(handle).contents
+        self._config = ModelConfig(**{n: (bool(getattr(c, n)) if n == "shared_classifier" else int(getattr(c, n)))
+                                      for n, _ in _Cfg._fields_})
+        self._logits = np.empty(self._config.vocab_size, np.float32)
+
+    # -- the reference trait --------------------------------------------------------------
+    def forward(self, token: int, pos: int) -> np.ndarray:
+        """Transformer::forward.  Out-of-range token/pos raises (the reference panics)."""
+        _check(load_library().q3_forward(self._h, int(token), int(pos), _ptr(self._logits)))
+        return self._logits.copy()
+
+    def get_config(self) -> ModelConfig:
+        return self._config
+
+    # -- extensions ----------------------------------------------------------
+    def forward_argmax(self, token: int, pos: int) -> int:
+        out = C.c_int(0)
+        _check(load_library().q3_forward_argmax(self._h, int(token), int(pos), C.byref(out)))
+        return out.value
+
+    def decode_greedy(self, first_token: int, pos0: int, n: int) -> List[int]:
+        out = np.zeros(max(n, 1), np.int32)
+        _check(load_library().q3_decode_greedy(self._h, int(first_token), int(pos0), int(n), _ptr(out)))
+        return out[:n].tolist()
+
+    def prefill(self, tokens: Sequence[int], pos0: int = 0, want_logits: bool = True) -> Optional[np.ndarray]:
+        t = np.ascontiguousarray(tokens, np.int32)
+        _check(load_library().q3_prefill(self._h, _ptr(t), t.size, int(pos0), _ptr(self._logits) if want_logits else None))
+        return self._logits.copy() if want_logits else None
+
+    def reset(self) -> None:
+        _check(load_library().q3_reset(self._h))
+
+    def kv_read(self, layer: int, pos0: int, n: int):
+        kv = self._config.n_kv_heads * self._config.head_dim
+        k = np.empty((n, kv), np.float32)
+        v = np.empty((n, kv), np.float32)
+        _check(load_library().q3_kv_read(self._h, layer, pos0, n, _ptr(k), _ptr(v)))
+        return k, v
+
+    def kv_write(self, layer: int, pos0: int, k: np.ndarray, v: np.ndarray) -> None:
+        k = np.ascontiguousarray(k, np.float32)
+        v = np.ascontiguousarray(v, np.float32)
+        _check(load_library().q3_kv_write(self._h, layer, pos0, k.shape[0], _ptr(k), _ptr(v)))
+
+    def forward_layers(self, x: np.ndarray, pos: int, layer0: int, layer1: int, run_head: bool = False):
+        x = np.array(x, np.float32)
+        lg = np.empty(self._config.vocab_size, np.float32) if run_head else None
+        _check(load_library().q3_forward_layers(self._h, int(pos), layer0, layer1, _ptr(x), int(run_head), _ptr(lg)))
+        return (x, lg) if run_head else x
+
+    def set_decode_path(self, path: int) -> None:
+        _check(load_library().q3_set_decode_path(self._h, path))
+
+    def bench_decode(self, first_token: int, pos0: int, steps: int) -> float:
+        ms = C.c_float(0)
+        _check(load_library().q3_bench_decode(self._h, first_token, pos0, steps, C.byref(ms)))
+        return ms.value
+
+    @property
+    def launches_per_step(self) -> int:
+        return load_library().q3_launches_per_step(self._h)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            load_library().q3_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TransformerBuilder:
+    """models/mod.rs:40-74."""
+
+    def __init__(self, checkpoint_path: str):
+        self.checkpoint_path = checkpoint_path
+        self.ctx_length: Optional[int] = None
+        self.device = 0
+        self.tp_rank, self.tp_size = 0, 1
+
+    @staticmethod
+    def new(checkpoint_path: str) -> "TransformerBuilder":
+        return TransformerBuilder(checkpoint_path)
+
+    def with_ctx_length(self, ctx_length: Optional[int]) -> "TransformerBuilder":
+        self.ctx_length = ctx_length
+        return self
+
+    def with_device(self, device: int) -> "TransformerBuilder":
+        self.device = device
+        return self
+
+    def with_tensor_parallel(self, rank: int, size: int) -> "TransformerBuilder":
+        self.tp_rank, self.tp_size = rank, size
+        return self
+
+    def build(self) -> Transformer:
+        L = load_library()
+        h = C.c_void_p(0)
+        ctx = int(self.ctx_length) if self.ctx_length else 0
+        if self.tp_size == 1:
+            rc = L.q3_create(self.checkpoint_path.encode(), ctx, self.device, C.byref(h))
+        else:
+            rc = L.q3_create_tp(self.checkpoint_path.encode(), ctx, self.device, self.tp_rank, self.tp_size, C.byref(h))
+        _check(rc)
+        return Transformer(h.value)
+
+
+# ---- operator-level entry points (tests) ---------------------------------------------------
+def op_quantize(x: np.ndarray, gs: int, device: int = 0):
+    x = np.ascontiguousarray(x, np.float32)
+    q = np.empty(x.size, np.int8)
+    s = np.empty(x.size // gs, np.float32)
+    _check(load_library().q3_op_quantize(device, _ptr(x), x.size, gs, _ptr(q), _ptr(s)))
+    return q, s
+
+
+def op_matmul(xq, xs, wq, ws, n: int, d: int, gs: int, want_dots: bool = False, device: int = 0):
+    xq = np.ascontiguousarray(xq, np.int8)
+    xs = np.ascontiguousarray(xs, np.float32)
+    wq = np.ascontiguousarray(wq, np.int8)
+    ws = np.ascontiguousarray(ws, np.float32)
+    out = np.empty(d, np.float32)
+    dots = np.empty((d, n // gs), np.int32) if want_dots else None
+    _check(load_library().q3_op_matmul(device, _ptr(xq), _ptr(xs), _ptr(wq), _ptr(ws), n, d, gs, _ptr(out), _ptr(dots)))
+    return (out, dots) if want_dots else out
+
+
+def op_rmsnorm(x, w, device: int = 0):
+    x = np.ascontiguousarray(x, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    out = np.empty_like(x)
+    _check(load_library().q3_op_rmsnorm(device, _ptr(x), _ptr(w), x.size, _ptr(out)))
+    return out
+
+
+def op_quantize_q80(w, gs: int, device: int = 0):
+    w = np.ascontiguousarray(w, np.float32).reshape(-1)
+    q = np.empty(w.size, np.int8)
+    s = np.empty(w.size // gs, np.float32)
+    _check(load_library().q3_op_quantize_q80(device, _ptr(w), w.size, gs, _ptr(q), _ptr(s)))
+    return q, s, None
