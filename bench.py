@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- Qwen3 Q8 batch-1 decode throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+One "step" = `--tokens-per-step` (default 64) greedy decode tokens of the named model, batch 1.
+Workload at N=1: Qwen3-8B architecture, random-init weights exported with group size 64 through
+the repo's exporter (no checkpoints offline), i.e. BASELINE.json configs[3] at one GPU.
+
+  value   : decode tokens/s, whole job, device-timed (CUDA events on the launch stream inside
+            q3_bench_decode, cross-checked by a host clock around barrier+synchronize), token
+            feedback on the device, weights/KV resident in HBM.
+  e2e     : the same tokens/s through the reference-facing call -- Transformer.forward(token, pos)
+            -> host logits (vocab x f32 D2H every token) -> host argmax (sampler.rs semantics).
+  roofline: the dominant kernel (gate/up GEMV) timed alone, algorithmic weight+scale bytes per
+            launch / CUDA-event time, against MEASURED_PEAKS.json's HBM copy bandwidth; plus
+            `token_roofline` for the whole step (bytes per token / time per token).
+  cpu_baseline: the CPU oracle (C restatement of the reference forward, OpenMP over rows/heads
+            like the reference's rayon) on the same .bin and the box's host cores, bounded sample.
+
+Prints exactly one JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# checkpoint (synthetic, exported by the repo's exporter)
+# ---------------------------------------------------------------------------------------------
+def _quantize_q80_torch(t, gs):
+    """export.quantize_q80 evaluated with torch on the GPU (IEEE div + round-half-even, bit-identical
+    on finite inputs); used only to make multi-GB bench checkpoints quickly."""
+    import torch
+
+    g = t.reshape(-1, gs)
+    gmax = g.abs().amax(dim=1)
+    scale = torch.where(gmax > 0, gmax / 127.0, torch.ones_like(gmax))
+    q = torch.round(g / scale[:, None]).clamp_(-127, 127).to(torch.int8)
+    return q.reshape(-1).cpu().numpy(), scale.cpu().numpy(), 0.0
+
+
+def bench_checkpoint(model: str, gs: int, seed: int = 0) -> str:
+    from qwen3_rs_b200 import synth
+
+    shape = synth.SHAPES[model]
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
+    d = os.path.join(base, "q3_bench")
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, f"{model}_gs{gs}_s{seed}.bin")
+    want = synth.checkpoint_bytes(shape, gs)
+    if os.path.exists(path) and os.path.getsize(path) == want:
+        return path
+    t0 = time.time()
+    try:
+        import torch
+
+        cuda = torch.cuda.is_available()
+    except Exception:
+        cuda = False
+    tmp = path + f".tmp{os.getpid()}"
+    if cuda:
+        synth.export_synthetic(shape, tmp, gs, seed=seed, device="cuda", quantizer=_quantize_q80_torch)
+    else:
+        synth.export_synthetic(shape, tmp, gs, seed=seed)
+    os.replace(tmp, path)
+    log(f"[bench] exported {model} gs{gs} -> {path} ({want / 1e9:.2f} GB) in {time.time() - t0:.1f}s")
+    return path
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kind: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get(kind)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (the oracle; the only place bench.py executes oracle/)
+# ---------------------------------------------------------------------------------------------
+def cpu_decode_tok_s(path: str, ctx: int, n_tokens: int, threads: int = 0):
+    from oracle import binding as orc
+
+    if threads:
+        orc.set_threads(threads)
+    cores = orc.max_threads()
+    m = orc.Model(path, ctx)
+    tok = 1
+    tok = orc.argmax(m.forward(tok, 0))  # untimed first touch (page-in of the mmap)
+    t0 = time.perf_counter()
+    for pos in range(1, 1 + n_tokens):
+        tok = orc.argmax(m.forward(tok, pos))
+    dt = time.perf_counter() - t0
+    m.close()
+    return n_tokens / dt, cores, dt
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    path = bench_checkpoint(args.model, args.group_size)
+    # bounded sample: a few tokens per step so the whole run stays within minutes
+    tps = max(1, min(args.tokens_per_step, args.ref_tokens_per_step))
+    from oracle import binding as orc
+
+    cores = orc.max_threads()
+    m = orc.Model(path, args.ctx)
+    tok, pos = 1, 0
+    for _ in range(args.warmup):
+        for _ in range(1):
+            tok = orc.argmax(m.forward(tok, pos))
+            pos += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(tps):
+            tok = orc.argmax(m.forward(tok, pos))
+            pos += 1
+    dt = time.perf_counter() - t0
+    val = args.steps * tps / dt
+    sample = f"{args.steps} steps x {tps} greedy tokens of {args.model} gs{args.group_size} (bounded sample of the {args.tokens_per_step}-token step), {cores} OpenMP threads"
+    out = {
+        "impl": "reference", "metric": "decode_tokens_per_s", "value": val, "unit": "tok/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int8 weights x int8 activations, int32 group dots, f32 accumulate",
+        "data": "synthetic", "config": workload_config(args, 1, "cpu"),
+        "cpu_baseline": {"value": val, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = C restatement of qwen3-rs's CPU forward (oracle/q3_oracle.c); the Rust toolchain is absent so the reference itself cannot be built",
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, n_gpus: int, where: str) -> dict:
+    return {
+        "workload": f"{args.model} Q8_0 group_size {args.group_size}, batch-1 greedy decode, {args.tokens_per_step} tokens/step, ctx {args.ctx}",
+        "model_shape": args.model, "group_size": args.group_size, "ctx": args.ctx, "tokens_per_step": args.tokens_per_step,
+        "parallelism": ("tp%d" % n_gpus) if n_gpus > 1 else "single",
+        "l2": "weights streamed per token (>= 0.6 GB) exceed the 126 MB L2; no explicit flush",
+        "weights": "random-init, seeded, exported by qwen3_rs_b200.export (reference .bin format)",
+        "where": where,
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# main arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="qwen3-8b")
+    ap.add_argument("--group-size", type=int, default=64)
+    ap.add_argument("--ctx", type=int, default=2048)
+    ap.add_argument("--tokens-per-step", type=int, default=64)
+    ap.add_argument("--ref-tokens-per-step", type=int, default=2)
+    ap.add_argument("--cpu-sample-tokens", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decode-path", type=int, default=-1)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    need = (args.steps + args.warmup) * args.tokens_per_step + 8
+    if args.ctx < need:
+        args.ctx = need
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from qwen3_rs_b200 import synth, transformer as T
+    from qwen3_rs_b200.sampler import argmax_last
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the forward path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    shape = synth.SHAPES[args.model]
+    if rank == 0:
+        path = bench_checkpoint(args.model, args.group_size)
+    barrier()
+    path = bench_checkpoint(args.model, args.group_size)
+
+    b = T.TransformerBuilder.new(path).with_ctx_length(args.ctx).with_device(local_rank)
+    tp = world
+    if tp > 1:
+        b = b.with_tensor_parallel(rank, tp)
+    m = b.build()
+    if tp > 1:
+        T.tp_connect(m, dist)
+    if args.decode_path >= 0:
+        m.set_decode_path(args.decode_path)
+    tps = args.tokens_per_step
+
+    # ---- device-timed: value ----
+    tok0 = 1
+    pos = 0
+    for _ in range(args.warmup):
+        m.bench_decode(tok0, pos, tps)
+        pos += tps
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    pos_start = pos
+    for _ in range(args.steps):
+        dev_ms += m.bench_decode(tok0, pos, tps)
+        pos += tps
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clk = clocks.stop()
+    times = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = times.tolist()
+    n_tok = args.steps * tps
+    value = n_tok / (dev_ms / 1e3)
+
+    # ---- end to end through the reference-facing call: forward -> host logits -> host argmax ----
+    m.reset()
+    tok, p = tok0, 0
+    for _ in range(8):
+        tok = argmax_last(m.forward(tok, p))
+        p += 1
+    e2e_tokens = min(n_tok, 256)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_tokens):
+        tok = argmax_last(m.forward(tok, p))
+        p += 1
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = e2e_tokens / e2e_t.item()
+
+    if rank != 0:
+        m.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel, timed alone ----
+    peak, peak_src = measured_peak_gbs()
+    roof = None
+    kernels = {}
+    try:
+        for kind in ("gate_up", "down", "qkv", "o_proj", "lm_head"):
+            ms, nbytes, n = m.bench_kernel(kind, 0, reps=3 if kind != "lm_head" else 1)
+            kernels[kind] = {"us": ms * 1e3, "GBps": nbytes / ms / 1e6, "bytes": nbytes}
+        g = kernels["gate_up"]
+        roof = {"bound": "hbm", "kernel": "gate/up int8 GEMV + SwiGLU (%s)" % ("mega" if False else "k_gemv<EPI_SWIGLU>"),
+                "achieved": g["GBps"], "peak": peak, "unit": "GB/s", "frac": g["GBps"] / peak,
+                "traffic": ncu_traffic("gate_up"), "bytes_per_launch": g["bytes"], "us_per_launch": g["us"],
+                "peak_source": peak_src}
+    except Exception as e:  # noqa: BLE001
+        log(f"[bench] kernel roofline failed: {e}")
+    mean_pos = pos_start + (n_tok - 1) / 2.0
+    btok = shape.bytes_per_token(args.group_size, int(mean_pos)) / tp
+    tok_ms = dev_ms / n_tok
+    token_roof = {"bytes_per_token_per_gpu": btok, "achieved": btok / tok_ms / 1e6, "peak": peak, "unit": "GB/s",
+                  "frac": btok / tok_ms / 1e6 / peak, "frac_of_8TBps": btok / tok_ms / 1e6 / 8000.0,
+                  "us_per_token": tok_ms * 1e3, "mean_pos": mean_pos}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            v, cores, dt = cpu_decode_tok_s(path, args.ctx, args.cpu_sample_tokens)
+            cpu = {"value": v, "unit": "tok/s", "cores": cores, "kind": "port",
+                   "sample": f"{args.cpu_sample_tokens} greedy tokens of the same {args.model} gs{args.group_size} .bin after 1 untimed token ({dt:.1f}s), all host threads"}
+        except Exception as e:  # noqa: BLE001
+            log(f"[bench] cpu baseline failed: {e}")
+
+    vocab = m.get_config().vocab_size
+    out = {
+        "metric": "decode_tokens_per_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "dtype": "int8 weights x int8 activations, int32 group dots, f32 accumulate", "data": "synthetic",
+        "config": workload_config(args, world, "cuda"),
+        "wall_ms_per_step": wall_ms / args.steps,
+        "e2e": {"value": e2e_val, "unit": "tok/s", "h2d_bytes_per_step": 16 * tps, "d2h_bytes_per_step": vocab * 4 * tps,
+                "tokens_timed": e2e_tokens, "path": "Transformer.forward -> host logits -> host argmax (sampler.rs)"},
+        "gpu_launches": m.launches_per_step * n_tok,
+        "launches_per_token": m.launches_per_step,
+        "clocks": clk, "roofline": roof, "token_roofline": token_roof, "kernels": kernels, "cpu_baseline": cpu,
+    }
+    print(json.dumps(out), flush=True)
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

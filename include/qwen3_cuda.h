@@ -117,10 +117,24 @@ int q3_forward_layers(q3_handle *h, int pos, int layer0, int layer1, float *x_ho
  * single-launch decode kernel.  Default: the fastest available. */
 int q3_set_decode_path(q3_handle *h, int path);
 
+/* Reference-order mode.  on != 0: every float reduction on the path (RMSNorm sum of squares,
+ * QK-norm, GEMV group fold, attention scores / softmax denominator / value mix) is evaluated in
+ * the reference's left-fold order and exp() is glibc's expf algorithm, so -- unlike the default
+ * fast mode, which differs in summation order only -- logits are bit-identical to the
+ * reference's.  Same kernels otherwise; slower (serial sums).  Used to demonstrate exact parity. */
+int q3_set_exact(q3_handle *h, int on);
+
 /* Timing helper for benchmarks: runs `steps` decode steps at positions pos0.. (greedy token
  * feedback on the device) with inputs already resident, timed with CUDA events on the launch
  * stream; returns total milliseconds. */
 int q3_bench_decode(q3_handle *h, int first_token, int pos0, int steps, float *ms_out);
+/* Roofline helper: times ONE kernel family in isolation with CUDA events on the launch stream.
+ * kind: 0 qkv GEMV, 1 o_proj GEMV, 2 gate/up GEMV (+SwiGLU), 3 down GEMV, 4 lm_head GEMV,
+ * 5 decode attention at position `pos`.  Each rep launches the kernel once per layer (distinct
+ * weights every launch, so the working set is far larger than L2).  Outputs: total milliseconds,
+ * number of launches, algorithmic bytes per launch (weights + scales, or K/V rows read). */
+int q3_bench_kernel(q3_handle *h, int kind, int pos, int reps, float *ms_out, int *launches_out,
+                    double *bytes_per_launch_out);
 /* Number of kernel launches one decode step issues on the current path. */
 int q3_launches_per_step(const q3_handle *h);
 
@@ -130,9 +144,12 @@ int q3_launches_per_step(const q3_handle *h);
 int q3_op_quantize(int device, const float *x, int n, int gs, int8_t *q_out, float *s_out);
 /* tensor.rs:23-62 matmul: out[d] from x (int8[n] + f32[n/gs]) and row-major w (int8[d*n] +
  * f32[d*n/gs]).  group_dots_out (optional, int32[d*(n/gs)]) receives the per-group integer
- * dot products the kernel accumulated. */
+ * dot products the kernel accumulated.  exact != 0: reference-order group fold (bit-identical
+ * f32 result), see q3_set_exact. */
 int q3_op_matmul(int device, const int8_t *xq, const float *xs, const int8_t *wq, const float *ws,
-                 int n, int d, int gs, float *out, int32_t *group_dots_out);
+                 int n, int d, int gs, int exact, float *out, int32_t *group_dots_out);
+/* glibc expf restated on the device (exact mode's exp); x, out: n f32. */
+int q3_op_expf(int device, const float *x, int n, float *out);
 /* layers.rs:109-119 RMSNorm::forward */
 int q3_op_rmsnorm(int device, const float *x, const float *w, int n, float *out);
 /* qwen3-export model_exporter.rs:104-161 quantize_q80 on the device. */

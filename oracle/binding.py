@@ -58,6 +58,7 @@ def lib():
             "orc_rope_freqs": (None, [vp, i32, i32]),
             "orc_rope_apply": (None, [vp, vp, i32]),
             "orc_softmax": (None, [vp, i32]),
+            "orc_expf_array": (None, [vp, vp, sz]),
             "orc_argmax": (i32, [vp, i32]),
             "orc_sampler_new": (vp, [i32, f32, f32, u64]),
             "orc_sampler_free": (None, [vp]),
@@ -73,6 +74,7 @@ def lib():
             "orc_model_file_bytes": (sz, [vp]),
             "orc_model_forward": (C.POINTER(C.c_float), [vp, i32, i32]),
             "orc_model_reset": (None, [vp]),
+            "orc_model_forward_layers": (C.POINTER(C.c_float), [vp, i32, i32, i32, vp, i32]),
             "orc_model_key_cache": (C.POINTER(C.c_float), [vp]),
             "orc_model_value_cache": (C.POINTER(C.c_float), [vp]),
             "orc_model_set_trace": (None, [vp, i32, C.POINTER(OrcTrace)]),
@@ -161,6 +163,13 @@ def softmax(x):
     return x
 
 
+def expf(x):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(x)
+    lib().orc_expf_array(_p(out), _p(x), x.size)
+    return out
+
+
 def argmax(logits) -> int:
     a = np.ascontiguousarray(logits, np.float32)
     return lib().orc_argmax(_p(a), a.size)
@@ -232,6 +241,13 @@ class Model:
 
     def reset(self):
         lib().orc_model_reset(self._h)
+
+    def forward_layers(self, x, pos: int, l0: int, l1: int, run_head: bool = False):
+        x = np.array(x, np.float32)
+        p = lib().orc_model_forward_layers(self._h, pos, l0, l1, _p(x), int(run_head))
+        if run_head:
+            return x, np.ctypeslib.as_array(p, shape=(self.config["vocab_size"],)).copy()
+        return x
 
     def kv_cache(self):
         c = self.config

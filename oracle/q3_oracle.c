@@ -207,6 +207,11 @@ ORC_API void orc_rope_apply(float *v, const float *cos_sin, int head_dim) {
     }
 }
 
+/* The platform expf (what Rust's f32::exp resolves to), exposed for testing the device restatement. */
+ORC_API void orc_expf_array(float *out, const float *x, size_t n) {
+    for (size_t i = 0; i < n; i++) out[i] = expf(x[i]);
+}
+
 /* layers.rs:495-506 softmax(): max fold from -inf, exp(x-max), left-fold sum, multiply by 1/sum. */
 ORC_API void orc_softmax(float *x, int n) {
     float m = -INFINITY;
@@ -695,6 +700,22 @@ ORC_API const float *orc_model_forward(OrcModel *m, int token, int pos) {
     orc_rmsnorm(m->x, m->x, m->rms_final, dim);                                   /* :72 */
     orc_quantize(m->xq_q, m->xq_s, m->x, dim, cf->group_size);                    /* :75 */
     orc_matmul(m->logits, m->xq_q, m->xq_s, m->wcls.q, m->wcls.s, dim, cf->vocab_size, cf->group_size); /* :76 */
+    return m->logits;
+}
+
+/* Layers [l0, l1) of one decode step on a caller-supplied residual stream (in place); with
+ * run_head also final norm + lm_head.  Test helper mirroring q3_forward_layers: lets a test
+ * compare one layer at a time with identical inputs (no error cascade). */
+ORC_API const float *orc_model_forward_layers(OrcModel *m, int pos, int l0, int l1, float *x_io, int run_head) {
+    const OrcConfig *cf = &m->cfg;
+    int dim = cf->dim;
+    memcpy(m->x, x_io, (size_t)dim * 4);
+    for (int l = l0; l < l1; l++) block_forward(m, l, pos);
+    memcpy(x_io, m->x, (size_t)dim * 4);
+    if (!run_head) return NULL;
+    orc_rmsnorm(m->x, m->x, m->rms_final, dim);
+    orc_quantize(m->xq_q, m->xq_s, m->x, dim, cf->group_size);
+    orc_matmul(m->logits, m->xq_q, m->xq_s, m->wcls.q, m->wcls.s, dim, cf->vocab_size, cf->group_size);
     return m->logits;
 }
 

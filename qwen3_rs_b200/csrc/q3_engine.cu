@@ -83,7 +83,9 @@ struct q3_handle {
     float *h_logits = nullptr; // pinned
     int *h_small = nullptr;    // pinned scratch
     cudaStream_t stream = nullptr;
-    cudaGraphExec_t g_fwd = nullptr, g_greedy = nullptr;
+    cudaGraphExec_t g_fwd[2] = {nullptr, nullptr}, g_greedy[2] = {nullptr, nullptr}; // [exact]
+    int exact = 0;          // 1: reference-order reductions + glibc expf (bit-level parity mode)
+    float *att = nullptr;   // exact mode scratch [n_heads_l][seq_len] (the reference's `att`)
     int decode_path = 0;
     int launches_per_step = 0;
     size_t dev_bytes = 0;
@@ -286,7 +288,12 @@ static void launch_gemv_t(const q3_handle *h, GemvArgs a, cudaStream_t s) {
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     size_t smem = (size_t)a.K + (size_t)(a.K / GS) * 4;
-    k_gemv<GS, EPI><<<grid, 256, smem, s>>>(a);
+    if (h->exact) {
+        smem += (size_t)16 * (a.K / GS) * 4; // [8 warps][2 rows][ng] terms
+        k_gemv<GS, EPI, true><<<grid, 256, smem, s>>>(a);
+    } else {
+        k_gemv<GS, EPI, false><<<grid, 256, smem, s>>>(a);
+    }
 }
 template <int EPI>
 static void launch_gemv(const q3_handle *h, const GemvArgs &a, cudaStream_t s) {
@@ -294,7 +301,11 @@ static void launch_gemv(const q3_handle *h, const GemvArgs &a, cudaStream_t s) {
 }
 
 static int launch_norm_quant(const q3_handle *h, const NormQuantArgs &a, cudaStream_t s) {
-    GS_DISPATCH(h->cfg.group_size, (k_rmsnorm_quant<GS><<<1, 1024, 0, s>>>(a)));
+    if (h->exact) {
+        GS_DISPATCH(h->cfg.group_size, (k_rmsnorm_quant<GS, true><<<1, 1024, (size_t)a.n * 4, s>>>(a)));
+    } else {
+        GS_DISPATCH(h->cfg.group_size, (k_rmsnorm_quant<GS, false><<<1, 1024, 0, s>>>(a)));
+    }
     return 1;
 }
 
@@ -319,10 +330,19 @@ static int launch_layer(q3_handle *h, int l, bool first_from_embed, cudaStream_t
     launch_gemv<EPI_QKV>(h, g, s); n++;
     // QK-norm + RoPE (layers.rs:339-340)
     int nh = h->n_heads_l + h->n_kv_l;
-    k_qknorm_rope<<<(nh + 3) / 4, 128, 0, s>>>(h->q, kc_l, W.q_ln, W.k_ln, h->rope, d_pos, h->n_heads_l, h->n_kv_l, h->KV_l);
+    if (h->exact)
+        k_qknorm_rope<true><<<(nh + 3) / 4, 128, 0, s>>>(h->q, kc_l, W.q_ln, W.k_ln, h->rope, d_pos, h->n_heads_l, h->n_kv_l, h->KV_l);
+    else
+        k_qknorm_rope<false><<<(nh + 3) / 4, 128, 0, s>>>(h->q, kc_l, W.q_ln, W.k_ln, h->rope, d_pos, h->n_heads_l, h->n_kv_l, h->KV_l);
     n++;
     // attention (layers.rs:343) + quantize (qwen3.rs:152)
     dim3 ag(h->n_kv_l, ATTN_MAX_SPLITS);
+    if (h->exact) {
+        k_attn_ordered<<<h->n_heads_l, 128, 0, s>>>(h->q, kc_l, vc_l, h->att, h->xb, d_pos, h->KV_l, h->kv_mul, c.seq_len);
+        int n4 = h->AH_l / 4, grid = (n4 + 255) / 256;
+        GS_DISPATCH(gs, (k_quantize<GS><<<grid, 256, 0, s>>>(h->xb, h->AH_l, h->xq, h->xs)));
+        n += 2;
+    } else {
     switch (h->kv_mul) {
     case 1: k_attn_partial<1><<<ag, 128, 0, s>>>(h->q, kc_l, vc_l, h->attn_part, d_pos, h->KV_l, h->n_heads_l); break;
     case 2: k_attn_partial<2><<<ag, 128, 0, s>>>(h->q, kc_l, vc_l, h->attn_part, d_pos, h->KV_l, h->n_heads_l); break;
@@ -332,6 +352,7 @@ static int launch_layer(q3_handle *h, int l, bool first_from_embed, cudaStream_t
     n++;
     GS_DISPATCH(gs, (k_attn_combine_quant<GS><<<h->n_heads_l, 128, 0, s>>>(h->attn_part, d_pos, h->xb, h->xq, h->xs)));
     n++;
+    }
     // o_proj + residual (qwen3.rs:153-156)
     GemvArgs o{};
     o.wq = W.wo.q; o.ws = W.wo.s; o.xq = h->xq; o.xs = h->xs; o.K = h->AH_l; o.rows = dim; o.out = h->x;
@@ -385,16 +406,44 @@ static int launch_step(q3_handle *h, bool argmax, bool feedback, cudaStream_t s)
 }
 
 static int build_graphs(q3_handle *h) {
+    const int ex = h->exact;
     for (int which = 0; which < 2; which++) {
+        cudaGraphExec_t *slot = which ? &h->g_greedy[ex] : &h->g_fwd[ex];
         cudaGraph_t g;
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         int n = launch_step(h, which == 1, which == 1, h->stream);
         cudaError_t e = cudaStreamEndCapture(h->stream, &g);
         if (e != cudaSuccess) return fail(Q3_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
-        CK(cudaGraphInstantiate(which ? &h->g_greedy : &h->g_fwd, g, 0));
+        if (!*slot) CK(cudaGraphInstantiate(slot, g, 0));
         CK(cudaGraphDestroy(g));
         if (which == 1) h->launches_per_step = n;
     }
+    return 0;
+}
+
+template <class K>
+static int allow_smem(K kernel, int bytes) {
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return 0;
+}
+static int prepare_exact_kernels() {
+    int rc;
+    if ((rc = allow_smem(k_rmsnorm_quant<32, true>, 65536))) return rc;
+    if ((rc = allow_smem(k_rmsnorm_quant<64, true>, 65536))) return rc;
+    if ((rc = allow_smem(k_rmsnorm_quant<128, true>, 65536))) return rc;
+#define ALLOW_GEMV(GS)                                                      \
+    if ((rc = allow_smem(k_gemv<GS, EPI_STORE, true>, 131072))) return rc;  \
+    if ((rc = allow_smem(k_gemv<GS, EPI_QKV, true>, 131072))) return rc;    \
+    if ((rc = allow_smem(k_gemv<GS, EPI_RESID, true>, 131072))) return rc;  \
+    if ((rc = allow_smem(k_gemv<GS, EPI_SWIGLU, true>, 131072))) return rc; \
+    if ((rc = allow_smem(k_gemv<GS, EPI_STORE, false>, 98304))) return rc;  \
+    if ((rc = allow_smem(k_gemv<GS, EPI_QKV, false>, 98304))) return rc;    \
+    if ((rc = allow_smem(k_gemv<GS, EPI_RESID, false>, 98304))) return rc;  \
+    if ((rc = allow_smem(k_gemv<GS, EPI_SWIGLU, false>, 98304))) return rc;
+    ALLOW_GEMV(32)
+    ALLOW_GEMV(64)
+    ALLOW_GEMV(128)
+#undef ALLOW_GEMV
     return 0;
 }
 
@@ -512,6 +561,8 @@ static int create_impl(const char *path, int ctx_len, int device, int tp_rank, i
     TRY(dmalloc(h, (void **)&h->hq, (size_t)h->H_l));
     TRY(dmalloc(h, (void **)&h->hs, (size_t)(h->H_l / gs + 1) * 4));
     TRY(dmalloc(h, (void **)&h->attn_part, (size_t)h->n_heads_l * ATTN_MAX_SPLITS * ATTN_PART_STRIDE * 4));
+    TRY(dmalloc(h, (void **)&h->att, (size_t)h->n_heads_l * c.seq_len * 4));
+    TRY(prepare_exact_kernels());
     size_t kvn = (size_t)L * c.seq_len * h->KV_l;
     TRY(dmalloc(h, (void **)&h->kc, kvn * 4));
     TRY(dmalloc(h, (void **)&h->vc, kvn * 4));
@@ -545,8 +596,10 @@ extern "C" void q3_destroy(q3_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->g_fwd) cudaGraphExecDestroy(h->g_fwd);
-    if (h->g_greedy) cudaGraphExecDestroy(h->g_greedy);
+    for (int e = 0; e < 2; e++) {
+        if (h->g_fwd[e]) cudaGraphExecDestroy(h->g_fwd[e]);
+        if (h->g_greedy[e]) cudaGraphExecDestroy(h->g_greedy[e]);
+    }
     for (void *p : h->allocs) cudaFree(p);
     if (h->h_logits) cudaFreeHost(h->h_logits);
     if (h->h_small) cudaFreeHost(h->h_small);
@@ -561,6 +614,15 @@ extern "C" int q3_set_decode_path(q3_handle *h, int path) {
     if (!h) return fail(Q3_EINVAL, "null handle");
     if (path != 0) return fail(Q3_EUNSUPPORTED, "decode path %d not available", path);
     h->decode_path = path;
+    return Q3_OK;
+}
+
+extern "C" int q3_set_exact(q3_handle *h, int on) {
+    if (!h) return fail(Q3_EINVAL, "null handle");
+    CK(cudaSetDevice(h->device));
+    h->exact = on ? 1 : 0;
+    if (h->exact && h->cfg.dim > 16384) return fail(Q3_EUNSUPPORTED, "exact mode needs dim <= 16384");
+    if (!h->g_fwd[h->exact]) return build_graphs(h);
     return Q3_OK;
 }
 
@@ -587,7 +649,7 @@ extern "C" int q3_forward(q3_handle *h, int token, int pos, float *logits_host) 
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
     if ((rc = set_tok_pos(h, token, pos))) return rc;
-    CK(cudaGraphLaunch(h->g_fwd, h->stream));
+    CK(cudaGraphLaunch(h->g_fwd[h->exact], h->stream));
     if (logits_host) {
         CK(cudaMemcpyAsync(h->h_logits, h->logits, (size_t)h->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -604,7 +666,7 @@ extern "C" int q3_forward_argmax(q3_handle *h, int token, int pos, int *next_tok
     if (!next_token) return fail(Q3_EINVAL, "null next_token");
     CK(cudaSetDevice(h->device));
     if ((rc = set_tok_pos(h, token, pos))) return rc;
-    CK(cudaGraphLaunch(h->g_greedy, h->stream));
+    CK(cudaGraphLaunch(h->g_greedy[h->exact], h->stream));
     CK(cudaMemcpyAsync(h->h_small + 8, h->d_tokpos + 2, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     *next_token = h->h_small[8];
@@ -618,7 +680,7 @@ extern "C" int q3_decode_greedy(q3_handle *h, int first_token, int pos0, int n, 
     if (n > h->history_cap) return fail(Q3_EINVAL, "n too large");
     CK(cudaSetDevice(h->device));
     if ((rc = set_tok_pos(h, first_token, pos0))) return rc;
-    for (int i = 0; i < n; i++) CK(cudaGraphLaunch(h->g_greedy, h->stream));
+    for (int i = 0; i < n; i++) CK(cudaGraphLaunch(h->g_greedy[h->exact], h->stream));
     if (tokens_out && n > 0) {
         CK(cudaMemcpyAsync(tokens_out, h->d_history, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
     }
@@ -637,7 +699,7 @@ extern "C" int q3_bench_decode(q3_handle *h, int first_token, int pos0, int step
     CK(cudaEventCreate(&e1));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaEventRecord(e0, h->stream));
-    for (int i = 0; i < steps; i++) CK(cudaGraphLaunch(h->g_greedy, h->stream));
+    for (int i = 0; i < steps; i++) CK(cudaGraphLaunch(h->g_greedy[h->exact], h->stream));
     CK(cudaEventRecord(e1, h->stream));
     CK(cudaEventSynchronize(e1));
     float ms = 0;
@@ -645,6 +707,85 @@ extern "C" int q3_bench_decode(q3_handle *h, int first_token, int pos0, int step
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (ms_out) *ms_out = ms;
+    return Q3_OK;
+}
+
+extern "C" int q3_bench_kernel(q3_handle *h, int kind, int pos, int reps, float *ms_out, int *launches_out,
+                               double *bytes_out) {
+    if (!h || kind < 0 || kind > 5 || reps < 1) return fail(Q3_EINVAL, "bad bench arguments");
+    if (pos < 0 || pos >= h->cfg.seq_len) return fail(Q3_EINVAL, "index out of bounds: pos %d", pos);
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = set_tok_pos(h, 0, pos))) return rc;
+    const q3_config &c = h->cfg;
+    const int gs = c.group_size, dim = c.dim, L = c.n_layers;
+    auto one = [&](int l) {
+        const LayerDev &W = h->layers[l];
+        float *kc_l = h->kc + (size_t)l * c.seq_len * h->KV_l;
+        float *vc_l = h->vc + (size_t)l * c.seq_len * h->KV_l;
+        GemvArgs g{};
+        g.xq = h->xq; g.xs = h->xs; g.pos = h->d_tokpos + 1;
+        switch (kind) {
+        case 0:
+            g.wq = W.qkv.q; g.ws = W.qkv.s; g.K = dim; g.rows = W.qkv.rows; g.q = h->q; g.kc = kc_l; g.vc = vc_l;
+            g.AH = h->AH_l; g.KV = h->KV_l;
+            launch_gemv<EPI_QKV>(h, g, h->stream);
+            break;
+        case 1:
+            g.wq = W.wo.q; g.ws = W.wo.s; g.K = h->AH_l; g.rows = dim; g.out = h->xb;
+            launch_gemv<EPI_STORE>(h, g, h->stream);
+            break;
+        case 2:
+            g.wq = W.w13.q; g.ws = W.w13.s; g.K = dim; g.rows = W.w13.rows; g.out = h->hb;
+            launch_gemv<EPI_SWIGLU>(h, g, h->stream);
+            break;
+        case 3:
+            g.wq = W.w2.q; g.ws = W.w2.s; g.xq = h->hq; g.xs = h->hs; g.K = h->H_l; g.rows = dim; g.out = h->xb;
+            launch_gemv<EPI_STORE>(h, g, h->stream);
+            break;
+        case 4:
+            g.wq = h->wcls.q; g.ws = h->wcls.s; g.K = dim; g.rows = c.vocab_size; g.out = h->logits;
+            launch_gemv<EPI_STORE>(h, g, h->stream);
+            break;
+        case 5: {
+            dim3 ag(h->n_kv_l, ATTN_MAX_SPLITS);
+            switch (h->kv_mul) {
+            case 1: k_attn_partial<1><<<ag, 128, 0, h->stream>>>(h->q, kc_l, vc_l, h->attn_part, h->d_tokpos + 1, h->KV_l, h->n_heads_l); break;
+            case 2: k_attn_partial<2><<<ag, 128, 0, h->stream>>>(h->q, kc_l, vc_l, h->attn_part, h->d_tokpos + 1, h->KV_l, h->n_heads_l); break;
+            case 4: k_attn_partial<4><<<ag, 128, 0, h->stream>>>(h->q, kc_l, vc_l, h->attn_part, h->d_tokpos + 1, h->KV_l, h->n_heads_l); break;
+            case 8: k_attn_partial<8><<<ag, 128, 0, h->stream>>>(h->q, kc_l, vc_l, h->attn_part, h->d_tokpos + 1, h->KV_l, h->n_heads_l); break;
+            }
+        } break;
+        }
+    };
+    double bytes = 0;
+    const double sc = 1.0 + 4.0 / gs;
+    switch (kind) {
+    case 0: bytes = (double)h->layers[0].qkv.rows * dim * sc; break;
+    case 1: bytes = (double)dim * h->AH_l * sc; break;
+    case 2: bytes = (double)h->layers[0].w13.rows * dim * sc; break;
+    case 3: bytes = (double)dim * h->H_l * sc; break;
+    case 4: bytes = (double)c.vocab_size * dim * sc; break;
+    case 5: bytes = 2.0 * (pos + 1) * h->KV_l * 4; break;
+    }
+    for (int l = 0; l < L; l++) one(l); // warm-up pass
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(e0, h->stream));
+    for (int r = 0; r < reps; r++)
+        for (int l = 0; l < L; l++) one(l);
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_out) *ms_out = ms;
+    if (launches_out) *launches_out = reps * L;
+    if (bytes_out) *bytes_out = bytes;
     return Q3_OK;
 }
 
@@ -742,8 +883,25 @@ extern "C" int q3_op_quantize(int device, const float *x, int n, int gs, int8_t 
     return Q3_OK;
 }
 
+__global__ void k_expf_ref(const float *x, float *out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = expf_ref(x[i]);
+}
+extern "C" int q3_op_expf(int device, const float *x, int n, float *out) {
+    CK(cudaSetDevice(device));
+    if (n <= 0) return Q3_OK;
+    DevBuf dx, dout;
+    int rc;
+    if ((rc = dx.alloc((size_t)n * 4)) || (rc = dout.alloc((size_t)n * 4))) return rc;
+    CK(cudaMemcpy(dx.p, x, (size_t)n * 4, cudaMemcpyHostToDevice));
+    k_expf_ref<<<(n + 255) / 256, 256>>>(dx.as<float>(), dout.as<float>(), n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return Q3_OK;
+}
+
 extern "C" int q3_op_matmul(int device, const int8_t *xq, const float *xs, const int8_t *wq, const float *ws, int n,
-                            int d, int gs, float *out, int32_t *group_dots_out) {
+                            int d, int gs, int exact, float *out, int32_t *group_dots_out) {
     int rc = op_prologue(device, gs);
     if (rc) return rc;
     if (n <= 0 || d < 0 || n % gs || n % 16 || d % 2) return fail(Q3_EINVAL, "need n %% gs == 0, n %% 16 == 0, d even");
@@ -766,6 +924,8 @@ extern "C" int q3_op_matmul(int device, const int8_t *xq, const float *xs, const
     cudaGetDeviceProperties(&prop, device);
     fake.num_sms = prop.multiProcessorCount;
     fake.cfg.group_size = gs;
+    fake.exact = exact ? 1 : 0;
+    if ((rc = prepare_exact_kernels())) return rc;
     launch_gemv<EPI_STORE>(&fake, a, 0);
     CK(cudaGetLastError());
     CK(cudaMemcpy(out, dout.p, (size_t)d * 4, cudaMemcpyDeviceToHost));

@@ -64,6 +64,59 @@ __device__ __forceinline__ int total_key(float f) {
     return b ^ (int)(((unsigned)(b >> 31)) >> 1);
 }
 
+// ------------------------------------------------------------------------------------------
+// Reference-order ("exact") mode.  The reference's floats come from glibc's libm; its expf
+// (sysdeps/ieee754/flt-32/e_expf.c, glibc 2.27+; the algorithm of ARM optimized-routines) is
+// a double-precision table + cubic evaluated in a fixed order, restated here so that
+// exp() inside softmax / SwiGLU yields the same f32 bits on the device.  Table entries are
+// 2^(i/32) as correctly rounded doubles minus (i << 47) (checked with 80-digit arithmetic).
+// ------------------------------------------------------------------------------------------
+__device__ __constant__ unsigned long long EXP2F_TAB[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+
+__device__ __forceinline__ float expf_ref(float x) {
+    const unsigned abstop = (__float_as_uint(x) >> 20) & 0x7ff;
+    if (abstop >= 0x42b) { // |x| >= 88 or nan
+        if (__float_as_uint(x) == 0xff800000u) return 0.0f;
+        if (abstop >= 0x7f8) return x + x;
+        if (x > 0x1.62e42ep6f) return INFINITY;
+        if (x < -0x1.9fe368p6f) return 0.0f;
+    }
+    // x86-64 glibc dispatches to its FMA build (__expf_fma, compiled with -mfma and GCC's default
+    // -ffp-contract=fast) on every AVX2 host, so the products below are fused into the following
+    // add exactly as that build does: kd = fma(InvLn2N, x, SHIFT), r = fma(InvLn2N, x, -kd), and
+    // the three polynomial steps.  (Checked against glibc 2.39 on 4M+ inputs incl. hard cases.)
+    const double xd = (double)x;
+    const double InvLn2N = 0x1.71547652b82fep+0 * 32.0;
+    const double SHIFT = 0x1.8p+52;
+    double kd = __fma_rn(InvLn2N, xd, SHIFT);
+    const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+    kd = __dsub_rn(kd, SHIFT);
+    const double r = __fma_rn(InvLn2N, xd, -kd);
+    unsigned long long t = EXP2F_TAB[ki & 31];
+    t += ki << (52 - 5);
+    const double sc = __longlong_as_double((long long)t);
+    const double C0 = 0x1.c6af84b912394p-5 / 32.0 / 32.0 / 32.0, C1 = 0x1.ebfce50fac4f3p-3 / 32.0 / 32.0,
+                 C2 = 0x1.62e42ff0c52d6p-1 / 32.0;
+    const double zz = __fma_rn(C0, r, C1);
+    const double r2 = __dmul_rn(r, r);
+    double y = __fma_rn(C2, r, 1.0);
+    y = __fma_rn(zz, r2, y);
+    y = __dmul_rn(y, sc);
+    return (float)y;
+}
+template <bool ORDERED>
+__device__ __forceinline__ float exp_sel(float x) {
+    return ORDERED ? expf_ref(x) : expf(x);
+}
+
 // Quantise 4 consecutive values held by each of GS/4 adjacent lanes (one group = GS/4 lanes).
 // tensor.rs:91-119: wmax = fold(0, max|x|), scale = wmax/127, q = round(x/scale).
 template <int GS>
@@ -96,8 +149,11 @@ struct NormQuantArgs {
     int write_normed;      // 1: x <- normed value (final norm is in place, qwen3.rs:72)
 };
 
-template <int GS>
+// ORDERED: the sum of squares is the reference's left fold (one thread, element order), so the
+// normalisation factor -- and with it every int8 activation -- is bit-identical to the reference.
+template <int GS, bool ORDERED = false>
 __global__ void __launch_bounds__(1024) k_rmsnorm_quant(NormQuantArgs a) {
+    extern __shared__ __align__(16) float s_x[]; // ORDERED only: n floats
     __shared__ float red[32];
     __shared__ float s_f;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -119,19 +175,29 @@ __global__ void __launch_bounds__(1024) k_rmsnorm_quant(NormQuantArgs a) {
             } else {
                 v[k] = reinterpret_cast<const float4 *>(a.x)[i4];
             }
+            if (ORDERED) reinterpret_cast<float4 *>(s_x)[i4] = v[k];
             ss += __fmul_rn(v[k].x, v[k].x);
             ss += __fmul_rn(v[k].y, v[k].y);
             ss += __fmul_rn(v[k].z, v[k].z);
             ss += __fmul_rn(v[k].w, v[k].w);
         }
     }
-    ss = warp_sum(ss);
-    if (lane == 0) red[warp] = ss;
-    __syncthreads();
-    if (warp == 0) {
-        float t = red[lane];
-        t = warp_sum(t);
-        if (lane == 0) s_f = __fdiv_rn(1.0f, sqrtf(__fadd_rn(__fdiv_rn(t, (float)a.n), NORM_EPS)));
+    if (ORDERED) {
+        __syncthreads();
+        if (tid == 0) { // layers.rs:113: input.iter().map(|x| x*x).sum::<f32>()
+            float t = 0.0f;
+            for (int i = 0; i < a.n; i++) t = __fadd_rn(t, __fmul_rn(s_x[i], s_x[i]));
+            s_f = __fdiv_rn(1.0f, sqrtf(__fadd_rn(__fdiv_rn(t, (float)a.n), NORM_EPS)));
+        }
+    } else {
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp] = ss;
+        __syncthreads();
+        if (warp == 0) {
+            float t = red[lane];
+            t = warp_sum(t);
+            if (lane == 0) s_f = __fdiv_rn(1.0f, sqrtf(__fadd_rn(__fdiv_rn(t, (float)a.n), NORM_EPS)));
+        }
     }
     __syncthreads();
     const float f = s_f;
@@ -224,11 +290,15 @@ struct GemvArgs {
     int32_t *dots;     // optional [rows][K/GS] per-group integer dots (tests)
 };
 
-template <int GS, int EPI>
+// ORDERED: the per-group f32 terms are parked in shared memory and folded left to right by one
+// lane per row (tensor.rs:41-61 `.map(..).sum()`), making the row result bit-identical to the
+// reference; exp() in the SwiGLU epilogue uses the glibc restatement.
+template <int GS, int EPI, bool ORDERED = false>
 __global__ void __launch_bounds__(256) k_gemv(GemvArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     int4 *sx = reinterpret_cast<int4 *>(smem);
     float *sxs = reinterpret_cast<float *>(smem + a.K);
+    float *sterms = sxs + (a.K / GS) + (threadIdx.x >> 5) * 2 * (a.K / GS); // ORDERED: [warp][2][ng]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nchunk = a.K >> 4; // 16-byte chunks per row
     const int ng = a.K / GS;
@@ -275,8 +345,15 @@ __global__ void __launch_bounds__(256) k_gemv(GemvArgs a) {
                         int g = c / LPG;
                         float xsg = sxs[g];
                         // (dot as f32 * weight_scale) * input_scale   (tensor.rs:59)
-                        acc0 = __fadd_rn(acc0, __fmul_rn(__fmul_rn((float)d0, __ldg(s0 + g)), xsg));
-                        acc1 = __fadd_rn(acc1, __fmul_rn(__fmul_rn((float)d1, __ldg(s1 + g)), xsg));
+                        float t0 = __fmul_rn(__fmul_rn((float)d0, __ldg(s0 + g)), xsg);
+                        float t1 = __fmul_rn(__fmul_rn((float)d1, __ldg(s1 + g)), xsg);
+                        if (ORDERED) {
+                            sterms[g] = t0;
+                            sterms[ng + g] = t1;
+                        } else {
+                            acc0 = __fadd_rn(acc0, t0);
+                            acc1 = __fadd_rn(acc1, t1);
+                        }
                         if (a.dots) {
                             a.dots[r0 * ng + g] = d0;
                             a.dots[(r0 + 1) * ng + g] = d1;
@@ -285,8 +362,18 @@ __global__ void __launch_bounds__(256) k_gemv(GemvArgs a) {
                 }
             }
         }
-        acc0 = warp_sum(acc0);
-        acc1 = warp_sum(acc1);
+        if (ORDERED) {
+            __syncwarp();
+            float t = 0.0f;
+            if (lane < 2)
+                for (int g = 0; g < ng; g++) t = __fadd_rn(t, sterms[lane * ng + g]);
+            acc0 = __shfl_sync(0xffffffffu, t, 0);
+            acc1 = __shfl_sync(0xffffffffu, t, 1);
+            __syncwarp();
+        } else {
+            acc0 = warp_sum(acc0);
+            acc1 = warp_sum(acc1);
+        }
         if (lane == 0) {
             if (EPI == EPI_STORE) {
                 a.out[r0] = acc0;
@@ -296,7 +383,7 @@ __global__ void __launch_bounds__(256) k_gemv(GemvArgs a) {
                 a.out[r0 + 1] = __fadd_rn(a.out[r0 + 1], acc1);
             } else if (EPI == EPI_SWIGLU) { // layers.rs:472-475: g * (1/(1+exp(-g))) * up
                 float g = acc0;
-                float sw = __fmul_rn(g, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-g))));
+                float sw = __fmul_rn(g, __fdiv_rn(1.0f, __fadd_rn(1.0f, exp_sel<ORDERED>(-g))));
                 a.out[p] = __fmul_rn(sw, acc1);
             } else { // EPI_QKV, layers.rs:334-336: K and V go straight into the cache row of `pos`
                 const int pos = *a.pos;
@@ -319,9 +406,11 @@ __global__ void __launch_bounds__(256) k_gemv(GemvArgs a) {
 //   (layers.rs:161-171 evaluated with glibc, bit-identical to the reference's libm calls).
 // One warp per head; lane holds 4 consecutive dims; the pair partner lives in lane^16.
 // ------------------------------------------------------------------------------------------
+template <bool ORDERED = false>
 __global__ void __launch_bounds__(128) k_qknorm_rope(float *q, float *kc_layer, const float *q_ln,
                                                      const float *k_ln, const float *rope, const int *pos_p,
                                                      int n_heads, int n_kv, int KV) {
+    __shared__ float s_head[4][HEAD_DIM];
     const int lane = threadIdx.x & 31;
     const int head = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (head >= n_heads + n_kv) return;
@@ -334,7 +423,17 @@ __global__ void __launch_bounds__(128) k_qknorm_rope(float *q, float *kc_layer, 
     ss = __fadd_rn(ss, __fmul_rn(v.y, v.y));
     ss = __fadd_rn(ss, __fmul_rn(v.z, v.z));
     ss = __fadd_rn(ss, __fmul_rn(v.w, v.w));
-    ss = warp_sum(ss);
+    if (ORDERED) { // left fold over the 128 dims in index order (layers.rs:113)
+        float *sh = s_head[threadIdx.x >> 5];
+        reinterpret_cast<float4 *>(sh)[lane] = v;
+        __syncwarp();
+        float t = 0.0f;
+        if (lane == 0)
+            for (int i = 0; i < HEAD_DIM; i++) t = __fadd_rn(t, __fmul_rn(sh[i], sh[i]));
+        ss = __shfl_sync(0xffffffffu, t, 0);
+    } else {
+        ss = warp_sum(ss);
+    }
     const float f = __fdiv_rn(1.0f, sqrtf(__fadd_rn(__fdiv_rn(ss, (float)HEAD_DIM), NORM_EPS)));
     float4 wv = reinterpret_cast<const float4 *>(w)[lane];
     float4 y;
@@ -501,6 +600,54 @@ __global__ void __launch_bounds__(128) k_attn_combine_quant(const float *__restr
     float scale = __fdiv_rn(__int_as_float(gmax[d / G]), 127.0f);
     q[head * HEAD_DIM + d] = (int8_t)quant_one(y, scale);
     if (d % G == 0) s[(head * HEAD_DIM + d) / G] = scale;
+}
+
+// Reference-order attention (exact mode): one CTA per query head, every reduction in the
+// reference's order -- scores are left folds over the 128 dims (layers.rs:395-400), the softmax
+// denominator a left fold over positions (layers.rs:497-503), the value mix a left fold over
+// positions per output dim with separate multiply and add (layers.rs:408-417).  att: scratch
+// [n_heads][seq_len] like the reference's `att` buffer.
+__global__ void __launch_bounds__(128) k_attn_ordered(const float *__restrict__ q, const float *__restrict__ kc,
+                                                      const float *__restrict__ vc, float *att, float *xb,
+                                                      const int *pos_p, int KV, int kv_mul, int seq_len) {
+    __shared__ float s_q[HEAD_DIM];
+    __shared__ float red[4];
+    __shared__ float s_bcast;
+    const int head = blockIdx.x, tid = threadIdx.x;
+    const int pos = *pos_p, n = pos + 1;
+    const int kvh = head / kv_mul;
+    float *a = att + (size_t)head * seq_len;
+    s_q[tid] = q[(size_t)head * HEAD_DIM + tid];
+    __syncthreads();
+    const float scale = __fdiv_rn(1.0f, sqrtf((float)HEAD_DIM));
+    float mx = -INFINITY;
+    for (int t = tid; t < n; t += 128) {
+        const float *k = kc + (size_t)t * KV + (size_t)kvh * HEAD_DIM;
+        float sdot = 0.0f;
+        for (int i = 0; i < HEAD_DIM; i++) sdot = __fadd_rn(sdot, __fmul_rn(s_q[i], k[i]));
+        sdot = __fmul_rn(sdot, scale);
+        a[t] = sdot;
+        mx = fmaxf(mx, sdot);
+    }
+    mx = warp_max(mx);
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    for (int t = tid; t < n; t += 128) a[t] = expf_ref(__fsub_rn(a[t], mx));
+    __syncthreads();
+    if (tid == 0) {
+        float sum = 0.0f;
+        for (int t = 0; t < n; t++) sum = __fadd_rn(sum, a[t]);
+        s_bcast = __fdiv_rn(1.0f, sum);
+    }
+    __syncthreads();
+    const float inv = s_bcast;
+    for (int t = tid; t < n; t += 128) a[t] = __fmul_rn(a[t], inv);
+    __syncthreads();
+    float o = 0.0f;
+    const float *v = vc + (size_t)kvh * HEAD_DIM + tid;
+    for (int t = 0; t < n; t++) o = __fadd_rn(o, __fmul_rn(a[t], v[(size_t)t * KV]));
+    xb[(size_t)head * HEAD_DIM + tid] = o;
 }
 
 // ------------------------------------------------------------------------------------------

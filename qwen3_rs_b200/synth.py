@@ -171,7 +171,8 @@ def export_synthetic(shape: Shape, output_path: str, group_size: int = 64, seed:
             return None
         tshape, kind = specs[name]
         t = make_tensor(name, tshape, kind, seed, device=device)
-        return t if quantizer is not None and device != "cpu" else t.cpu().numpy()
+        # quantised tensors may stay on the device for a device-side quantizer; norms are written as f32
+        return t if (quantizer is not None and device != "cpu" and kind != "norm") else t.cpu().numpy()
 
     info = export_from_loader(load, shape.export_config(), output_path, group_size,
                               shared_classifier=shape.tied, quantizer=quantizer or quantize_q80)

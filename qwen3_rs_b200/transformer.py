@@ -74,10 +74,13 @@ ABI = {
     "q3_kv_write": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "q3_forward_layers": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "q3_set_decode_path": (_i, [_vp, _i]),
+    "q3_set_exact": (_i, [_vp, _i]),
     "q3_bench_decode": (_i, [_vp, _i, _i, _i, C.POINTER(_f)]),
+    "q3_bench_kernel": (_i, [_vp, _i, _i, _i, C.POINTER(_f), C.POINTER(_i), C.POINTER(C.c_double)]),
     "q3_launches_per_step": (_i, [_vp]),
     "q3_op_quantize": (_i, [_i, _vp, _i, _i, _vp, _vp]),
-    "q3_op_matmul": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "q3_op_matmul": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "q3_op_expf": (_i, [_i, _vp, _i, _vp]),
     "q3_op_rmsnorm": (_i, [_i, _vp, _vp, _i, _vp]),
     "q3_op_quantize_q80": (_i, [_i, _vp, _sz, _i, _vp, _vp]),
     "q3_last_error": (C.c_char_p, []),
@@ -169,6 +172,10 @@ class Transformer:
         _check(load_library().q3_forward_layers(self._h, int(pos), layer0, layer1, _ptr(x), int(run_head), _ptr(lg)))
         return (x, lg) if run_head else x
 
+    def set_exact(self, on: bool) -> None:
+        """Reference-order reductions + glibc expf: logits bit-identical to the reference (slow)."""
+        _check(load_library().q3_set_exact(self._h, int(on)))
+
     def set_decode_path(self, path: int) -> None:
         _check(load_library().q3_set_decode_path(self._h, path))
 
@@ -176,6 +183,14 @@ class Transformer:
         ms = C.c_float(0)
         _check(load_library().q3_bench_decode(self._h, first_token, pos0, steps, C.byref(ms)))
         return ms.value
+
+    KERNEL_KINDS = {"qkv": 0, "o_proj": 1, "gate_up": 2, "down": 3, "lm_head": 4, "attention": 5}
+
+    def bench_kernel(self, kind: str, pos: int = 0, reps: int = 4):
+        """-> (avg ms per launch, algorithmic bytes per launch, launches)."""
+        ms, n, b = C.c_float(0), C.c_int(0), C.c_double(0)
+        _check(load_library().q3_bench_kernel(self._h, self.KERNEL_KINDS[kind], pos, reps, C.byref(ms), C.byref(n), C.byref(b)))
+        return ms.value / max(n.value, 1), b.value, n.value
 
     @property
     def launches_per_step(self) -> int:
@@ -239,14 +254,21 @@ def op_quantize(x: np.ndarray, gs: int, device: int = 0):
     return q, s
 
 
-def op_matmul(xq, xs, wq, ws, n: int, d: int, gs: int, want_dots: bool = False, device: int = 0):
+def op_expf(x, device: int = 0):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(x)
+    _check(load_library().q3_op_expf(device, _ptr(x), x.size, _ptr(out)))
+    return out
+
+
+def op_matmul(xq, xs, wq, ws, n: int, d: int, gs: int, want_dots: bool = False, exact: bool = False, device: int = 0):
     xq = np.ascontiguousarray(xq, np.int8)
     xs = np.ascontiguousarray(xs, np.float32)
     wq = np.ascontiguousarray(wq, np.int8)
     ws = np.ascontiguousarray(ws, np.float32)
     out = np.empty(d, np.float32)
     dots = np.empty((d, n // gs), np.int32) if want_dots else None
-    _check(load_library().q3_op_matmul(device, _ptr(xq), _ptr(xs), _ptr(wq), _ptr(ws), n, d, gs, _ptr(out), _ptr(dots)))
+    _check(load_library().q3_op_matmul(device, _ptr(xq), _ptr(xs), _ptr(wq), _ptr(ws), n, d, gs, int(exact), _ptr(out), _ptr(dots)))
     return (out, dots) if want_dots else out
 
 
