@@ -6,6 +6,7 @@
 // TransformerBlockBuffers::new (qwen3.rs:412-445), then Qwen3Transformer::forward (qwen3.rs:62-79).
 #include "../../include/qwen3_cuda.h"
 #include "q3_kernels.cuh"
+#include "q3_mega.cuh"
 
 #include <cuda_runtime.h>
 #include <fcntl.h>
@@ -86,8 +87,20 @@ struct q3_handle {
     cudaGraphExec_t g_fwd[2] = {nullptr, nullptr}, g_greedy[2] = {nullptr, nullptr}; // [exact]
     int exact = 0;          // 1: reference-order reductions + glibc expf (bit-level parity mode)
     float *att = nullptr;   // exact mode scratch [n_heads_l][seq_len] (the reference's `att`)
-    int decode_path = 0;
-    int launches_per_step = 0;
+    int decode_path = 0;    // 0 = multi-kernel CUDA graph, 1 = persistent megakernel
+    int launches_per_step = 0, graph_launches_per_step = 0;
+    // megakernel state
+    bool mega_ok = false;
+    std::string mega_why;
+    MegaArgs margs{};
+    unsigned long long bar_base = 0;
+    unsigned int xepoch = 0;
+    int *h_status = nullptr;  // mapped pinned: kernel-side abort flag
+    float *x2 = nullptr, *kraw = nullptr, *part_buf[2] = {nullptr, nullptr};
+    unsigned long long *d_best = nullptr, *d_bar = nullptr;
+    unsigned int *d_flags = nullptr;
+    size_t mega_smem = 0;
+    void *mega_fn = nullptr;
     size_t dev_bytes = 0;
     std::vector<void *> allocs;
 };
@@ -448,6 +461,154 @@ static int prepare_exact_kernels() {
 }
 
 // ------------------------------------------------------------------------------------------
+// megakernel: stream layout + launch
+// ------------------------------------------------------------------------------------------
+static int pick_n_kt(int K, int gs) {
+    for (int n = (K + MEGA_MAX_KT - 1) / MEGA_MAX_KT; n <= 64; n++)
+        if (K % (n * gs) == 0 && ((K / n) / gs) % 4 == 0 && K / n <= MEGA_MAX_KT) return n;
+    return 0;
+}
+
+template <int GS>
+static void *mega_kernel_for(int kvmul) {
+    switch (kvmul) {
+    case 1: return (void *)k_mega_decode<GS, 1>;
+    case 2: return (void *)k_mega_decode<GS, 2>;
+    case 4: return (void *)k_mega_decode<GS, 4>;
+    case 8: return (void *)k_mega_decode<GS, 8>;
+    }
+    return nullptr;
+}
+
+static int build_stream(q3_handle *h, MegaGemv &g, const std::vector<const DevQT *> &src, int units, int K, bool pair) {
+    const int gs = h->cfg.group_size;
+    g.units = units;
+    g.K = K;
+    g.n_kt = pick_n_kt(K, gs);
+    if (!g.n_kt) return fail(Q3_EUNSUPPORTED, "no K tiling for K=%d gs=%d", K, gs);
+    g.KT = K / g.n_kt;
+    g.G = g.KT / gs;
+    g.tile_bytes = g.KT + 4 * g.G;
+    const size_t rows = (size_t)units * (pair ? 2 : 1);
+    g.layer_stride = (long long)(rows * g.n_kt * g.tile_bytes);
+    uint8_t *buf = nullptr;
+    int rc;
+    if ((rc = dmalloc(h, (void **)&buf, (size_t)g.layer_stride * src.size()))) return rc;
+    g.base = buf;
+    for (size_t l = 0; l < src.size(); l++) {
+        dim3 grid(units, g.n_kt);
+        GS_DISPATCH(gs, (k_build_stream<GS><<<grid, 256, 0, h->stream>>>(src[l]->q, src[l]->s, buf + l * g.layer_stride, units, K,
+                                                                        g.n_kt, h->num_sms, pair ? 1 : 0)));
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_ffn_all, const float *q_ln_all, const float *k_ln_all) {
+    const q3_config &c = h->cfg;
+    const int gs = c.group_size, L = c.n_layers, dim = c.dim;
+    h->mega_ok = false;
+    if (dim > MEGA_MAX_KT) { h->mega_why = "dim > 4096 (QKV/gate-up/lm_head phases need a single K tile)"; return 0; }
+    if ((dim / gs) % 4) { h->mega_why = "dim/group_size not a multiple of 4"; return 0; }
+    if (!pick_n_kt(h->AH_l, gs) || !pick_n_kt(h->H_l, gs)) { h->mega_why = "no K tiling for o_proj/down"; return 0; }
+    if (h->AH_l > 16384 || h->H_l > 16384 || dim > 16384) { h->mega_why = "activation vector > 16384"; return 0; }
+    if (c.vocab_size % h->tp_size) { h->mega_why = "vocab not divisible by tp"; return 0; }
+    MegaArgs &a = h->margs;
+    a = MegaArgs{};
+    a.dim = dim; a.n_layers = L; a.n_heads_l = h->n_heads_l; a.n_kv_l = h->n_kv_l; a.AH_l = h->AH_l; a.KV_l = h->KV_l;
+    a.H_l = h->H_l; a.seq_len = c.seq_len; a.tp_rank = h->tp_rank; a.tp_size = h->tp_size;
+    a.vocab_l = c.vocab_size / h->tp_size;
+    a.vocab_row0 = a.vocab_l * h->tp_rank;
+    int rc;
+    std::vector<const DevQT *> v;
+    for (auto &W : h->layers) v.push_back(&W.qkv);
+    if ((rc = build_stream(h, a.g[PH_QKV], v, h->layers[0].qkv.rows, dim, false))) return rc;
+    v.clear();
+    for (auto &W : h->layers) v.push_back(&W.wo);
+    if ((rc = build_stream(h, a.g[PH_O], v, dim, h->AH_l, false))) return rc;
+    v.clear();
+    for (auto &W : h->layers) v.push_back(&W.w13);
+    if ((rc = build_stream(h, a.g[PH_GU], v, h->H_l, dim, true))) return rc;
+    v.clear();
+    for (auto &W : h->layers) v.push_back(&W.w2);
+    if ((rc = build_stream(h, a.g[PH_DN], v, dim, h->H_l, false))) return rc;
+    DevQT head_slice = h->wcls; // this rank's vocab rows
+    head_slice.q = h->wcls.q + (size_t)a.vocab_row0 * dim;
+    head_slice.s = h->wcls.s + (size_t)a.vocab_row0 * (dim / gs);
+    v.assign(1, &head_slice);
+    if ((rc = build_stream(h, a.g[PH_HEAD], v, a.vocab_l, dim, false))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    float *p;
+    if ((rc = upload_f32(h, &p, rms_att_all, (size_t)L * dim))) return rc; a.rms_att = p;
+    if ((rc = upload_f32(h, &p, rms_ffn_all, (size_t)L * dim))) return rc; a.rms_ffn = p;
+    if ((rc = upload_f32(h, &p, q_ln_all, (size_t)L * HEAD_DIM))) return rc; a.q_ln = p;
+    if ((rc = upload_f32(h, &p, k_ln_all, (size_t)L * HEAD_DIM))) return rc; a.k_ln = p;
+    a.rms_final = h->rms_final;
+    a.embed_q = h->embed.q; a.embed_s = h->embed.s; a.rope = h->rope; a.kc = h->kc; a.vc = h->vc;
+    if ((rc = dmalloc(h, (void **)&h->x2, (size_t)dim * 4))) return rc;
+    if ((rc = dmalloc(h, (void **)&h->kraw, (size_t)h->KV_l * 4))) return rc;
+    for (int i = 0; i < 2; i++) {
+        if ((rc = dmalloc(h, (void **)&h->part_buf[i], (size_t)h->tp_size * dim * 4))) return rc;
+        CK(cudaMemset(h->part_buf[i], 0, (size_t)h->tp_size * dim * 4));
+    }
+    if ((rc = dmalloc(h, (void **)&h->d_best, (size_t)h->tp_size * h->num_sms * 8))) return rc;
+    if ((rc = dmalloc(h, (void **)&h->d_bar, 64))) return rc;
+    if ((rc = dmalloc(h, (void **)&h->d_flags, 64 * 4))) return rc;
+    CK(cudaMemset(h->d_bar, 0, 64));
+    CK(cudaMemset(h->d_flags, 0, 64 * 4));
+    CK(cudaHostAlloc((void **)&h->h_status, 64, cudaHostAllocMapped));
+    *h->h_status = 0;
+    int *d_status = nullptr;
+    CK(cudaHostGetDevicePointer((void **)&d_status, h->h_status, 0));
+    a.x[0] = h->x; a.x[1] = h->x2;
+    a.q = h->q; a.kraw = h->kraw; a.hb = h->hb; a.attn_part = h->attn_part;
+    a.bar = h->d_bar; a.status = d_status; a.tokpos = h->d_tokpos; a.history = h->d_history;
+    // until q3_tp_connect every "peer" slot points at this rank's own buffers
+    for (int r = 0; r < MEGA_MAX_TP; r++) {
+        a.part[0][r] = h->part_buf[0]; a.part[1][r] = h->part_buf[1];
+        a.logits[r] = h->logits; a.best[r] = h->d_best; a.flags[r] = h->d_flags;
+    }
+    GS_DISPATCH(gs, (h->mega_fn = mega_kernel_for<GS>(h->kv_mul)));
+    if (!h->mega_fn) { h->mega_why = "no kernel for this GQA factor"; return 0; }
+    const size_t slot = (size_t)MEGA_NCW * (MEGA_MAX_KT + 4 * (MEGA_MAX_KT / gs));
+    h->mega_smem = MEGA_NSTAGE * slot + MEGA_SCRATCH + 256;
+    CK(cudaFuncSetAttribute(h->mega_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mega_smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->mega_fn, MEGA_THREADS, h->mega_smem));
+    if (occ < 1) { h->mega_why = "megakernel does not fit on an SM"; return 0; }
+    h->mega_ok = true;
+    return 0;
+}
+
+// one cooperative launch: layers [l0, l1) (+ head).  All ranks of a TP group must issue the same sequence.
+static int launch_mega(q3_handle *h, int l0, int l1, bool from_embed, bool run_head, bool feedback, bool gather) {
+    MegaArgs a = h->margs;
+    a.layer0 = l0; a.layer1 = l1; a.from_embed = from_embed; a.run_head = run_head; a.feedback = feedback;
+    a.gather_logits = gather && h->tp_size > 1;
+    a.bar_base = h->bar_base;
+    a.xepoch_base = h->xepoch;
+    const int nbar = 5 * (l1 - l0) + (run_head ? 1 : 0);
+    const int nx = 2 * (l1 - l0) + (run_head ? 1 : 0);
+    void *params[] = {&a};
+    CK(cudaLaunchCooperativeKernel(h->mega_fn, dim3(h->num_sms), dim3(MEGA_THREADS), params, h->mega_smem, h->stream));
+    h->bar_base += (unsigned long long)nbar * h->num_sms;
+    h->xepoch += nx;
+    return 0;
+}
+
+static int mega_check(q3_handle *h) {
+    if (h->h_status && *h->h_status) {
+        int code = *h->h_status;
+        *h->h_status = 0;
+        h->bar_base = 0;
+        cudaMemset(h->d_bar, 0, 64);
+        return fail(Q3_ECUDA, "megakernel wait timed out (status %d: 1 grid barrier, 2 stage ring, 3 peer flag)", code);
+    }
+    return 0;
+}
+static inline bool use_mega(const q3_handle *h) { return h->decode_path == 1 && h->mega_ok && !h->exact; }
+
+// ------------------------------------------------------------------------------------------
 // construction
 // ------------------------------------------------------------------------------------------
 static int create_impl(const char *path, int ctx_len, int device, int tp_rank, int tp_size, q3_handle **out) {
@@ -577,6 +738,13 @@ static int create_impl(const char *path, int ctx_len, int device, int tp_rank, i
     CKH(cudaMallocHost((void **)&h->h_small, 64 * 4));
     CKH(cudaDeviceSynchronize());
     TRY(build_graphs(h));
+    h->graph_launches_per_step = h->launches_per_step;
+    TRY(build_mega(h, ck.rms_att, ck.rms_ffn, ck.q_ln, ck.k_ln));
+    if (h->mega_ok && !getenv("Q3_NO_MEGA")) {
+        h->decode_path = 1;
+        h->launches_per_step = 1;
+    }
+    CKH(cudaDeviceSynchronize());
     *out = h;
     return Q3_OK;
 }
@@ -603,6 +771,7 @@ extern "C" void q3_destroy(q3_handle *h) {
     for (void *p : h->allocs) cudaFree(p);
     if (h->h_logits) cudaFreeHost(h->h_logits);
     if (h->h_small) cudaFreeHost(h->h_small);
+    if (h->h_status) cudaFreeHost(h->h_status);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -612,8 +781,11 @@ extern "C" const float *q3_logits_device(const q3_handle *h) { return h ? h->log
 extern "C" int q3_launches_per_step(const q3_handle *h) { return h ? h->launches_per_step : 0; }
 extern "C" int q3_set_decode_path(q3_handle *h, int path) {
     if (!h) return fail(Q3_EINVAL, "null handle");
-    if (path != 0) return fail(Q3_EUNSUPPORTED, "decode path %d not available", path);
+    if (path != 0 && path != 1) return fail(Q3_EINVAL, "decode path %d unknown", path);
+    if (path == 1 && !h->mega_ok)
+        return fail(Q3_EUNSUPPORTED, "persistent decode kernel unavailable for this shape: %s", h->mega_why.c_str());
     h->decode_path = path;
+    h->launches_per_step = path == 1 ? 1 : h->graph_launches_per_step;
     return Q3_OK;
 }
 
@@ -649,7 +821,11 @@ extern "C" int q3_forward(q3_handle *h, int token, int pos, float *logits_host) 
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
     if ((rc = set_tok_pos(h, token, pos))) return rc;
-    CK(cudaGraphLaunch(h->g_fwd[h->exact], h->stream));
+    if (use_mega(h)) {
+        if ((rc = launch_mega(h, 0, h->cfg.n_layers, true, true, false, logits_host != nullptr))) return rc;
+    } else {
+        CK(cudaGraphLaunch(h->g_fwd[h->exact], h->stream));
+    }
     if (logits_host) {
         CK(cudaMemcpyAsync(h->h_logits, h->logits, (size_t)h->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -657,7 +833,7 @@ extern "C" int q3_forward(q3_handle *h, int token, int pos, float *logits_host) 
     } else {
         CK(cudaStreamSynchronize(h->stream));
     }
-    return Q3_OK;
+    return mega_check(h);
 }
 
 extern "C" int q3_forward_argmax(q3_handle *h, int token, int pos, int *next_token) {
@@ -666,11 +842,15 @@ extern "C" int q3_forward_argmax(q3_handle *h, int token, int pos, int *next_tok
     if (!next_token) return fail(Q3_EINVAL, "null next_token");
     CK(cudaSetDevice(h->device));
     if ((rc = set_tok_pos(h, token, pos))) return rc;
-    CK(cudaGraphLaunch(h->g_greedy[h->exact], h->stream));
+    if (use_mega(h)) {
+        if ((rc = launch_mega(h, 0, h->cfg.n_layers, true, true, true, false))) return rc;
+    } else {
+        CK(cudaGraphLaunch(h->g_greedy[h->exact], h->stream));
+    }
     CK(cudaMemcpyAsync(h->h_small + 8, h->d_tokpos + 2, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     *next_token = h->h_small[8];
-    return Q3_OK;
+    return mega_check(h);
 }
 
 extern "C" int q3_decode_greedy(q3_handle *h, int first_token, int pos0, int n, int *tokens_out) {
@@ -680,12 +860,18 @@ extern "C" int q3_decode_greedy(q3_handle *h, int first_token, int pos0, int n, 
     if (n > h->history_cap) return fail(Q3_EINVAL, "n too large");
     CK(cudaSetDevice(h->device));
     if ((rc = set_tok_pos(h, first_token, pos0))) return rc;
-    for (int i = 0; i < n; i++) CK(cudaGraphLaunch(h->g_greedy[h->exact], h->stream));
+    for (int i = 0; i < n; i++) {
+        if (use_mega(h)) {
+            if ((rc = launch_mega(h, 0, h->cfg.n_layers, true, true, true, false))) return rc;
+        } else {
+            CK(cudaGraphLaunch(h->g_greedy[h->exact], h->stream));
+        }
+    }
     if (tokens_out && n > 0) {
         CK(cudaMemcpyAsync(tokens_out, h->d_history, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
-    return Q3_OK;
+    return mega_check(h);
 }
 
 extern "C" int q3_bench_decode(q3_handle *h, int first_token, int pos0, int steps, float *ms_out) {
@@ -699,7 +885,13 @@ extern "C" int q3_bench_decode(q3_handle *h, int first_token, int pos0, int step
     CK(cudaEventCreate(&e1));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaEventRecord(e0, h->stream));
-    for (int i = 0; i < steps; i++) CK(cudaGraphLaunch(h->g_greedy[h->exact], h->stream));
+    for (int i = 0; i < steps; i++) {
+        if (use_mega(h)) {
+            if ((rc = launch_mega(h, 0, h->cfg.n_layers, true, true, true, false))) return rc;
+        } else {
+            CK(cudaGraphLaunch(h->g_greedy[h->exact], h->stream));
+        }
+    }
     CK(cudaEventRecord(e1, h->stream));
     CK(cudaEventSynchronize(e1));
     float ms = 0;
@@ -707,7 +899,7 @@ extern "C" int q3_bench_decode(q3_handle *h, int first_token, int pos0, int step
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (ms_out) *ms_out = ms;
-    return Q3_OK;
+    return mega_check(h);
 }
 
 extern "C" int q3_bench_kernel(q3_handle *h, int kind, int pos, int reps, float *ms_out, int *launches_out,
@@ -838,16 +1030,23 @@ extern "C" int q3_forward_layers(q3_handle *h, int pos, int layer0, int layer1, 
     int rc;
     if ((rc = set_tok_pos(h, 0, pos))) return rc;
     CK(cudaMemcpyAsync(h->x, x_host, (size_t)h->cfg.dim * 4, cudaMemcpyHostToDevice, h->stream));
-    for (int l = layer0; l < layer1; l++) launch_layer(h, l, false, h->stream);
+    if (use_mega(h)) {
+        if (layer1 > layer0 && (rc = launch_mega(h, layer0, layer1, false, false, false, false))) return rc;
+    } else {
+        for (int l = layer0; l < layer1; l++) launch_layer(h, l, false, h->stream);
+    }
     CK(cudaMemcpyAsync(x_host, h->x, (size_t)h->cfg.dim * 4, cudaMemcpyDeviceToHost, h->stream));
     if (run_head) {
+        if (use_mega(h)) {
+            if ((rc = launch_mega(h, 0, 0, false, true, false, true))) return rc;
+        } else
         launch_head(h, h->stream);
         if (logits_host)
             CK(cudaMemcpyAsync(logits_host, h->logits, (size_t)h->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
-    return Q3_OK;
+    return mega_check(h);
 }
 
 // ------------------------------------------------------------------------------------------

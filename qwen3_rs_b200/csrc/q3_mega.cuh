@@ -1,0 +1,798 @@
+// q3_mega.cuh -- persistent single-launch decode step ("megakernel") for sm_100a.
+//
+// One cooperative launch per token: 148 CTAs (one per SM) walk the whole forward pass
+// (qwen3.rs:62-79, 131-176) phase by phase, separated by grid barriers.  Inside each CTA one
+// PRODUCER warp streams the CTA's share of the int8 weights HBM -> shared memory with
+// cp.async.bulk (TMA, 1-D) into a ring of mbarrier-guarded stages, and runs AHEAD of the
+// consumers across phase and layer boundaries (weights do not depend on activations), so HBM
+// stays busy while the 8 CONSUMER warps sit in a grid barrier or rebuild the quantised
+// activation vector.  Consumers keep their slice of the activation vector in registers and do
+// the int8 dot products with dp4a straight out of shared memory.
+//
+// HBM "stream" layout (built once at load by k_build_stream): for every GEMV phase, rows are
+// split contiguously over CTAs; a CTA's rows are stored in the exact order its consumers eat
+// them, one "row tile" (KT <= 4096 columns + their f32 scales) per consumer warp per stage,
+// and inside a tile the 16-byte chunks are permuted so that lane l owns whole quantisation
+// groups (l, l+32, ...) while every 128-bit shared-memory load stays bank-conflict free.
+//
+// Float semantics are those of the fast multi-kernel path (q3_kernels.cuh): identical per-group
+// terms, parallel reductions.  Exact (reference-order) mode uses the multi-kernel path.
+#pragma once
+#include "q3_kernels.cuh"
+
+namespace q3 {
+
+constexpr int MEGA_NCW = 8;                         // consumer warps
+constexpr int MEGA_CTHREADS = MEGA_NCW * 32;        // 256 consumer threads
+constexpr int MEGA_THREADS = MEGA_CTHREADS + 32;    // + producer warp
+constexpr int MEGA_NSTAGE = 5;
+constexpr int MEGA_MAX_KT = 4096;
+constexpr int MEGA_SCRATCH = 40960;                 // xq/xs or attention buffers
+constexpr int MEGA_MAX_TP = 8;
+constexpr int MEGA_MAX_SPLITS = ATTN_MAX_SPLITS;
+
+enum { PH_QKV = 0, PH_O = 1, PH_GU = 2, PH_DN = 3, PH_HEAD = 4 };
+
+struct MegaGemv {
+    const uint8_t *base;     // stream of layer 0 (or the lm_head stream)
+    long long layer_stride;  // bytes between layers
+    int units;               // rows, or (gate, up) PAIRS for PH_GU
+    int K, n_kt, KT, G;      // columns, K tiles per row, columns per tile, groups per tile
+    int tile_bytes;          // KT + 4*G
+};
+
+struct MegaArgs {
+    int dim, n_layers, n_heads_l, n_kv_l, AH_l, KV_l, H_l, vocab_l, vocab_row0, seq_len;
+    int tp_rank, tp_size;
+    MegaGemv g[5];
+    const float *rms_att, *rms_ffn, *q_ln, *k_ln, *rms_final; // [L][dim] / [L][128] contiguous
+    const int8_t *embed_q;
+    const float *embed_s;
+    const float *rope;
+    float *kc, *vc;
+    float *x[2];                     // residual stream, ping-pong
+    float *part[2][MEGA_MAX_TP];     // [o|down][rank]: that rank's landing zone [tp][dim] (peer memory under TP)
+    float *q, *kraw, *hb, *attn_part;
+    float *logits[MEGA_MAX_TP];      // full-vocab logits buffer of every rank
+    unsigned long long *best[MEGA_MAX_TP]; // [tp][grid] argmax candidates of every rank
+    unsigned long long *bar;         // grid barrier counter (monotonic, never reset)
+    unsigned long long bar_base;     // counter value when this launch starts (host-tracked)
+    unsigned int *flags[MEGA_MAX_TP]; // cross-GPU barrier flags of every rank: [tp]
+    unsigned int xepoch_base;        // cross-GPU exchange epochs completed before this launch (host-tracked)
+    int *tokpos, *history;
+    int *status;                     // != 0: a wait timed out (kernel aborts)
+    int layer0, layer1, from_embed, run_head, feedback, gather_logits;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + bulk copy
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *status) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL || *(volatile int *)status) { // ~2 s: a scheduling bug, not a stall
+            atomicExch(status, 2);
+            return;
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(MEGA_CTHREADS) : "memory"); }
+__device__ __forceinline__ float ldcg_f(const float *p) { return __ldcg(p); }
+__device__ __forceinline__ float4 ldcg_f4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+
+// contiguous split of `units` over `nctas`
+__device__ __host__ __forceinline__ void cta_share(int units, int nctas, int c, int &start, int &count) {
+    int base = units / nctas, rem = units % nctas;
+    count = base + (c < rem ? 1 : 0);
+    start = c * base + (c < rem ? c : rem);
+}
+
+// ------------------------------------------------------------------------------------------
+// stream builder: row-major int8 [rows][K] + scales [rows][K/GS]  ->  megakernel stream
+// grid = (units, n_kt); one block per unit (row, or gate/up pair) and K tile.
+// ------------------------------------------------------------------------------------------
+template <int GS>
+__global__ void __launch_bounds__(256) k_build_stream(const int8_t *__restrict__ src_q, const float *__restrict__ src_s,
+                                                      uint8_t *dst, int units, int K, int n_kt, int nctas, int pair) {
+    constexpr int CPG = GS / 16;
+    const int u = blockIdx.x, kt = blockIdx.y;
+    const int KT = K / n_kt, G = KT / GS, tile_bytes = KT + 4 * G;
+    const int base = units / nctas, rem = units % nctas;
+    int c, j;
+    if (u < rem * (base + 1)) {
+        c = u / (base + 1);
+        j = u % (base + 1);
+    } else {
+        c = rem + (u - rem * (base + 1)) / base;
+        j = (u - rem * (base + 1)) % base;
+    }
+    int start, n_c;
+    cta_share(units, nctas, c, start, n_c);
+    for (int half = 0; half < (pair ? 2 : 1); half++) {
+        long long tile_index;
+        size_t src_row;
+        if (pair) { // blocks of 8 pairs: [gate x np][up x np]
+            int blk = j / 8, w = j % 8, np = n_c - 8 * blk;
+            if (np > 8) np = 8;
+            tile_index = (long long)start * 2 + 16 * blk + half * np + w;
+            src_row = (size_t)2 * u + half;
+        } else { // batches of 32 rows: [kt][row]
+            int b = j / 32, jb = j % 32, nb = n_c - 32 * b;
+            if (nb > 32) nb = 32;
+            tile_index = ((long long)start + 32 * b) * n_kt + (long long)kt * nb + jb;
+            src_row = (size_t)u;
+        }
+        uint8_t *tile = dst + tile_index * tile_bytes;
+        const int8_t *srow = src_q + src_row * K + (size_t)kt * KT;
+        for (int ch = threadIdx.x; ch < KT / 16; ch += blockDim.x) {
+            int g = ch / CPG, p = ch % CPG, b = g / 32, l = g % 32;
+            int ngb = G - 32 * b;
+            if (ngb > 32) ngb = 32;
+            int dpos = b * 32 * CPG + p * ngb + l;
+            reinterpret_cast<int4 *>(tile)[dpos] = reinterpret_cast<const int4 *>(srow)[ch];
+        }
+        const float *ss = src_s + src_row * (K / GS) + (size_t)kt * G;
+        for (int g = threadIdx.x; g < G; g += blockDim.x) reinterpret_cast<float *>(tile + KT)[g] = ss[g];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// consumer-side building blocks
+// ------------------------------------------------------------------------------------------
+template <int GS>
+struct XRegs { // this lane's groups of the current K tile: MEGA_MAX_KT/128 = 32 registers + scales
+    static constexpr int CPG = GS / 16;
+    static constexpr int NBLK = MEGA_MAX_KT / (32 * GS);
+    int4 x[NBLK][CPG];
+    float s[NBLK];
+};
+
+template <int GS>
+__device__ __forceinline__ void load_x(XRegs<GS> &xr, const uint8_t *sxq, const float *sxs, int kt, int KT, int G, int lane) {
+#pragma unroll
+    for (int b = 0; b < XRegs<GS>::NBLK; b++) {
+        int g = b * 32 + lane;
+        bool ok = g < G;
+        xr.s[b] = ok ? sxs[kt * G + g] : 0.0f;
+#pragma unroll
+        for (int p = 0; p < XRegs<GS>::CPG; p++)
+            xr.x[b][p] = ok ? *reinterpret_cast<const int4 *>(sxq + (size_t)kt * KT + (size_t)g * GS + p * 16) : make_int4(0, 0, 0, 0);
+    }
+}
+
+// dot of one row tile (in shared memory) with the register-resident activation slice.
+// Per group: exact int32 dot, then (dot as f32 * weight_scale) * input_scale (tensor.rs:47-59).
+template <int GS>
+__device__ __forceinline__ float tile_dot(const uint8_t *tile, const XRegs<GS> &xr, int KT, int G, int lane) {
+    constexpr int CPG = XRegs<GS>::CPG;
+    const float *ws = reinterpret_cast<const float *>(tile + KT);
+    float acc = 0.0f;
+#pragma unroll
+    for (int b = 0; b < XRegs<GS>::NBLK; b++) {
+        int ngb = G - 32 * b;
+        if (ngb > 32) ngb = 32;
+        if (lane < ngb) { // ngb <= 0 -> nobody
+            const int4 *wp = reinterpret_cast<const int4 *>(tile) + b * 32 * CPG + lane;
+            int d = 0;
+#pragma unroll
+            for (int p = 0; p < CPG; p++) d = dot16(wp[p * ngb], xr.x[b][p], d);
+            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn((float)d, ws[b * 32 + lane]), xr.s[b]));
+        }
+    }
+    return warp_sum(acc);
+}
+
+// RMSNorm + group quantise of the residual stream into shared memory (all 256 consumer threads).
+// Also merges the pending partial sums of the previous row-parallel GEMV (o_proj / down_proj:
+// x <- x + sum_r part[r], ResidualConnection layers.rs:249-259; under TP this IS the all-reduce,
+// summed in rank order so every rank computes bit-identical x) and gathers the embedding row.
+template <int GS>
+__device__ __forceinline__ void prologue_norm(const MegaArgs &a, const float *w, bool from_embed, const float *const *parts,
+                                              int &cur, uint8_t *sxq, float *sxs, float *sred, bool write_normed) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n4 = a.dim >> 2;
+    constexpr int MAXV = MEGA_MAX_KT / (4 * MEGA_CTHREADS); // dim <= 4096 on this path
+    float4 v[MAXV];
+    float ss = 0.0f;
+    const float *xin = a.x[cur];
+    float *xout = a.x[cur ^ 1];
+    const bool merge = parts != nullptr;
+#pragma unroll
+    for (int k = 0; k < MAXV; k++) {
+        int i4 = tid + k * MEGA_CTHREADS;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i4 < n4) {
+            if (from_embed) {
+                size_t base = (size_t)a.tokpos[0] * a.dim + (size_t)i4 * 4;
+                char4 e = *reinterpret_cast<const char4 *>(a.embed_q + base);
+                float sc = a.embed_s[base / GS];
+                v[k] = make_float4((float)e.x * sc, (float)e.y * sc, (float)e.z * sc, (float)e.w * sc);
+            } else {
+                v[k] = ldcg_f4(xin + (size_t)i4 * 4);
+                if (merge) {
+                    for (int r = 0; r < a.tp_size; r++) {
+                        float4 p = ldcg_f4(parts[a.tp_rank] + (size_t)r * a.dim + (size_t)i4 * 4);
+                        v[k].x = __fadd_rn(v[k].x, p.x);
+                        v[k].y = __fadd_rn(v[k].y, p.y);
+                        v[k].z = __fadd_rn(v[k].z, p.z);
+                        v[k].w = __fadd_rn(v[k].w, p.w);
+                    }
+                }
+            }
+            if ((from_embed || merge) && blockIdx.x == 0) reinterpret_cast<float4 *>(from_embed ? a.x[cur] : xout)[i4] = v[k];
+            ss += __fmul_rn(v[k].x, v[k].x);
+            ss += __fmul_rn(v[k].y, v[k].y);
+            ss += __fmul_rn(v[k].z, v[k].z);
+            ss += __fmul_rn(v[k].w, v[k].w);
+        }
+    }
+    if (merge && !from_embed) cur ^= 1;
+    ss = warp_sum(ss);
+    if (lane == 0) sred[warp] = ss;
+    csync();
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MEGA_NCW; i++) t += sred[i];
+    const float f = __fdiv_rn(1.0f, sqrtf(__fadd_rn(__fdiv_rn(t, (float)a.dim), NORM_EPS)));
+#pragma unroll
+    for (int k = 0; k < MAXV; k++) {
+        int i4 = tid + k * MEGA_CTHREADS;
+        if (i4 - lane < n4) {
+            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i4 < n4) {
+                float4 wv = __ldg(reinterpret_cast<const float4 *>(w) + i4);
+                y.x = __fmul_rn(wv.x, __fmul_rn(f, v[k].x));
+                y.y = __fmul_rn(wv.y, __fmul_rn(f, v[k].y));
+                y.z = __fmul_rn(wv.z, __fmul_rn(f, v[k].z));
+                y.w = __fmul_rn(wv.w, __fmul_rn(f, v[k].w));
+            }
+            uint32_t packed;
+            float scale;
+            quantize_group4<GS>(y, packed, scale);
+            if (i4 < n4) {
+                reinterpret_cast<uint32_t *>(sxq)[i4] = packed;
+                if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
+                if (write_normed && blockIdx.x == 0) reinterpret_cast<float4 *>(a.x[cur])[i4] = y;
+            }
+        }
+    }
+    csync();
+}
+
+// quantise an f32 vector in global memory (written by other CTAs) into shared memory
+template <int GS>
+__device__ __forceinline__ void prologue_quant(const float *src, int n, uint8_t *sxq, float *sxs) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n4 = n >> 2;
+    for (int base = tid - lane; base < n4; base += MEGA_CTHREADS) {
+        int i4 = base + lane;
+        float4 y = (i4 < n4) ? ldcg_f4(src + (size_t)i4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t packed;
+        float scale;
+        quantize_group4<GS>(y, packed, scale);
+        if (i4 < n4) {
+            reinterpret_cast<uint32_t *>(sxq)[i4] = packed;
+            if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
+        }
+    }
+    csync();
+}
+
+// merge the attention split partials (k_attn_combine_quant's math) and quantise into shared memory
+template <int GS>
+__device__ __forceinline__ void prologue_attn_out(const MegaArgs &a, int nsplit, uint8_t *sxq, float *sxs) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n4 = a.AH_l >> 2;
+    for (int base = tid - lane; base < n4; base += MEGA_CTHREADS) {
+        int i4 = base + lane;
+        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i4 < n4) {
+            int head = i4 >> 5, d4 = i4 & 31;
+            const float *pb = a.attn_part + (size_t)head * MEGA_MAX_SPLITS * ATTN_PART_STRIDE;
+            float M = -INFINITY;
+            for (int s = 0; s < nsplit; s++) M = fmaxf(M, ldcg_f(pb + s * ATTN_PART_STRIDE + HEAD_DIM));
+            float L = 0.0f;
+            float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < nsplit; s++) {
+                const float *ps = pb + s * ATTN_PART_STRIDE;
+                float c = expf(ldcg_f(ps + HEAD_DIM) - M);
+                L += ldcg_f(ps + HEAD_DIM + 1) * c;
+                float4 p = ldcg_f4(ps + d4 * 4);
+                A.x += p.x * c;
+                A.y += p.y * c;
+                A.z += p.z * c;
+                A.w += p.w * c;
+            }
+            float inv = __fdiv_rn(1.0f, L);
+            y = make_float4(__fmul_rn(A.x, inv), __fmul_rn(A.y, inv), __fmul_rn(A.z, inv), __fmul_rn(A.w, inv));
+        }
+        uint32_t packed;
+        float scale;
+        quantize_group4<GS>(y, packed, scale);
+        if (i4 < n4) {
+            reinterpret_cast<uint32_t *>(sxq)[i4] = packed;
+            if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
+        }
+    }
+    csync();
+}
+
+// QK-RMSNorm + RoPE of one head held as float4 per lane (same math as k_qknorm_rope)
+__device__ __forceinline__ float4 qk_norm_rope(float4 v, const float *w, const float *rope_row, int lane) {
+    float ss = __fmul_rn(v.x, v.x);
+    ss = __fadd_rn(ss, __fmul_rn(v.y, v.y));
+    ss = __fadd_rn(ss, __fmul_rn(v.z, v.z));
+    ss = __fadd_rn(ss, __fmul_rn(v.w, v.w));
+    ss = warp_sum(ss);
+    const float f = __fdiv_rn(1.0f, sqrtf(__fadd_rn(__fdiv_rn(ss, (float)HEAD_DIM), NORM_EPS)));
+    float4 wv = __ldg(reinterpret_cast<const float4 *>(w) + lane);
+    float4 y;
+    y.x = __fmul_rn(wv.x, __fmul_rn(f, v.x));
+    y.y = __fmul_rn(wv.y, __fmul_rn(f, v.y));
+    y.z = __fmul_rn(wv.z, __fmul_rn(f, v.z));
+    y.w = __fmul_rn(wv.w, __fmul_rn(f, v.w));
+    float4 o;
+    o.x = __shfl_xor_sync(0xffffffffu, y.x, 16);
+    o.y = __shfl_xor_sync(0xffffffffu, y.y, 16);
+    o.z = __shfl_xor_sync(0xffffffffu, y.z, 16);
+    o.w = __shfl_xor_sync(0xffffffffu, y.w, 16);
+    const float4 *cs = reinterpret_cast<const float4 *>(rope_row) + (lane & 15) * 2;
+    float4 cs01 = __ldg(cs), cs23 = __ldg(cs + 1);
+    float4 r;
+    if (lane < 16) {
+        r.x = __fsub_rn(__fmul_rn(y.x, cs01.x), __fmul_rn(o.x, cs01.y));
+        r.y = __fsub_rn(__fmul_rn(y.y, cs01.z), __fmul_rn(o.y, cs01.w));
+        r.z = __fsub_rn(__fmul_rn(y.z, cs23.x), __fmul_rn(o.z, cs23.y));
+        r.w = __fsub_rn(__fmul_rn(y.w, cs23.z), __fmul_rn(o.w, cs23.w));
+    } else {
+        r.x = __fadd_rn(__fmul_rn(o.x, cs01.y), __fmul_rn(y.x, cs01.x));
+        r.y = __fadd_rn(__fmul_rn(o.y, cs01.w), __fmul_rn(y.y, cs01.z));
+        r.z = __fadd_rn(__fmul_rn(o.z, cs23.y), __fmul_rn(y.z, cs23.x));
+        r.w = __fadd_rn(__fmul_rn(o.w, cs23.w), __fmul_rn(y.w, cs23.z));
+    }
+    return r;
+}
+
+__device__ __forceinline__ int mega_nsplit(int pos, int n_kv_l, int grid) {
+    int n = pos + 1;
+    int ns = (n + ATTN_MIN_CHUNK - 1) / ATTN_MIN_CHUNK;
+    int cap = grid / n_kv_l;
+    if (cap > MEGA_MAX_SPLITS) cap = MEGA_MAX_SPLITS;
+    if (cap < 1) cap = 1;
+    return ns > cap ? cap : ns;
+}
+
+// attention phase for one (kv head, split) work item; all 256 consumer threads.
+template <int KVMUL>
+__device__ __forceinline__ void attention_item(const MegaArgs &a, int layer, int pos, int kvh, int split, int nsplit,
+                                               uint8_t *scratch) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float4 *sq = reinterpret_cast<float4 *>(scratch);                 // [KVMUL][32]
+    float4 *sk = sq + KVMUL * 32;                                     // [32]
+    float *sm_m = reinterpret_cast<float *>(sk + 32);                 // [8][KVMUL]
+    float *sm_l = sm_m + MEGA_NCW * KVMUL;                            // [8][KVMUL]
+    float4 *sm_acc = reinterpret_cast<float4 *>(sm_l + MEGA_NCW * KVMUL); // [8][KVMUL][32]
+    const int n = pos + 1;
+    const int per = (n + nsplit - 1) / nsplit;
+    const int t0 = split * per;
+    int t1 = t0 + per;
+    if (t1 > n) t1 = n;
+    float *kc_l = a.kc + (size_t)layer * a.seq_len * a.KV_l;
+    float *vc_l = a.vc + (size_t)layer * a.seq_len * a.KV_l;
+    const float *rope_row = a.rope + (size_t)pos * HEAD_DIM;
+    // QK-norm + RoPE (layers.rs:346-372): KVMUL query heads and the key head of this kv group
+    for (int hh = warp; hh < KVMUL + 1; hh += MEGA_NCW) {
+        if (hh < KVMUL) {
+            float4 v = ldcg_f4(a.q + (size_t)(kvh * KVMUL + hh) * HEAD_DIM + lane * 4);
+            sq[hh * 32 + lane] = qk_norm_rope(v, a.q_ln + (size_t)layer * HEAD_DIM, rope_row, lane);
+        } else {
+            float4 v = ldcg_f4(a.kraw + (size_t)kvh * HEAD_DIM + lane * 4);
+            float4 r = qk_norm_rope(v, a.k_ln + (size_t)layer * HEAD_DIM, rope_row, lane);
+            sk[lane] = r;
+            if (pos >= t0 && pos < t1) // the split that owns `pos` publishes the cache row
+                reinterpret_cast<float4 *>(kc_l + (size_t)pos * a.KV_l + (size_t)kvh * HEAD_DIM)[lane] = r;
+        }
+    }
+    csync();
+    const float scale = __fdiv_rn(1.0f, sqrtf((float)HEAD_DIM));
+    float4 qv[KVMUL];
+    float m[KVMUL], l[KVMUL];
+    float4 acc[KVMUL];
+#pragma unroll
+    for (int h = 0; h < KVMUL; h++) {
+        qv[h] = sq[h * 32 + lane];
+        m[h] = -INFINITY;
+        l[h] = 0.0f;
+        acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float *kbase = kc_l + (size_t)kvh * HEAD_DIM + lane * 4;
+    const float *vbase = vc_l + (size_t)kvh * HEAD_DIM + lane * 4;
+    for (int t = t0 + warp; t < t1; t += MEGA_NCW) {
+        float4 kv = (t == pos) ? sk[lane] : ldcg_f4(kbase + (size_t)t * a.KV_l);
+        float4 vv = ldcg_f4(vbase + (size_t)t * a.KV_l);
+        float s[KVMUL];
+#pragma unroll
+        for (int h = 0; h < KVMUL; h++) s[h] = qv[h].x * kv.x + qv[h].y * kv.y + qv[h].z * kv.z + qv[h].w * kv.w;
+#pragma unroll
+        for (int h = 0; h < KVMUL; h++) s[h] = __fmul_rn(warp_sum(s[h]), scale);
+#pragma unroll
+        for (int h = 0; h < KVMUL; h++) {
+            float mn = fmaxf(m[h], s[h]);
+            float corr = expf(m[h] - mn);
+            float p = expf(s[h] - mn);
+            l[h] = l[h] * corr + p;
+            acc[h].x = acc[h].x * corr + p * vv.x;
+            acc[h].y = acc[h].y * corr + p * vv.y;
+            acc[h].z = acc[h].z * corr + p * vv.z;
+            acc[h].w = acc[h].w * corr + p * vv.w;
+            m[h] = mn;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < KVMUL; h++) {
+        if (lane == 0) {
+            sm_m[warp * KVMUL + h] = m[h];
+            sm_l[warp * KVMUL + h] = l[h];
+        }
+        sm_acc[(warp * KVMUL + h) * 32 + lane] = acc[h];
+    }
+    csync();
+    for (int h = warp; h < KVMUL; h += MEGA_NCW) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < MEGA_NCW; w++) M = fmaxf(M, sm_m[w * KVMUL + h]);
+        float L = 0.0f;
+        float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < MEGA_NCW; w++) {
+            float mw = sm_m[w * KVMUL + h];
+            float c = (mw == -INFINITY) ? 0.0f : expf(mw - M);
+            L += sm_l[w * KVMUL + h] * c;
+            float4 aw = sm_acc[(w * KVMUL + h) * 32 + lane];
+            A.x += aw.x * c;
+            A.y += aw.y * c;
+            A.z += aw.z * c;
+            A.w += aw.w * c;
+        }
+        float *dst = a.attn_part + ((size_t)(kvh * KVMUL + h) * MEGA_MAX_SPLITS + split) * ATTN_PART_STRIDE;
+        reinterpret_cast<float4 *>(dst)[lane] = A;
+        if (lane == 0) {
+            dst[HEAD_DIM] = M;
+            dst[HEAD_DIM + 1] = L;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// grid barrier (+ cross-GPU flag exchange under TP)
+// ------------------------------------------------------------------------------------------
+struct BarState {
+    unsigned long long target; // next value the local counter must reach
+    unsigned int xepoch;       // cross-GPU epoch of the next exchange barrier
+};
+
+__device__ __forceinline__ void grid_barrier(const MegaArgs &a, BarState &bs, bool cross) {
+    csync();
+    if (threadIdx.x == 0) {
+        if (cross && a.tp_size > 1) __threadfence_system();
+        else __threadfence();
+        atomicAdd(a.bar, 1ULL);
+        long long t0 = clock64();
+        volatile int *st = a.status;
+        while (true) {
+            unsigned long long v;
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
+            if (v >= bs.target) break;
+            if (*st) break;
+            if (clock64() - t0 > 4000000000LL) {
+                atomicExch(a.status, 1);
+                break;
+            }
+        }
+        if (cross && a.tp_size > 1) {
+            const unsigned int e = bs.xepoch;
+            if (blockIdx.x == 0) { // everyone on this GPU has arrived (and fenced): tell the peers
+                __threadfence_system();
+                for (int r = 0; r < a.tp_size; r++)
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[r] + a.tp_rank), "r"(e) : "memory");
+            }
+            for (int r = 0; r < a.tp_size; r++) {
+                while (true) {
+                    unsigned int v;
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flags[a.tp_rank] + r) : "memory");
+                    if ((int)(v - e) >= 0) break;
+                    if (*st) break;
+                    if (clock64() - t0 > 8000000000LL) {
+                        atomicExch(a.status, 3);
+                        break;
+                    }
+                }
+            }
+        }
+    }
+    bs.target += gridDim.x;
+    if (cross) bs.xepoch += 1;
+    csync();
+}
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+struct PhaseGeom {
+    const uint8_t *seg; // this CTA's segment of the phase stream
+    int start, count;   // units owned by this CTA
+};
+__device__ __forceinline__ PhaseGeom phase_geom(const MegaGemv &g, int layer, int pair) {
+    PhaseGeom pg;
+    cta_share(g.units, gridDim.x, blockIdx.x, pg.start, pg.count);
+    pg.seg = g.base + (long long)layer * g.layer_stride +
+             (long long)pg.start * (pair ? 2 : 1) * g.n_kt * (long long)g.tile_bytes;
+    return pg;
+}
+
+template <int GS, int KVMUL>
+__global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_constant__ MegaArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // layout: [ring: NSTAGE x slot][scratch][barriers]
+    const int slot_bytes = MEGA_NCW * (MEGA_MAX_KT + 4 * (MEGA_MAX_KT / GS));
+    uint8_t *ring = smem;
+    uint8_t *scratch = smem + MEGA_NSTAGE * slot_bytes;
+    uint8_t *sxq = scratch;                                          // up to 16384 B
+    float *sxs = reinterpret_cast<float *>(scratch + 16384);         // up to 512 groups
+    float *sred = reinterpret_cast<float *>(scratch + 16384 + 2048); // 8 floats (+ argmax scratch)
+    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + MEGA_SCRATCH);
+    uint64_t *empty = full + MEGA_NSTAGE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < MEGA_NSTAGE; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], MEGA_NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int L0 = a.layer0, L1 = a.layer1;
+
+    if (warp == MEGA_NCW) {
+        // =============================== PRODUCER ===============================
+        if (lane != 0) return;
+        uint64_t policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        unsigned it = 0;
+        auto push = [&](const uint8_t *src, int nr, int tile_bytes) {
+            const int slot = it % MEGA_NSTAGE;
+            mbar_wait(&empty[slot], ((it / MEGA_NSTAGE) & 1) ^ 1, a.status);
+            const uint32_t bytes = (uint32_t)nr * tile_bytes;
+            mbar_expect_tx(&full[slot], bytes);
+            bulk_g2s(ring + (size_t)slot * slot_bytes, src, bytes, &full[slot], policy);
+            it++;
+        };
+        auto plain = [&](int ph, int layer) {
+            const MegaGemv &g = a.g[ph];
+            PhaseGeom pg = phase_geom(g, layer, 0);
+            const uint8_t *src = pg.seg;
+            for (int b0 = 0; b0 < pg.count; b0 += 32) {
+                int nb = pg.count - b0 < 32 ? pg.count - b0 : 32;
+                for (int kt = 0; kt < g.n_kt; kt++)
+                    for (int s = 0; s < nb; s += 8) {
+                        int nr = nb - s < 8 ? nb - s : 8;
+                        push(src, nr, g.tile_bytes);
+                        src += (size_t)nr * g.tile_bytes;
+                    }
+            }
+        };
+        auto pairs = [&](int layer) {
+            const MegaGemv &g = a.g[PH_GU];
+            PhaseGeom pg = phase_geom(g, layer, 1);
+            const uint8_t *src = pg.seg;
+            for (int p0 = 0; p0 < pg.count; p0 += 8) {
+                int np = pg.count - p0 < 8 ? pg.count - p0 : 8;
+                for (int half = 0; half < 2; half++) {
+                    push(src, np, g.tile_bytes);
+                    src += (size_t)np * g.tile_bytes;
+                }
+            }
+        };
+        for (int l = L0; l < L1; l++) {
+            plain(PH_QKV, l);
+            plain(PH_O, l);
+            pairs(l);
+            plain(PH_DN, l);
+        }
+        if (a.run_head) plain(PH_HEAD, 0);
+        return;
+    }
+
+    // =============================== CONSUMERS ===============================
+    unsigned it = 0;
+    BarState bs;
+    bs.target = a.bar_base + gridDim.x;
+    bs.xepoch = a.xepoch_base + 1;
+    const int pos = a.tokpos[1];
+    int cur = 0;
+    XRegs<GS> xr;
+
+    // generic row phase: rows -> value; EPI(row_local_index, value) by lane 0
+    auto run_plain = [&](int ph, int layer, auto &&epi) {
+        const MegaGemv &g = a.g[ph];
+        int start, count;
+        cta_share(g.units, gridDim.x, blockIdx.x, start, count);
+        for (int b0 = 0; b0 < count; b0 += 32) {
+            const int nb = count - b0 < 32 ? count - b0 : 32;
+            float accs[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int kt = 0; kt < g.n_kt; kt++) {
+                load_x<GS>(xr, sxq, sxs, kt, g.KT, g.G, lane);
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    if (8 * s < nb) {
+                        const int slot = it % MEGA_NSTAGE;
+                        mbar_wait(&full[slot], (it / MEGA_NSTAGE) & 1, a.status);
+                        if (8 * s + warp < nb)
+                            accs[s] += tile_dot<GS>(ring + (size_t)slot * slot_bytes + (size_t)warp * g.tile_bytes, xr, g.KT, g.G, lane);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[slot]);
+                        it++;
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 4; s++)
+                if (8 * s + warp < nb && lane == 0) epi(start + b0 + 8 * s + warp, accs[s]);
+        }
+    };
+
+    for (int l = L0; l < L1; l++) {
+        // ---- attn_norm + quantize (qwen3.rs:134-136) | q,k,v projections (layers.rs:334-336) ----
+        {
+            const bool emb = (l == L0) && a.from_embed;
+            const float *const *parts = (l > L0) ? (const float *const *)a.part[1] : nullptr;
+            prologue_norm<GS>(a, a.rms_att + (size_t)l * a.dim, emb, parts, cur, sxq, sxs, sred, false);
+            float *vrow = a.vc + ((size_t)l * a.seq_len + pos) * a.KV_l;
+            run_plain(PH_QKV, l, [&](int r, float v) {
+                if (r < a.AH_l) a.q[r] = v;
+                else if (r < a.AH_l + a.KV_l) a.kraw[r - a.AH_l] = v;
+                else vrow[r - a.AH_l - a.KV_l] = v;
+            });
+        }
+        grid_barrier(a, bs, false);
+        // ---- QK-norm + RoPE + attention (layers.rs:339-343) ----
+        const int nsplit = mega_nsplit(pos, a.n_kv_l, gridDim.x);
+        if ((int)blockIdx.x < a.n_kv_l * nsplit)
+            attention_item<KVMUL>(a, l, pos, blockIdx.x % a.n_kv_l, blockIdx.x / a.n_kv_l, nsplit, scratch);
+        grid_barrier(a, bs, false);
+        // ---- quantize(att) + o_proj (qwen3.rs:152-153); residual merged by the next prologue ----
+        {
+            prologue_attn_out<GS>(a, nsplit, sxq, sxs);
+            run_plain(PH_O, l, [&](int r, float v) {
+                for (int p = 0; p < a.tp_size; p++) a.part[0][p][(size_t)a.tp_rank * a.dim + r] = v;
+            });
+        }
+        grid_barrier(a, bs, true);
+        // ---- ffn_norm + quantize (qwen3.rs:159-161) | gate/up + SwiGLU (layers.rs:468-475) ----
+        {
+            prologue_norm<GS>(a, a.rms_ffn + (size_t)l * a.dim, false, (const float *const *)a.part[0], cur, sxq, sxs, sred, false);
+            const MegaGemv &g = a.g[PH_GU];
+            int start, count;
+            cta_share(g.units, gridDim.x, blockIdx.x, start, count);
+            load_x<GS>(xr, sxq, sxs, 0, g.KT, g.G, lane);
+            for (int p0 = 0; p0 < count; p0 += 8) {
+                const int np = count - p0 < 8 ? count - p0 : 8;
+                float gate = 0.0f, up = 0.0f;
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    const int slot = it % MEGA_NSTAGE;
+                    mbar_wait(&full[slot], (it / MEGA_NSTAGE) & 1, a.status);
+                    if (warp < np) {
+                        float v = tile_dot<GS>(ring + (size_t)slot * slot_bytes + (size_t)warp * g.tile_bytes, xr, g.KT, g.G, lane);
+                        if (half == 0) gate = v;
+                        else up = v;
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[slot]);
+                    it++;
+                }
+                if (warp < np && lane == 0) {
+                    float sw = __fmul_rn(gate, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-gate))));
+                    a.hb[start + p0 + warp] = __fmul_rn(sw, up);
+                }
+            }
+        }
+        grid_barrier(a, bs, false);
+        // ---- quantize(hb) + down (layers.rs:478-479); residual merged by the next prologue ----
+        {
+            prologue_quant<GS>(a.hb, a.H_l, sxq, sxs);
+            run_plain(PH_DN, l, [&](int r, float v) {
+                for (int p = 0; p < a.tp_size; p++) a.part[1][p][(size_t)a.tp_rank * a.dim + r] = v;
+            });
+        }
+        grid_barrier(a, bs, true);
+    }
+
+    if (a.run_head) {
+        // ---- final norm (in place) + quantize + lm_head (qwen3.rs:72-76) + greedy argmax (sampler.rs:57-59) ----
+        const float *const *parts = (L1 > L0) ? (const float *const *)a.part[1] : nullptr;
+        prologue_norm<GS>(a, a.rms_final, false, parts, cur, sxq, sxs, sred, true);
+        long long best = (long long)0x8000000000000000LL;
+        run_plain(PH_HEAD, 0, [&](int r, float v) {
+            const int row = a.vocab_row0 + r;
+            a.logits[a.tp_rank][row] = v;
+            if (a.gather_logits)
+                for (int p = 0; p < a.tp_size; p++)
+                    if (p != a.tp_rank) a.logits[p][row] = v;
+            long long key = ((long long)total_key(v) << 32) | (unsigned)row;
+            best = key > best ? key : best;
+        });
+        long long *sbest = reinterpret_cast<long long *>(sred + 16);
+        if (lane == 0) sbest[warp] = best;
+        csync();
+        if (tid == 0) {
+            for (int w = 1; w < MEGA_NCW; w++) best = sbest[w] > best ? sbest[w] : best;
+            for (int p = 0; p < a.tp_size; p++) a.best[p][(size_t)a.tp_rank * gridDim.x + blockIdx.x] = (unsigned long long)best;
+        }
+        grid_barrier(a, bs, true);
+        if (blockIdx.x == 0 && warp == 0) {
+            long long b = (long long)0x8000000000000000LL;
+            const int n = a.tp_size * gridDim.x;
+            for (int i = lane; i < n; i += 32) {
+                long long k = (long long)__ldcg(a.best[a.tp_rank] + i);
+                b = k > b ? k : b;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                long long other = __shfl_xor_sync(0xffffffffu, b, o);
+                b = other > b ? other : b;
+            }
+            if (lane == 0) {
+                int tok = (int)(b & 0xffffffffLL);
+                a.tokpos[2] = tok;
+                if (a.feedback) {
+                    a.tokpos[0] = tok;
+                    a.tokpos[1] = pos + 1;
+                    a.history[a.tokpos[3]] = tok;
+                    a.tokpos[3] += 1;
+                }
+            }
+        }
+    } else {
+        // teacher-forced layer range: materialise x = x + pending partial sums into x[0]
+        if (blockIdx.x == 0 && L1 > L0) {
+            for (int i = tid; i < a.dim; i += MEGA_CTHREADS) {
+                float v = ldcg_f(a.x[cur] + i);
+                for (int r = 0; r < a.tp_size; r++) v = __fadd_rn(v, ldcg_f(a.part[1][a.tp_rank] + (size_t)r * a.dim + i));
+                a.x[0][i] = v;
+            }
+        } else if (blockIdx.x == 0 && cur != 0) {
+            for (int i = tid; i < a.dim; i += MEGA_CTHREADS) a.x[0][i] = ldcg_f(a.x[cur] + i);
+        }
+    }
+}
+
+} // namespace q3
