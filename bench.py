@@ -332,27 +332,38 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel, timed alone ----
+    # ---- roofline ----
     peak, peak_src = measured_peak_gbs()
-    roof = None
-    kernels = {}
-    try:
-        for kind in ("gate_up", "down", "qkv", "o_proj", "lm_head"):
-            ms, nbytes, n = m.bench_kernel(kind, 0, reps=3 if kind != "lm_head" else 1)
-            kernels[kind] = {"us": ms * 1e3, "GBps": nbytes / ms / 1e6, "bytes": nbytes}
-        g = kernels["gate_up"]
-        roof = {"bound": "hbm", "kernel": "gate/up int8 GEMV + SwiGLU (%s)" % ("mega" if False else "k_gemv<EPI_SWIGLU>"),
-                "achieved": g["GBps"], "peak": peak, "unit": "GB/s", "frac": g["GBps"] / peak,
-                "traffic": ncu_traffic("gate_up"), "bytes_per_launch": g["bytes"], "us_per_launch": g["us"],
-                "peak_source": peak_src}
-    except Exception as e:  # noqa: BLE001
-        log(f"[bench] kernel roofline failed: {e}")
     mean_pos = pos_start + (n_tok - 1) / 2.0
     btok = shape.bytes_per_token(args.group_size, int(mean_pos)) / tp
     tok_ms = dev_ms / n_tok
     token_roof = {"bytes_per_token_per_gpu": btok, "achieved": btok / tok_ms / 1e6, "peak": peak, "unit": "GB/s",
                   "frac": btok / tok_ms / 1e6 / peak, "frac_of_8TBps": btok / tok_ms / 1e6 / 8000.0,
                   "us_per_token": tok_ms * 1e3, "mean_pos": mean_pos}
+    roof = None
+    kernels = {}
+    persistent = m.launches_per_step == 1
+    try:
+        if persistent:
+            # the whole decode step is ONE launch of k_mega_decode: algorithmic bytes per launch = bytes per
+            # token (weights + scales + f32 KV rows read), duration = CUDA-event time per launch measured
+            # over the timed region above
+            roof = {"bound": "hbm", "kernel": "k_mega_decode (persistent single-launch decode step)",
+                    "achieved": token_roof["achieved"], "peak": peak, "unit": "GB/s", "frac": token_roof["frac"],
+                    "traffic": ncu_traffic("mega"), "bytes_per_launch": btok, "us_per_launch": tok_ms * 1e3,
+                    "peak_source": peak_src}
+        m.set_decode_path(0)
+        for kind in ("gate_up", "down", "qkv", "o_proj", "lm_head"):
+            ms, nbytes, n = m.bench_kernel(kind, 0, reps=3 if kind != "lm_head" else 1)
+            kernels[kind] = {"us": ms * 1e3, "GBps": nbytes / ms / 1e6, "bytes": nbytes}
+        if not persistent:
+            g = kernels["gate_up"]
+            roof = {"bound": "hbm", "kernel": "gate/up int8 GEMV + SwiGLU (k_gemv<EPI_SWIGLU>)",
+                    "achieved": g["GBps"], "peak": peak, "unit": "GB/s", "frac": g["GBps"] / peak,
+                    "traffic": ncu_traffic("gate_up"), "bytes_per_launch": g["bytes"], "us_per_launch": g["us"],
+                    "peak_source": peak_src}
+    except Exception as e:  # noqa: BLE001
+        log(f"[bench] kernel roofline failed: {e}")
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -375,7 +386,8 @@ def main():
                 "tokens_timed": e2e_tokens, "path": "Transformer.forward -> host logits -> host argmax (sampler.rs)"},
         "gpu_launches": m.launches_per_step * n_tok,
         "launches_per_token": m.launches_per_step,
-        "clocks": clk, "roofline": roof, "token_roofline": token_roof, "kernels": kernels, "cpu_baseline": cpu,
+        "clocks": clk, "roofline": roof, "token_roofline": token_roof, "graph_path_kernels": kernels, "cpu_baseline": cpu,
+        "decode_path": "persistent" if persistent else "graph",
     }
     print(json.dumps(out), flush=True)
     m.close()

@@ -135,6 +135,10 @@ int q3_bench_decode(q3_handle *h, int first_token, int pos0, int steps, float *m
  * number of launches, algorithmic bytes per launch (weights + scales, or K/V rows read). */
 int q3_bench_kernel(q3_handle *h, int kind, int pos, int reps, float *ms_out, int *launches_out,
                     double *bytes_per_launch_out);
+/* Developer aid: one decode step of the persistent kernel with per-CTA clock64 stamps at every
+ * phase boundary (14 per layer: prologue / GEMV / barrier of the 5 phases; attention has no
+ * prologue).  out: [num_SMs][1024] u64 SM cycles. */
+int q3_debug_profile(q3_handle *h, int token, int pos, unsigned long long *out, int *n_events_out);
 /* Number of kernel launches one decode step issues on the current path. */
 int q3_launches_per_step(const q3_handle *h);
 

@@ -95,7 +95,7 @@ struct q3_handle {
     MegaArgs margs{};
     unsigned long long bar_base = 0;
     unsigned int xepoch = 0;
-    int *h_status = nullptr;  // mapped pinned: kernel-side abort flag
+    int *d_status = nullptr;  // device abort flag raised by a timed-out wait inside the kernel
     float *x2 = nullptr, *kraw = nullptr, *part_buf[2] = {nullptr, nullptr};
     unsigned long long *d_best = nullptr, *d_bar = nullptr;
     unsigned int *d_flags = nullptr;
@@ -556,10 +556,9 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
     if ((rc = dmalloc(h, (void **)&h->d_flags, 64 * 4))) return rc;
     CK(cudaMemset(h->d_bar, 0, 64));
     CK(cudaMemset(h->d_flags, 0, 64 * 4));
-    CK(cudaHostAlloc((void **)&h->h_status, 64, cudaHostAllocMapped));
-    *h->h_status = 0;
-    int *d_status = nullptr;
-    CK(cudaHostGetDevicePointer((void **)&d_status, h->h_status, 0));
+    if ((rc = dmalloc(h, (void **)&h->d_status, 64))) return rc;
+    CK(cudaMemset(h->d_status, 0, 64));
+    int *d_status = h->d_status;
     a.x[0] = h->x; a.x[1] = h->x2;
     a.q = h->q; a.kraw = h->kraw; a.hb = h->hb; a.attn_part = h->attn_part;
     a.bar = h->d_bar; a.status = d_status; a.tokpos = h->d_tokpos; a.history = h->d_history;
@@ -570,8 +569,8 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
     }
     GS_DISPATCH(gs, (h->mega_fn = mega_kernel_for<GS>(h->kv_mul)));
     if (!h->mega_fn) { h->mega_why = "no kernel for this GQA factor"; return 0; }
-    const size_t slot = (size_t)MEGA_NCW * (MEGA_MAX_KT + 4 * (MEGA_MAX_KT / gs));
-    h->mega_smem = MEGA_NSTAGE * slot + MEGA_SCRATCH + 256;
+    const size_t slot = (size_t)MEGA_GW * (MEGA_MAX_KT + 4 * (MEGA_MAX_KT / gs));
+    h->mega_smem = MEGA_NSTAGE * slot + MEGA_SCRATCH + 128 + sizeof(MegaShared) + 64;
     CK(cudaFuncSetAttribute(h->mega_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mega_smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->mega_fn, MEGA_THREADS, h->mega_smem));
@@ -596,16 +595,42 @@ static int launch_mega(q3_handle *h, int l0, int l1, bool from_embed, bool run_h
     return 0;
 }
 
+// after a synchronize: did any in-kernel wait time out?
 static int mega_check(q3_handle *h) {
-    if (h->h_status && *h->h_status) {
-        int code = *h->h_status;
-        *h->h_status = 0;
+    if (!h->d_status || h->decode_path != 1) return 0;
+    int code = 0;
+    CK(cudaMemcpy(&code, h->d_status, 4, cudaMemcpyDeviceToHost));
+    if (code) {
+        cudaMemset(h->d_status, 0, 64);
         h->bar_base = 0;
         cudaMemset(h->d_bar, 0, 64);
-        return fail(Q3_ECUDA, "megakernel wait timed out (status %d: 1 grid barrier, 2 stage ring, 3 peer flag)", code);
+        return fail(Q3_ECUDA, "persistent decode kernel: a wait timed out (status %d: 1 grid barrier, 2 stage ring, 3 peer flag)", code);
     }
     return 0;
 }
+extern "C" int q3_debug_profile(q3_handle *h, int token, int pos, unsigned long long *out, int *n_events_out) {
+    if (!h || !out) return fail(Q3_EINVAL, "null argument");
+    if (!h->mega_ok) return fail(Q3_EUNSUPPORTED, "persistent decode kernel unavailable: %s", h->mega_why.c_str());
+    CK(cudaSetDevice(h->device));
+    h->h_small[0] = token; h->h_small[1] = pos; h->h_small[2] = 0; h->h_small[3] = 0;
+    CK(cudaMemcpyAsync(h->d_tokpos, h->h_small, 16, cudaMemcpyHostToDevice, h->stream));
+    unsigned long long *d = nullptr;
+    size_t bytes = (size_t)h->num_sms * MEGA_PROF_EVENTS * 8;
+    CK(cudaMalloc((void **)&d, bytes));
+    CK(cudaMemsetAsync(d, 0, bytes, h->stream));
+    h->margs.prof = d;
+    int rc = launch_mega(h, 0, h->cfg.n_layers, true, true, false, false);
+    h->margs.prof = nullptr;
+    if (!rc) {
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e == cudaSuccess) e = cudaMemcpy(out, d, bytes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(Q3_ECUDA, "profile run failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    if (n_events_out) *n_events_out = 1 + 15 * h->cfg.n_layers + 3;
+    return rc;
+}
+
 static inline bool use_mega(const q3_handle *h) { return h->decode_path == 1 && h->mega_ok && !h->exact; }
 
 // ------------------------------------------------------------------------------------------
@@ -771,7 +796,6 @@ extern "C" void q3_destroy(q3_handle *h) {
     for (void *p : h->allocs) cudaFree(p);
     if (h->h_logits) cudaFreeHost(h->h_logits);
     if (h->h_small) cudaFreeHost(h->h_small);
-    if (h->h_status) cudaFreeHost(h->h_status);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }

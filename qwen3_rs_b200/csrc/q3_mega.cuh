@@ -22,14 +22,18 @@
 
 namespace q3 {
 
-constexpr int MEGA_NCW = 8;                         // consumer warps
-constexpr int MEGA_CTHREADS = MEGA_NCW * 32;        // 256 consumer threads
+constexpr int MEGA_GW = 8;                          // consumer warps per group = row tiles per stage
+constexpr int MEGA_GROUPS = 2;                      // consumer groups; stages alternate between them
+constexpr int MEGA_NCW = MEGA_GW * MEGA_GROUPS;     // 16 consumer warps
+constexpr int MEGA_CTHREADS = MEGA_NCW * 32;        // 512 consumer threads
 constexpr int MEGA_THREADS = MEGA_CTHREADS + 32;    // + producer warp
 constexpr int MEGA_NSTAGE = 5;
 constexpr int MEGA_MAX_KT = 4096;
 constexpr int MEGA_SCRATCH = 40960;                 // xq/xs or attention buffers
 constexpr int MEGA_MAX_TP = 8;
 constexpr int MEGA_MAX_SPLITS = ATTN_MAX_SPLITS;
+constexpr long long MEGA_L2_AHEAD = 0;              // bytes per CTA the L2 prefetch cursor runs ahead of the ring (0 = off:
+                                                    // measured SLOWER on B200 -- the extra L2 fill traffic delays the consumers' activation loads)
 
 enum { PH_QKV = 0, PH_O = 1, PH_GU = 2, PH_DN = 3, PH_HEAD = 4 };
 
@@ -62,7 +66,15 @@ struct MegaArgs {
     int *tokpos, *history;
     int *status;                     // != 0: a wait timed out (kernel aborts)
     int layer0, layer1, from_embed, run_head, feedback, gather_logits;
+    unsigned long long *prof;        // optional [grid][MEGA_PROF_EVENTS] clock64 stamps (thread 0 of each CTA)
 };
+constexpr int MEGA_PROF_EVENTS = 1024;
+__device__ __forceinline__ void prof_mark(const MegaArgs &a, int &ev) {
+    if (a.prof && threadIdx.x == 0 && ev < MEGA_PROF_EVENTS) {
+        a.prof[(size_t)blockIdx.x * MEGA_PROF_EVENTS + ev] = (unsigned long long)clock64();
+    }
+    ev++;
+}
 
 // ------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + bulk copy
@@ -85,13 +97,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
                  : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *status) {
+// Waits never hang the GPU: after ~2 s (a scheduling bug, not a stall) the waiter raises the abort
+// flag (device memory, polled only every 4096 spins) and everybody falls through.
+__device__ __noinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *status) {
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = clock64();
+    unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL || *(volatile int *)status) { // ~2 s: a scheduling bug, not a stall
-            atomicExch(status, 2);
-            return;
+        if ((++spins & 4095u) == 0) {
+            if (*(volatile int *)status) return;
+            if (clock64() - t0 > 4000000000LL) {
+                atomicExch(status, 2);
+                return;
+            }
         }
     }
 }
@@ -199,9 +217,13 @@ __device__ __forceinline__ float tile_dot(const uint8_t *tile, const XRegs<GS> &
         if (ngb > 32) ngb = 32;
         if (lane < ngb) { // ngb <= 0 -> nobody
             const int4 *wp = reinterpret_cast<const int4 *>(tile) + b * 32 * CPG + lane;
-            int d = 0;
+            int d0 = 0, d1 = 0; // two independent dp4a chains; int32 addition is exact in any order
 #pragma unroll
-            for (int p = 0; p < CPG; p++) d = dot16(wp[p * ngb], xr.x[b][p], d);
+            for (int p = 0; p < CPG; p += 2) {
+                d0 = dot16(wp[p * ngb], xr.x[b][p], d0);
+                d1 = dot16(wp[(p + 1) * ngb], xr.x[b][p + 1], d1);
+            }
+            const int d = d0 + d1;
             acc = __fadd_rn(acc, __fmul_rn(__fmul_rn((float)d, ws[b * 32 + lane]), xr.s[b]));
         }
     }
@@ -213,7 +235,7 @@ __device__ __forceinline__ float tile_dot(const uint8_t *tile, const XRegs<GS> &
 // x <- x + sum_r part[r], ResidualConnection layers.rs:249-259; under TP this IS the all-reduce,
 // summed in rank order so every rank computes bit-identical x) and gathers the embedding row.
 template <int GS>
-__device__ __forceinline__ void prologue_norm(const MegaArgs &a, const float *w, bool from_embed, const float *const *parts,
+__device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, bool from_embed, const float *const *parts,
                                               int &cur, uint8_t *sxq, float *sxs, float *sred, bool write_normed) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n4 = a.dim >> 2;
@@ -236,6 +258,7 @@ __device__ __forceinline__ void prologue_norm(const MegaArgs &a, const float *w,
             } else {
                 v[k] = ldcg_f4(xin + (size_t)i4 * 4);
                 if (merge) {
+#pragma unroll 1
                     for (int r = 0; r < a.tp_size; r++) {
                         float4 p = ldcg_f4(parts[a.tp_rank] + (size_t)r * a.dim + (size_t)i4 * 4);
                         v[k].x = __fadd_rn(v[k].x, p.x);
@@ -253,6 +276,12 @@ __device__ __forceinline__ void prologue_norm(const MegaArgs &a, const float *w,
         }
     }
     if (merge && !from_embed) cur ^= 1;
+    float4 wv[MAXV]; // norm weights: issue the loads before the reduction so their latency overlaps it
+#pragma unroll
+    for (int k = 0; k < MAXV; k++) {
+        int i4 = tid + k * MEGA_CTHREADS;
+        wv[k] = (i4 < n4) ? __ldg(reinterpret_cast<const float4 *>(w) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     ss = warp_sum(ss);
     if (lane == 0) sred[warp] = ss;
     csync();
@@ -266,11 +295,10 @@ __device__ __forceinline__ void prologue_norm(const MegaArgs &a, const float *w,
         if (i4 - lane < n4) {
             float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i4 < n4) {
-                float4 wv = __ldg(reinterpret_cast<const float4 *>(w) + i4);
-                y.x = __fmul_rn(wv.x, __fmul_rn(f, v[k].x));
-                y.y = __fmul_rn(wv.y, __fmul_rn(f, v[k].y));
-                y.z = __fmul_rn(wv.z, __fmul_rn(f, v[k].z));
-                y.w = __fmul_rn(wv.w, __fmul_rn(f, v[k].w));
+                y.x = __fmul_rn(wv[k].x, __fmul_rn(f, v[k].x));
+                y.y = __fmul_rn(wv[k].y, __fmul_rn(f, v[k].y));
+                y.z = __fmul_rn(wv[k].z, __fmul_rn(f, v[k].z));
+                y.w = __fmul_rn(wv[k].w, __fmul_rn(f, v[k].w));
             }
             uint32_t packed;
             float scale;
@@ -285,14 +313,20 @@ __device__ __forceinline__ void prologue_norm(const MegaArgs &a, const float *w,
     csync();
 }
 
-// quantise an f32 vector in global memory (written by other CTAs) into shared memory
+// quantise an f32 vector in global memory (written by other CTAs) into shared memory.
+// Rolled loop (one copy of the quantiser in the instruction stream) with the next load in flight
+// while the current float4 is processed.
 template <int GS>
-__device__ __forceinline__ void prologue_quant(const float *src, int n, uint8_t *sxq, float *sxs) {
+__device__ __noinline__ void prologue_quant(const float *src, int n, uint8_t *sxq, float *sxs) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int n4 = n >> 2;
-    for (int base = tid - lane; base < n4; base += MEGA_CTHREADS) {
-        int i4 = base + lane;
-        float4 y = (i4 < n4) ? ldcg_f4(src + (size_t)i4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int i4 = tid;
+    float4 nxt = (i4 < n4) ? ldcg_f4(src + (size_t)i4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (; i4 - lane < n4; i4 += MEGA_CTHREADS) {
+        const float4 y = nxt;
+        const int j4 = i4 + MEGA_CTHREADS;
+        nxt = (j4 < n4) ? ldcg_f4(src + (size_t)j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t packed;
         float scale;
         quantize_group4<GS>(y, packed, scale);
@@ -306,9 +340,43 @@ __device__ __forceinline__ void prologue_quant(const float *src, int n, uint8_t 
 
 // merge the attention split partials (k_attn_combine_quant's math) and quantise into shared memory
 template <int GS>
-__device__ __forceinline__ void prologue_attn_out(const MegaArgs &a, int nsplit, uint8_t *sxq, float *sxs) {
+__device__ __noinline__ void prologue_attn_out(const MegaArgs &a, int nsplit, uint8_t *sxq, float *sxs) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int n4 = a.AH_l >> 2;
+    if (nsplit == 1) { // short context: one partial per head; exp(m - M) == 1.  Rolled, next loads in flight.
+        int i4 = tid;
+        float4 An = make_float4(0.f, 0.f, 0.f, 0.f);
+        float Ln = 1.0f;
+        if (i4 < n4) {
+            const float *pb = a.attn_part + (size_t)(i4 >> 5) * MEGA_MAX_SPLITS * ATTN_PART_STRIDE;
+            An = ldcg_f4(pb + (i4 & 31) * 4);
+            Ln = ldcg_f(pb + HEAD_DIM + 1);
+        }
+#pragma unroll 1
+        for (; i4 - lane < n4; i4 += MEGA_CTHREADS) {
+            const float4 A = An;
+            const float Lc = Ln;
+            const int j4 = i4 + MEGA_CTHREADS;
+            if (j4 < n4) {
+                const float *pb = a.attn_part + (size_t)(j4 >> 5) * MEGA_MAX_SPLITS * ATTN_PART_STRIDE;
+                An = ldcg_f4(pb + (j4 & 31) * 4);
+                Ln = ldcg_f(pb + HEAD_DIM + 1);
+            }
+            // split 0 holds sum_t exp(s_t - m) v_t and l = sum_t exp(s_t - m); c = exp(m - M) = 1 exactly
+            float inv = __fdiv_rn(1.0f, Lc);
+            float4 y = make_float4(__fmul_rn(A.x, inv), __fmul_rn(A.y, inv), __fmul_rn(A.z, inv), __fmul_rn(A.w, inv));
+            uint32_t packed;
+            float scale;
+            quantize_group4<GS>(y, packed, scale);
+            if (i4 < n4) {
+                reinterpret_cast<uint32_t *>(sxq)[i4] = packed;
+                if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
+            }
+        }
+        csync();
+        return;
+    }
+#pragma unroll 1
     for (int base = tid - lane; base < n4; base += MEGA_CTHREADS) {
         int i4 = base + lane;
         float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -379,9 +447,10 @@ __device__ __forceinline__ float4 qk_norm_rope(float4 v, const float *w, const f
     return r;
 }
 
+constexpr int MEGA_ATTN_CHUNK = 64; // positions per split before another CTA is recruited
 __device__ __forceinline__ int mega_nsplit(int pos, int n_kv_l, int grid) {
     int n = pos + 1;
-    int ns = (n + ATTN_MIN_CHUNK - 1) / ATTN_MIN_CHUNK;
+    int ns = (n + MEGA_ATTN_CHUNK - 1) / MEGA_ATTN_CHUNK;
     int cap = grid / n_kv_l;
     if (cap > MEGA_MAX_SPLITS) cap = MEGA_MAX_SPLITS;
     if (cap < 1) cap = 1;
@@ -390,14 +459,15 @@ __device__ __forceinline__ int mega_nsplit(int pos, int n_kv_l, int grid) {
 
 // attention phase for one (kv head, split) work item; all 256 consumer threads.
 template <int KVMUL>
-__device__ __forceinline__ void attention_item(const MegaArgs &a, int layer, int pos, int kvh, int split, int nsplit,
+__device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int pos, int kvh, int split, int nsplit,
                                                uint8_t *scratch) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NATT = (KVMUL * MEGA_NCW * 512 + 8192 <= MEGA_SCRATCH) ? MEGA_NCW : MEGA_GW; // warps in the position loop
     float4 *sq = reinterpret_cast<float4 *>(scratch);                 // [KVMUL][32]
     float4 *sk = sq + KVMUL * 32;                                     // [32]
-    float *sm_m = reinterpret_cast<float *>(sk + 32);                 // [8][KVMUL]
-    float *sm_l = sm_m + MEGA_NCW * KVMUL;                            // [8][KVMUL]
-    float4 *sm_acc = reinterpret_cast<float4 *>(sm_l + MEGA_NCW * KVMUL); // [8][KVMUL][32]
+    float *sm_m = reinterpret_cast<float *>(sk + 32);                 // [NATT][KVMUL]
+    float *sm_l = sm_m + NATT * KVMUL;                                // [NATT][KVMUL]
+    float4 *sm_acc = reinterpret_cast<float4 *>(sm_l + NATT * KVMUL); // [NATT][KVMUL][32]
     const int n = pos + 1;
     const int per = (n + nsplit - 1) / nsplit;
     const int t0 = split * per;
@@ -433,44 +503,61 @@ __device__ __forceinline__ void attention_item(const MegaArgs &a, int layer, int
     }
     const float *kbase = kc_l + (size_t)kvh * HEAD_DIM + lane * 4;
     const float *vbase = vc_l + (size_t)kvh * HEAD_DIM + lane * 4;
-    for (int t = t0 + warp; t < t1; t += MEGA_NCW) {
-        float4 kv = (t == pos) ? sk[lane] : ldcg_f4(kbase + (size_t)t * a.KV_l);
-        float4 vv = ldcg_f4(vbase + (size_t)t * a.KV_l);
-        float s[KVMUL];
-#pragma unroll
-        for (int h = 0; h < KVMUL; h++) s[h] = qv[h].x * kv.x + qv[h].y * kv.y + qv[h].z * kv.z + qv[h].w * kv.w;
-#pragma unroll
-        for (int h = 0; h < KVMUL; h++) s[h] = __fmul_rn(warp_sum(s[h]), scale);
+    // two positions per iteration: both K/V row loads are in flight before either is used
+    for (int t = t0 + warp; t < t1 && warp < NATT; t += 2 * NATT) {
+        const int tb = t + NATT;
+        const bool hasb = tb < t1;
+        float4 kva = (t == pos) ? sk[lane] : ldcg_f4(kbase + (size_t)t * a.KV_l);
+        float4 vva = ldcg_f4(vbase + (size_t)t * a.KV_l);
+        float4 kvb = make_float4(0.f, 0.f, 0.f, 0.f), vvb = kvb;
+        if (hasb) {
+            kvb = (tb == pos) ? sk[lane] : ldcg_f4(kbase + (size_t)tb * a.KV_l);
+            vvb = ldcg_f4(vbase + (size_t)tb * a.KV_l);
+        }
+        float sa[KVMUL], sb[KVMUL];
 #pragma unroll
         for (int h = 0; h < KVMUL; h++) {
-            float mn = fmaxf(m[h], s[h]);
+            sa[h] = qv[h].x * kva.x + qv[h].y * kva.y + qv[h].z * kva.z + qv[h].w * kva.w;
+            sb[h] = qv[h].x * kvb.x + qv[h].y * kvb.y + qv[h].z * kvb.z + qv[h].w * kvb.w;
+        }
+#pragma unroll
+        for (int h = 0; h < KVMUL; h++) {
+            sa[h] = __fmul_rn(warp_sum(sa[h]), scale);
+            sb[h] = hasb ? __fmul_rn(warp_sum(sb[h]), scale) : -INFINITY;
+        }
+#pragma unroll
+        for (int h = 0; h < KVMUL; h++) {
+            float mn = fmaxf(m[h], fmaxf(sa[h], sb[h]));
             float corr = expf(m[h] - mn);
-            float p = expf(s[h] - mn);
-            l[h] = l[h] * corr + p;
-            acc[h].x = acc[h].x * corr + p * vv.x;
-            acc[h].y = acc[h].y * corr + p * vv.y;
-            acc[h].z = acc[h].z * corr + p * vv.z;
-            acc[h].w = acc[h].w * corr + p * vv.w;
+            float pa = expf(sa[h] - mn);
+            float pb = hasb ? expf(sb[h] - mn) : 0.0f;
+            l[h] = l[h] * corr + pa + pb;
+            acc[h].x = acc[h].x * corr + pa * vva.x + pb * vvb.x;
+            acc[h].y = acc[h].y * corr + pa * vva.y + pb * vvb.y;
+            acc[h].z = acc[h].z * corr + pa * vva.z + pb * vvb.z;
+            acc[h].w = acc[h].w * corr + pa * vva.w + pb * vvb.w;
             m[h] = mn;
         }
     }
+    if (warp < NATT) {
 #pragma unroll
-    for (int h = 0; h < KVMUL; h++) {
-        if (lane == 0) {
-            sm_m[warp * KVMUL + h] = m[h];
-            sm_l[warp * KVMUL + h] = l[h];
+        for (int h = 0; h < KVMUL; h++) {
+            if (lane == 0) {
+                sm_m[warp * KVMUL + h] = m[h];
+                sm_l[warp * KVMUL + h] = l[h];
+            }
+            sm_acc[(warp * KVMUL + h) * 32 + lane] = acc[h];
         }
-        sm_acc[(warp * KVMUL + h) * 32 + lane] = acc[h];
     }
     csync();
     for (int h = warp; h < KVMUL; h += MEGA_NCW) {
         float M = -INFINITY;
-#pragma unroll
-        for (int w = 0; w < MEGA_NCW; w++) M = fmaxf(M, sm_m[w * KVMUL + h]);
+#pragma unroll 1
+        for (int w = 0; w < NATT; w++) M = fmaxf(M, sm_m[w * KVMUL + h]);
         float L = 0.0f;
         float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int w = 0; w < MEGA_NCW; w++) {
+#pragma unroll 1
+        for (int w = 0; w < NATT; w++) {
             float mw = sm_m[w * KVMUL + h];
             float c = (mw == -INFINITY) ? 0.0f : expf(mw - M);
             L += sm_l[w * KVMUL + h] * c;
@@ -497,7 +584,7 @@ struct BarState {
     unsigned int xepoch;       // cross-GPU epoch of the next exchange barrier
 };
 
-__device__ __forceinline__ void grid_barrier(const MegaArgs &a, BarState &bs, bool cross) {
+__device__ __noinline__ void grid_barrier(const MegaArgs &a, BarState &bs, bool cross) {
     csync();
     if (threadIdx.x == 0) {
         if (cross && a.tp_size > 1) __threadfence_system();
@@ -505,14 +592,17 @@ __device__ __forceinline__ void grid_barrier(const MegaArgs &a, BarState &bs, bo
         atomicAdd(a.bar, 1ULL);
         long long t0 = clock64();
         volatile int *st = a.status;
+        unsigned spins = 0;
         while (true) {
             unsigned long long v;
             asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
             if (v >= bs.target) break;
-            if (*st) break;
-            if (clock64() - t0 > 4000000000LL) {
-                atomicExch(a.status, 1);
-                break;
+            if ((++spins & 1023u) == 0) {
+                if (*st) break;
+                if (clock64() - t0 > 4000000000LL) {
+                    atomicExch(a.status, 1);
+                    break;
+                }
             }
         }
         if (cross && a.tp_size > 1) {
@@ -527,10 +617,12 @@ __device__ __forceinline__ void grid_barrier(const MegaArgs &a, BarState &bs, bo
                     unsigned int v;
                     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flags[a.tp_rank] + r) : "memory");
                     if ((int)(v - e) >= 0) break;
-                    if (*st) break;
-                    if (clock64() - t0 > 8000000000LL) {
-                        atomicExch(a.status, 3);
-                        break;
+                    if ((++spins & 1023u) == 0) {
+                        if (*st) break;
+                        if (clock64() - t0 > 8000000000LL) {
+                            atomicExch(a.status, 3);
+                            break;
+                        }
                     }
                 }
             }
@@ -548,11 +640,19 @@ struct PhaseGeom {
     const uint8_t *seg; // this CTA's segment of the phase stream
     int start, count;   // units owned by this CTA
 };
-__device__ __forceinline__ PhaseGeom phase_geom(const MegaGemv &g, int layer, int pair) {
+// per-CTA constants computed once (integer divisions are ~40 instructions each on the GPU)
+struct MegaShared {
+    int start[5], count[5];
+    long long seg_off[5], seg_len[5];
+    float *part[2][MEGA_MAX_TP];
+    float *logits[MEGA_MAX_TP];
+    unsigned long long *best[MEGA_MAX_TP];
+};
+__device__ __forceinline__ PhaseGeom phase_geom(const MegaArgs &a, const MegaShared &sh, int ph, int layer) {
     PhaseGeom pg;
-    cta_share(g.units, gridDim.x, blockIdx.x, pg.start, pg.count);
-    pg.seg = g.base + (long long)layer * g.layer_stride +
-             (long long)pg.start * (pair ? 2 : 1) * g.n_kt * (long long)g.tile_bytes;
+    pg.start = sh.start[ph];
+    pg.count = sh.count[ph];
+    pg.seg = a.g[ph].base + (long long)layer * a.g[ph].layer_stride + sh.seg_off[ph];
     return pg;
 }
 
@@ -560,22 +660,39 @@ template <int GS, int KVMUL>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_constant__ MegaArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // layout: [ring: NSTAGE x slot][scratch][barriers]
-    const int slot_bytes = MEGA_NCW * (MEGA_MAX_KT + 4 * (MEGA_MAX_KT / GS));
+    const int slot_bytes = MEGA_GW * (MEGA_MAX_KT + 4 * (MEGA_MAX_KT / GS));
     uint8_t *ring = smem;
     uint8_t *scratch = smem + MEGA_NSTAGE * slot_bytes;
     uint8_t *sxq = scratch;                                          // up to 16384 B
     float *sxs = reinterpret_cast<float *>(scratch + 16384);         // up to 512 groups
-    float *sred = reinterpret_cast<float *>(scratch + 16384 + 2048); // 8 floats (+ argmax scratch)
+    float *sred = reinterpret_cast<float *>(scratch + 16384 + 2048); // 16 floats (+ argmax scratch at +32)
     uint64_t *full = reinterpret_cast<uint64_t *>(scratch + MEGA_SCRATCH);
     uint64_t *empty = full + MEGA_NSTAGE;
+    MegaShared &sh = *reinterpret_cast<MegaShared *>(scratch + MEGA_SCRATCH + 128);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
         for (int s = 0; s < MEGA_NSTAGE; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], MEGA_NCW);
+            mbar_init(&empty[s], MEGA_GW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll 1
+        for (int ph = 0; ph < 5; ph++) {
+            int st, cn;
+            cta_share(a.g[ph].units, gridDim.x, blockIdx.x, st, cn);
+            const long long per_unit = (long long)(ph == PH_GU ? 2 : 1) * a.g[ph].n_kt * a.g[ph].tile_bytes;
+            sh.start[ph] = st;
+            sh.count[ph] = cn;
+            sh.seg_off[ph] = st * per_unit;
+            sh.seg_len[ph] = cn * per_unit;
+        }
+    }
+    if (tid < MEGA_MAX_TP) {
+        sh.part[0][tid] = a.part[0][tid];
+        sh.part[1][tid] = a.part[1][tid];
+        sh.logits[tid] = a.logits[tid];
+        sh.best[tid] = a.best[tid];
     }
     __syncthreads();
 
@@ -587,17 +704,60 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
         uint64_t policy;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
         unsigned it = 0;
+        // L2 prefetch cursor.  The shared-memory ring alone (5 x 34 KB per SM) cannot keep enough
+        // bytes in flight to saturate HBM at its loaded latency, and it stalls whenever the consumers
+        // sit in a barrier or a prologue.  So a second cursor walks the same byte stream
+        // MEGA_L2_AHEAD bytes in front of the ring's fill pointer -- across phase and layer
+        // boundaries, weights being static -- and pulls it into L2 with cp.async.bulk.prefetch.L2;
+        // the ring then fills from L2.
+        int pf_l = L0, pf_ph = PH_QKV; // segment the cursor is in (PH_HEAD: pf_l unused)
+        const uint8_t *pf_ptr = nullptr;
+        long long pf_left = 0;
+        bool pf_done = false;
+        auto pf_open = [&]() {
+            PhaseGeom pg = phase_geom(a, sh, pf_ph, pf_ph == PH_HEAD ? 0 : pf_l);
+            pf_ptr = pg.seg;
+            pf_left = sh.seg_len[pf_ph];
+        };
+        auto pf_next_segment = [&]() {
+            if (pf_ph == PH_HEAD) { pf_done = true; return; }
+            if (pf_ph == PH_DN) {
+                pf_l++;
+                if (pf_l < L1) pf_ph = PH_QKV;
+                else if (a.run_head) pf_ph = PH_HEAD;
+                else { pf_done = true; return; }
+            } else {
+                pf_ph++;
+            }
+            pf_open();
+        };
+        auto pf_advance = [&](long long bytes) {
+            while (bytes > 0 && !pf_done) {
+                if (pf_left == 0) { pf_next_segment(); continue; }
+                long long chunk = bytes < pf_left ? bytes : pf_left;
+                if (chunk > 65536) chunk = 65536;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf_ptr), "r"((unsigned)chunk) : "memory");
+                pf_ptr += chunk;
+                pf_left -= chunk;
+                bytes -= chunk;
+            }
+        };
+        if (L1 > L0) pf_open();
+        else if (a.run_head) { pf_ph = PH_HEAD; pf_open(); }
+        else pf_done = true;
+        if (MEGA_L2_AHEAD > 0) pf_advance(MEGA_L2_AHEAD + (long long)MEGA_NSTAGE * slot_bytes);
         auto push = [&](const uint8_t *src, int nr, int tile_bytes) {
             const int slot = it % MEGA_NSTAGE;
             mbar_wait(&empty[slot], ((it / MEGA_NSTAGE) & 1) ^ 1, a.status);
             const uint32_t bytes = (uint32_t)nr * tile_bytes;
             mbar_expect_tx(&full[slot], bytes);
             bulk_g2s(ring + (size_t)slot * slot_bytes, src, bytes, &full[slot], policy);
+            if (MEGA_L2_AHEAD > 0) pf_advance(bytes);
             it++;
         };
         auto plain = [&](int ph, int layer) {
             const MegaGemv &g = a.g[ph];
-            PhaseGeom pg = phase_geom(g, layer, 0);
+            PhaseGeom pg = phase_geom(a, sh, ph, layer);
             const uint8_t *src = pg.seg;
             for (int b0 = 0; b0 < pg.count; b0 += 32) {
                 int nb = pg.count - b0 < 32 ? pg.count - b0 : 32;
@@ -611,7 +771,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
         };
         auto pairs = [&](int layer) {
             const MegaGemv &g = a.g[PH_GU];
-            PhaseGeom pg = phase_geom(g, layer, 1);
+            PhaseGeom pg = phase_geom(a, sh, PH_GU, layer);
             const uint8_t *src = pg.seg;
             for (int p0 = 0; p0 < pg.count; p0 += 8) {
                 int np = pg.count - p0 < 8 ? pg.count - p0 : 8;
@@ -632,137 +792,163 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
     }
 
     // =============================== CONSUMERS ===============================
+    // The forward pass is walked as a flat sequence of steps (5 per layer + the head) through ONE
+    // copy of each code path: the per-token instruction footprint has to stay inside the
+    // instruction cache -- an earlier version that inlined a GEMV loop per phase was 340 KB of SASS
+    // and spent more time fetching instructions (through the same L2 the weights stream through)
+    // than computing.
     unsigned it = 0;
     BarState bs;
     bs.target = a.bar_base + gridDim.x;
     bs.xepoch = a.xepoch_base + 1;
     const int pos = a.tokpos[1];
+    const int grp = warp / MEGA_GW, wl = warp % MEGA_GW; // consumer group and warp-in-group (= row tile in a stage)
     int cur = 0;
+    int ev = 0;
     XRegs<GS> xr;
+    prof_mark(a, ev); // 0: start
+    long long best = (long long)0x8000000000000000LL;
+    const int n_layer_steps = 5 * (L1 - L0);
+    const int n_steps = n_layer_steps + (a.run_head ? 1 : 0);
+    int nsplit = 1;
 
-    // generic row phase: rows -> value; EPI(row_local_index, value) by lane 0
-    auto run_plain = [&](int ph, int layer, auto &&epi) {
-        const MegaGemv &g = a.g[ph];
-        int start, count;
-        cta_share(g.units, gridDim.x, blockIdx.x, start, count);
-        for (int b0 = 0; b0 < count; b0 += 32) {
-            const int nb = count - b0 < 32 ? count - b0 : 32;
-            float accs[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int kt = 0; kt < g.n_kt; kt++) {
-                load_x<GS>(xr, sxq, sxs, kt, g.KT, g.G, lane);
-#pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    if (8 * s < nb) {
+    for (int step = 0; step < n_steps; step++) {
+        const bool head = step >= n_layer_steps;
+        const int l = head ? 0 : L0 + step / 5;
+        const int kind = head ? 5 : step % 5; // 0 qkv, 1 attention, 2 o_proj, 3 gate/up, 4 down, 5 lm_head
+        bool cross = false;
+        int ph = PH_QKV;
+        // ------------------------------ prologue ------------------------------
+        if (kind == 0 || kind == 3 || kind == 5) {
+            // RMSNorm + quantize of the residual stream (qwen3.rs:134-136, 159-161, 72-75)
+            const float *w = kind == 0 ? a.rms_att + (size_t)l * a.dim : kind == 3 ? a.rms_ffn + (size_t)l * a.dim : a.rms_final;
+            const bool emb = kind == 0 && l == L0 && a.from_embed;
+            const float *const *parts = nullptr;
+            if (kind == 3) parts = (const float *const *)sh.part[0];
+            else if (kind == 0 ? l > L0 : L1 > L0) parts = (const float *const *)sh.part[1];
+            prologue_norm<GS>(a, w, emb, parts, cur, sxq, sxs, sred, kind == 5);
+            ph = kind == 0 ? PH_QKV : kind == 3 ? PH_GU : PH_HEAD;
+        } else if (kind == 1) {
+            // QK-norm + RoPE + attention (layers.rs:339-343)
+            nsplit = mega_nsplit(pos, a.n_kv_l, gridDim.x);
+            if ((int)blockIdx.x < a.n_kv_l * nsplit)
+                attention_item<KVMUL>(a, l, pos, blockIdx.x % a.n_kv_l, blockIdx.x / a.n_kv_l, nsplit, scratch);
+        } else if (kind == 2) {
+            prologue_attn_out<GS>(a, nsplit, sxq, sxs); // quantize(att), qwen3.rs:152
+            ph = PH_O;
+        } else {
+            prologue_quant<GS>(a.hb, a.H_l, sxq, sxs); // quantize(hb), layers.rs:478
+            ph = PH_DN;
+        }
+        prof_mark(a, ev);
+        // ------------------------------ GEMV ------------------------------
+        if (kind != 1) {
+            const MegaGemv &g = a.g[ph];
+            const int start = sh.start[ph], count = sh.count[ph];
+            float *vrow = a.vc + ((size_t)l * a.seq_len + pos) * a.KV_l;
+            if (kind == 3) {
+                // gate/up + SwiGLU (layers.rs:468-475): blocks of 8 pairs, a gate stage then an up stage
+                load_x<GS>(xr, sxq, sxs, 0, g.KT, g.G, lane);
+                for (int p0 = 0; p0 < count; p0 += 8) {
+                    const int np = count - p0 < 8 ? count - p0 : 8;
+                    if (((p0 >> 3) & 1) != grp) { // blocks alternate between the consumer groups
+                        it += 2;
+                        continue;
+                    }
+                    float gate = 0.0f, up = 0.0f;
+                    for (int half = 0; half < 2; half++) {
                         const int slot = it % MEGA_NSTAGE;
                         mbar_wait(&full[slot], (it / MEGA_NSTAGE) & 1, a.status);
-                        if (8 * s + warp < nb)
-                            accs[s] += tile_dot<GS>(ring + (size_t)slot * slot_bytes + (size_t)warp * g.tile_bytes, xr, g.KT, g.G, lane);
+                        {   // every warp runs the dot (warp-convergent shuffles); a warp without a row reads stale smem and drops the value
+                            float v = tile_dot<GS>(ring + (size_t)slot * slot_bytes + (size_t)wl * g.tile_bytes, xr, g.KT, g.G, lane);
+                            gate = half == 0 ? v : gate;
+                            up = half == 0 ? up : v;
+                        }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty[slot]);
                         it++;
                     }
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < 4; s++)
-                if (8 * s + warp < nb && lane == 0) epi(start + b0 + 8 * s + warp, accs[s]);
-        }
-    };
-
-    for (int l = L0; l < L1; l++) {
-        // ---- attn_norm + quantize (qwen3.rs:134-136) | q,k,v projections (layers.rs:334-336) ----
-        {
-            const bool emb = (l == L0) && a.from_embed;
-            const float *const *parts = (l > L0) ? (const float *const *)a.part[1] : nullptr;
-            prologue_norm<GS>(a, a.rms_att + (size_t)l * a.dim, emb, parts, cur, sxq, sxs, sred, false);
-            float *vrow = a.vc + ((size_t)l * a.seq_len + pos) * a.KV_l;
-            run_plain(PH_QKV, l, [&](int r, float v) {
-                if (r < a.AH_l) a.q[r] = v;
-                else if (r < a.AH_l + a.KV_l) a.kraw[r - a.AH_l] = v;
-                else vrow[r - a.AH_l - a.KV_l] = v;
-            });
-        }
-        grid_barrier(a, bs, false);
-        // ---- QK-norm + RoPE + attention (layers.rs:339-343) ----
-        const int nsplit = mega_nsplit(pos, a.n_kv_l, gridDim.x);
-        if ((int)blockIdx.x < a.n_kv_l * nsplit)
-            attention_item<KVMUL>(a, l, pos, blockIdx.x % a.n_kv_l, blockIdx.x / a.n_kv_l, nsplit, scratch);
-        grid_barrier(a, bs, false);
-        // ---- quantize(att) + o_proj (qwen3.rs:152-153); residual merged by the next prologue ----
-        {
-            prologue_attn_out<GS>(a, nsplit, sxq, sxs);
-            run_plain(PH_O, l, [&](int r, float v) {
-                for (int p = 0; p < a.tp_size; p++) a.part[0][p][(size_t)a.tp_rank * a.dim + r] = v;
-            });
-        }
-        grid_barrier(a, bs, true);
-        // ---- ffn_norm + quantize (qwen3.rs:159-161) | gate/up + SwiGLU (layers.rs:468-475) ----
-        {
-            prologue_norm<GS>(a, a.rms_ffn + (size_t)l * a.dim, false, (const float *const *)a.part[0], cur, sxq, sxs, sred, false);
-            const MegaGemv &g = a.g[PH_GU];
-            int start, count;
-            cta_share(g.units, gridDim.x, blockIdx.x, start, count);
-            load_x<GS>(xr, sxq, sxs, 0, g.KT, g.G, lane);
-            for (int p0 = 0; p0 < count; p0 += 8) {
-                const int np = count - p0 < 8 ? count - p0 : 8;
-                float gate = 0.0f, up = 0.0f;
-#pragma unroll
-                for (int half = 0; half < 2; half++) {
-                    const int slot = it % MEGA_NSTAGE;
-                    mbar_wait(&full[slot], (it / MEGA_NSTAGE) & 1, a.status);
-                    if (warp < np) {
-                        float v = tile_dot<GS>(ring + (size_t)slot * slot_bytes + (size_t)warp * g.tile_bytes, xr, g.KT, g.G, lane);
-                        if (half == 0) gate = v;
-                        else up = v;
+                    if (wl < np && lane == 0) {
+                        float sw = __fmul_rn(gate, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-gate))));
+                        a.hb[start + p0 + wl] = __fmul_rn(sw, up);
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[slot]);
-                    it++;
                 }
-                if (warp < np && lane == 0) {
-                    float sw = __fmul_rn(gate, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-gate))));
-                    a.hb[start + p0 + warp] = __fmul_rn(sw, up);
+            } else {
+                // row phases: batches of 32 rows x n_kt K tiles x up to 4 stages of 8 rows
+                for (int b0 = 0; b0 < count; b0 += 32) {
+                    const int nb = count - b0 < 32 ? count - b0 : 32;
+                    float acc0 = 0.f, acc1 = 0.f; // this warp's rows in its (up to) two stages of the batch
+                    for (int kt = 0; kt < g.n_kt; kt++) {
+                        load_x<GS>(xr, sxq, sxs, kt, g.KT, g.G, lane);
+                        for (int sidx = 0; 8 * sidx < nb; sidx++) {
+                            if ((sidx & 1) == grp) { // stages alternate between the two consumer groups
+                                const int slot = it % MEGA_NSTAGE;
+                                mbar_wait(&full[slot], (it / MEGA_NSTAGE) & 1, a.status);
+                                {
+                                    float v = tile_dot<GS>(ring + (size_t)slot * slot_bytes + (size_t)wl * g.tile_bytes, xr, g.KT, g.G, lane);
+                                    v = (8 * sidx + wl < nb) ? v : 0.0f; // warp without a row: stale smem, value dropped
+                                    acc0 += sidx < 2 ? v : 0.0f;
+                                    acc1 += sidx < 2 ? 0.0f : v;
+                                }
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&empty[slot]);
+                            }
+                            it++;
+                        }
+                    }
+                    // epilogue: lane 0 of the owning warp, rows (grp) and (grp + 2) of the batch's stages
+                    if (lane == 0) {
+                        for (int j = 0; j < 2; j++) {
+                            const int sidx = grp + 2 * j;
+                            if (8 * sidx + wl >= nb) break;
+                            const int r = start + b0 + 8 * sidx + wl;
+                            const float v = j == 0 ? acc0 : acc1;
+                            if (kind == 0) { // layers.rs:334-336
+                                if (r < a.AH_l) a.q[r] = v;
+                                else if (r < a.AH_l + a.KV_l) a.kraw[r - a.AH_l] = v;
+                                else vrow[r - a.AH_l - a.KV_l] = v;
+                            } else if (kind == 2 || kind == 4) { // row-parallel partial sums -> every rank's landing zone
+                                float *const *dst = sh.part[kind == 2 ? 0 : 1];
+#pragma unroll 1
+                                for (int p = 0; p < a.tp_size; p++) dst[p][(size_t)a.tp_rank * a.dim + r] = v;
+                            } else { // lm_head (qwen3.rs:76) + greedy argmax candidate (sampler.rs:57-59)
+                                const int row = a.vocab_row0 + r;
+                                sh.logits[a.tp_rank][row] = v;
+                                if (a.gather_logits) {
+#pragma unroll 1
+                                    for (int p = 0; p < a.tp_size; p++)
+                                        if (p != a.tp_rank) sh.logits[p][row] = v;
+                                }
+                                long long key = ((long long)total_key(v) << 32) | (unsigned)row;
+                                best = key > best ? key : best;
+                            }
+                        }
+                    }
                 }
             }
+            cross = kind == 2 || kind == 4 || kind == 5;
         }
-        grid_barrier(a, bs, false);
-        // ---- quantize(hb) + down (layers.rs:478-479); residual merged by the next prologue ----
-        {
-            prologue_quant<GS>(a.hb, a.H_l, sxq, sxs);
-            run_plain(PH_DN, l, [&](int r, float v) {
-                for (int p = 0; p < a.tp_size; p++) a.part[1][p][(size_t)a.tp_rank * a.dim + r] = v;
-            });
+        prof_mark(a, ev);
+        if (kind == 5) {
+            long long *sbest = reinterpret_cast<long long *>(sred + 32);
+            if (lane == 0) sbest[warp] = best;
+            csync();
+            if (tid == 0) {
+                for (int w = 1; w < MEGA_NCW; w++) best = sbest[w] > best ? sbest[w] : best;
+#pragma unroll 1
+                for (int p = 0; p < a.tp_size; p++) sh.best[p][(size_t)a.tp_rank * gridDim.x + blockIdx.x] = (unsigned long long)best;
+            }
         }
-        grid_barrier(a, bs, true);
+        grid_barrier(a, bs, cross);
+        prof_mark(a, ev);
     }
 
     if (a.run_head) {
-        // ---- final norm (in place) + quantize + lm_head (qwen3.rs:72-76) + greedy argmax (sampler.rs:57-59) ----
-        const float *const *parts = (L1 > L0) ? (const float *const *)a.part[1] : nullptr;
-        prologue_norm<GS>(a, a.rms_final, false, parts, cur, sxq, sxs, sred, true);
-        long long best = (long long)0x8000000000000000LL;
-        run_plain(PH_HEAD, 0, [&](int r, float v) {
-            const int row = a.vocab_row0 + r;
-            a.logits[a.tp_rank][row] = v;
-            if (a.gather_logits)
-                for (int p = 0; p < a.tp_size; p++)
-                    if (p != a.tp_rank) a.logits[p][row] = v;
-            long long key = ((long long)total_key(v) << 32) | (unsigned)row;
-            best = key > best ? key : best;
-        });
-        long long *sbest = reinterpret_cast<long long *>(sred + 16);
-        if (lane == 0) sbest[warp] = best;
-        csync();
-        if (tid == 0) {
-            for (int w = 1; w < MEGA_NCW; w++) best = sbest[w] > best ? sbest[w] : best;
-            for (int p = 0; p < a.tp_size; p++) a.best[p][(size_t)a.tp_rank * gridDim.x + blockIdx.x] = (unsigned long long)best;
-        }
-        grid_barrier(a, bs, true);
         if (blockIdx.x == 0 && warp == 0) {
             long long b = (long long)0x8000000000000000LL;
             const int n = a.tp_size * gridDim.x;
             for (int i = lane; i < n; i += 32) {
-                long long k = (long long)__ldcg(a.best[a.tp_rank] + i);
+                long long k = (long long)__ldcg(sh.best[a.tp_rank] + i);
                 b = k > b ? k : b;
             }
 #pragma unroll
@@ -786,7 +972,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
         if (blockIdx.x == 0 && L1 > L0) {
             for (int i = tid; i < a.dim; i += MEGA_CTHREADS) {
                 float v = ldcg_f(a.x[cur] + i);
-                for (int r = 0; r < a.tp_size; r++) v = __fadd_rn(v, ldcg_f(a.part[1][a.tp_rank] + (size_t)r * a.dim + i));
+#pragma unroll 1
+                for (int r = 0; r < a.tp_size; r++) v = __fadd_rn(v, ldcg_f(sh.part[1][a.tp_rank] + (size_t)r * a.dim + i));
                 a.x[0][i] = v;
             }
         } else if (blockIdx.x == 0 && cur != 0) {

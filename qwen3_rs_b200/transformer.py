@@ -77,6 +77,7 @@ ABI = {
     "q3_set_exact": (_i, [_vp, _i]),
     "q3_bench_decode": (_i, [_vp, _i, _i, _i, C.POINTER(_f)]),
     "q3_bench_kernel": (_i, [_vp, _i, _i, _i, C.POINTER(_f), C.POINTER(_i), C.POINTER(C.c_double)]),
+    "q3_debug_profile": (_i, [_vp, _i, _i, _vp, C.POINTER(_i)]),
     "q3_launches_per_step": (_i, [_vp]),
     "q3_op_quantize": (_i, [_i, _vp, _i, _i, _vp, _vp]),
     "q3_op_matmul": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
@@ -191,6 +192,13 @@ class Transformer:
         ms, n, b = C.c_float(0), C.c_int(0), C.c_double(0)
         _check(load_library().q3_bench_kernel(self._h, self.KERNEL_KINDS[kind], pos, reps, C.byref(ms), C.byref(n), C.byref(b)))
         return ms.value / max(n.value, 1), b.value, n.value
+
+    def debug_profile(self, token: int, pos: int, num_sms: int = 148) -> np.ndarray:
+        """Per-CTA phase timestamps (ns) of one persistent-kernel decode step: [num_sms, n_events]."""
+        buf = np.zeros((num_sms, 1024), np.uint64)
+        n = C.c_int(0)
+        _check(load_library().q3_debug_profile(self._h, token, pos, _ptr(buf), C.byref(n)))
+        return buf[:, : n.value]
 
     @property
     def launches_per_step(self) -> int:
