@@ -99,8 +99,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 }
 // Waits never hang the GPU: after ~2 s (a scheduling bug, not a stall) the waiter raises the abort
 // flag (device memory, polled only every 4096 spins) and everybody falls through.
-__device__ __noinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *status) {
-    if (mbar_try_wait(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_slow(uint64_t *bar, uint32_t parity, int *status);
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *status) {
+    if (mbar_try_wait(bar, parity)) return; // common case: already complete, no call
+    mbar_wait_slow(bar, parity, status);
+}
+__device__ __noinline__ void mbar_wait_slow(uint64_t *bar, uint32_t parity, int *status) {
     long long t0 = clock64();
     unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -206,26 +210,46 @@ __device__ __forceinline__ void load_x(XRegs<GS> &xr, const uint8_t *sxq, const 
 
 // dot of one row tile (in shared memory) with the register-resident activation slice.
 // Per group: exact int32 dot, then (dot as f32 * weight_scale) * input_scale (tensor.rs:47-59).
-template <int GS>
-__device__ __forceinline__ float tile_dot(const uint8_t *tile, const XRegs<GS> &xr, int KT, int G, int lane) {
+// All 128-bit shared loads of the tile are issued before the first dp4a (explicit ld.shared.v4:
+// left to itself the compiler split them into 32-bit loads under the 96-register cap), and each
+// block runs two independent dp4a chains.  FULL: every block has 32 groups (G % 32 == 0), so all
+// offsets are immediates and no lane is predicated off.
+__device__ __forceinline__ int4 lds128(uint32_t saddr) {
+    int4 r;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+    return r;
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(saddr));
+    return r;
+}
+template <int GS, bool FULL>
+__device__ __forceinline__ float tile_dot(uint32_t tile, const XRegs<GS> &xr, int KT, int G, int lane) {
     constexpr int CPG = XRegs<GS>::CPG;
-    const float *ws = reinterpret_cast<const float *>(tile + KT);
+    constexpr int NBLK = XRegs<GS>::NBLK;
+    int4 w[NBLK][CPG];
+    float ws[NBLK];
+#pragma unroll
+    for (int b = 0; b < NBLK; b++) {
+        int ngb = FULL ? 32 : (G - 32 * b > 32 ? 32 : G - 32 * b);
+        const bool on = FULL ? (32 * b < G) : (lane < ngb);
+        if (!FULL && ngb < 1) ngb = 1;
+        const uint32_t base = tile + b * 32 * GS + lane * 16;
+#pragma unroll
+        for (int p = 0; p < CPG; p++) w[b][p] = on ? lds128(base + p * ngb * 16) : make_int4(0, 0, 0, 0);
+        ws[b] = on ? lds_f32(tile + KT + (b * 32 + lane) * 4) : 0.0f;
+    }
     float acc = 0.0f;
 #pragma unroll
-    for (int b = 0; b < XRegs<GS>::NBLK; b++) {
-        int ngb = G - 32 * b;
-        if (ngb > 32) ngb = 32;
-        if (lane < ngb) { // ngb <= 0 -> nobody
-            const int4 *wp = reinterpret_cast<const int4 *>(tile) + b * 32 * CPG + lane;
-            int d0 = 0, d1 = 0; // two independent dp4a chains; int32 addition is exact in any order
+    for (int b = 0; b < NBLK; b++) {
+        int d0 = 0, d1 = 0; // two independent dp4a chains; int32 addition is exact in any order
 #pragma unroll
-            for (int p = 0; p < CPG; p += 2) {
-                d0 = dot16(wp[p * ngb], xr.x[b][p], d0);
-                d1 = dot16(wp[(p + 1) * ngb], xr.x[b][p + 1], d1);
-            }
-            const int d = d0 + d1;
-            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn((float)d, ws[b * 32 + lane]), xr.s[b]));
+        for (int p = 0; p < CPG; p += 2) {
+            d0 = dot16(w[b][p], xr.x[b][p], d0);
+            d1 = dot16(w[b][p + 1], xr.x[b][p + 1], d1);
         }
+        acc = __fadd_rn(acc, __fmul_rn(__fmul_rn((float)(d0 + d1), ws[b]), xr.s[b]));
     }
     return warp_sum(acc);
 }
@@ -551,17 +575,16 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
     }
     csync();
     for (int h = warp; h < KVMUL; h += MEGA_NCW) {
-        float M = -INFINITY;
-#pragma unroll 1
-        for (int w = 0; w < NATT; w++) M = fmaxf(M, sm_m[w * KVMUL + h]);
-        float L = 0.0f;
+        // lane w owns partial w: one exp per lane instead of a serial chain of NATT of them
+        const float mw = lane < NATT ? sm_m[lane * KVMUL + h] : -INFINITY;
+        const float M = warp_max(mw);
+        const float cw = (mw == -INFINITY) ? 0.0f : expf(mw - M);
+        const float L = warp_sum(lane < NATT ? sm_l[lane * KVMUL + h] * cw : 0.0f);
         float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
+#pragma unroll 4
         for (int w = 0; w < NATT; w++) {
-            float mw = sm_m[w * KVMUL + h];
-            float c = (mw == -INFINITY) ? 0.0f : expf(mw - M);
-            L += sm_l[w * KVMUL + h] * c;
-            float4 aw = sm_acc[(w * KVMUL + h) * 32 + lane];
+            const float c = __shfl_sync(0xffffffffu, cw, w);
+            const float4 aw = sm_acc[(w * KVMUL + h) * 32 + lane];
             A.x += aw.x * c;
             A.y += aw.y * c;
             A.z += aw.z * c;
@@ -587,9 +610,10 @@ struct BarState {
 __device__ __noinline__ void grid_barrier(const MegaArgs &a, BarState &bs, bool cross) {
     csync();
     if (threadIdx.x == 0) {
+        // one release-reduction (no return value to wait for); bar.sync above makes the other threads'
+        // stores cumulative with it
         if (cross && a.tp_size > 1) __threadfence_system();
-        else __threadfence();
-        atomicAdd(a.bar, 1ULL);
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(a.bar), "l"(1ULL) : "memory");
         long long t0 = clock64();
         volatile int *st = a.status;
         unsigned spins = 0;
@@ -666,14 +690,18 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
     uint8_t *sxq = scratch;                                          // up to 16384 B
     float *sxs = reinterpret_cast<float *>(scratch + 16384);         // up to 512 groups
     float *sred = reinterpret_cast<float *>(scratch + 16384 + 2048); // 16 floats (+ argmax scratch at +32)
-    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + MEGA_SCRATCH);
-    uint64_t *empty = full + MEGA_NSTAGE;
+    // full barriers are per (consumer group, slot): a waiter can only tell adjacent mbarrier phases
+    // apart, and with ownership alternating between the groups a group would otherwise skip the
+    // other group's use of a slot and mistake the phase before it for its own.
+    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + MEGA_SCRATCH); // [MEGA_GROUPS][MEGA_NSTAGE]
+    uint64_t *empty = full + MEGA_GROUPS * MEGA_NSTAGE;                    // [MEGA_NSTAGE]
     MegaShared &sh = *reinterpret_cast<MegaShared *>(scratch + MEGA_SCRATCH + 128);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
         for (int s = 0; s < MEGA_NSTAGE; s++) {
             mbar_init(&full[s], 1);
+            mbar_init(&full[MEGA_NSTAGE + s], 1);
             mbar_init(&empty[s], MEGA_GW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -746,12 +774,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
         else if (a.run_head) { pf_ph = PH_HEAD; pf_open(); }
         else pf_done = true;
         if (MEGA_L2_AHEAD > 0) pf_advance(MEGA_L2_AHEAD + (long long)MEGA_NSTAGE * slot_bytes);
-        auto push = [&](const uint8_t *src, int nr, int tile_bytes) {
+        auto push = [&](const uint8_t *src, int nr, int tile_bytes, int owner) {
             const int slot = it % MEGA_NSTAGE;
             mbar_wait(&empty[slot], ((it / MEGA_NSTAGE) & 1) ^ 1, a.status);
             const uint32_t bytes = (uint32_t)nr * tile_bytes;
-            mbar_expect_tx(&full[slot], bytes);
-            bulk_g2s(ring + (size_t)slot * slot_bytes, src, bytes, &full[slot], policy);
+            uint64_t *fb = &full[owner * MEGA_NSTAGE + slot];
+            mbar_expect_tx(fb, bytes);
+            bulk_g2s(ring + (size_t)slot * slot_bytes, src, bytes, fb, policy);
             if (MEGA_L2_AHEAD > 0) pf_advance(bytes);
             it++;
         };
@@ -764,7 +793,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                 for (int kt = 0; kt < g.n_kt; kt++)
                     for (int s = 0; s < nb; s += 8) {
                         int nr = nb - s < 8 ? nb - s : 8;
-                        push(src, nr, g.tile_bytes);
+                        push(src, nr, g.tile_bytes, (s >> 3) & 1);
                         src += (size_t)nr * g.tile_bytes;
                     }
             }
@@ -776,7 +805,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
             for (int p0 = 0; p0 < pg.count; p0 += 8) {
                 int np = pg.count - p0 < 8 ? pg.count - p0 : 8;
                 for (int half = 0; half < 2; half++) {
-                    push(src, np, g.tile_bytes);
+                    push(src, np, g.tile_bytes, (p0 >> 3) & 1);
                     src += (size_t)np * g.tile_bytes;
                 }
             }
@@ -805,6 +834,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
     const int grp = warp / MEGA_GW, wl = warp % MEGA_GW; // consumer group and warp-in-group (= row tile in a stage)
     int cur = 0;
     int ev = 0;
+    unsigned fullp = 0; // bit s: parity of this group's next use of slot s
+    uint64_t *myfull = full + grp * MEGA_NSTAGE;
     XRegs<GS> xr;
     prof_mark(a, ev); // 0: start
     long long best = (long long)0x8000000000000000LL;
@@ -845,6 +876,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
         if (kind != 1) {
             const MegaGemv &g = a.g[ph];
             const int start = sh.start[ph], count = sh.count[ph];
+            const bool full_blocks = (g.G & 31) == 0;
+            const uint32_t ring_s = smem_u32(ring);
             float *vrow = a.vc + ((size_t)l * a.seq_len + pos) * a.KV_l;
             if (kind == 3) {
                 // gate/up + SwiGLU (layers.rs:468-475): blocks of 8 pairs, a gate stage then an up stage
@@ -858,9 +891,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                     float gate = 0.0f, up = 0.0f;
                     for (int half = 0; half < 2; half++) {
                         const int slot = it % MEGA_NSTAGE;
-                        mbar_wait(&full[slot], (it / MEGA_NSTAGE) & 1, a.status);
+                        mbar_wait(&myfull[slot], (fullp >> slot) & 1, a.status);
+                        fullp ^= 1u << slot;
                         {   // every warp runs the dot (warp-convergent shuffles); a warp without a row reads stale smem and drops the value
-                            float v = tile_dot<GS>(ring + (size_t)slot * slot_bytes + (size_t)wl * g.tile_bytes, xr, g.KT, g.G, lane);
+                            const uint32_t tile = ring_s + slot * slot_bytes + wl * g.tile_bytes;
+                            float v = full_blocks ? tile_dot<GS, true>(tile, xr, g.KT, g.G, lane) : tile_dot<GS, false>(tile, xr, g.KT, g.G, lane);
                             gate = half == 0 ? v : gate;
                             up = half == 0 ? up : v;
                         }
@@ -883,9 +918,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                         for (int sidx = 0; 8 * sidx < nb; sidx++) {
                             if ((sidx & 1) == grp) { // stages alternate between the two consumer groups
                                 const int slot = it % MEGA_NSTAGE;
-                                mbar_wait(&full[slot], (it / MEGA_NSTAGE) & 1, a.status);
+                                mbar_wait(&myfull[slot], (fullp >> slot) & 1, a.status);
+                                fullp ^= 1u << slot;
                                 {
-                                    float v = tile_dot<GS>(ring + (size_t)slot * slot_bytes + (size_t)wl * g.tile_bytes, xr, g.KT, g.G, lane);
+                                    const uint32_t tile = ring_s + slot * slot_bytes + wl * g.tile_bytes;
+                                    float v = full_blocks ? tile_dot<GS, true>(tile, xr, g.KT, g.G, lane) : tile_dot<GS, false>(tile, xr, g.KT, g.G, lane);
                                     v = (8 * sidx + wl < nb) ? v : 0.0f; // warp without a row: stale smem, value dropped
                                     acc0 += sidx < 2 ? v : 0.0f;
                                     acc1 += sidx < 2 ? 0.0f : v;
