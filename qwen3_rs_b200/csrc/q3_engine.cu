@@ -99,6 +99,12 @@ struct q3_handle {
     float *x2 = nullptr, *kraw = nullptr, *part_buf[2] = {nullptr, nullptr};
     unsigned long long *d_best = nullptr, *d_bar = nullptr;
     unsigned int *d_flags = nullptr;
+    // everything a TP peer writes into lives in ONE allocation (one CUDA IPC handle per rank):
+    // [part o_proj | part down | argmax candidates | barrier flags | logits]
+    uint8_t *xchg = nullptr;
+    size_t xchg_bytes = 0, off_part[2] = {0, 0}, off_best = 0, off_flags = 0, off_logits = 0;
+    bool tp_connected = false;
+    std::vector<void *> peer_maps;
     size_t mega_smem = 0;
     void *mega_fn = nullptr;
     size_t dev_bytes = 0;
@@ -547,15 +553,11 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
     a.embed_q = h->embed.q; a.embed_s = h->embed.s; a.rope = h->rope; a.kc = h->kc; a.vc = h->vc;
     if ((rc = dmalloc(h, (void **)&h->x2, (size_t)dim * 4))) return rc;
     if ((rc = dmalloc(h, (void **)&h->kraw, (size_t)h->KV_l * 4))) return rc;
-    for (int i = 0; i < 2; i++) {
-        if ((rc = dmalloc(h, (void **)&h->part_buf[i], (size_t)h->tp_size * dim * 4))) return rc;
-        CK(cudaMemset(h->part_buf[i], 0, (size_t)h->tp_size * dim * 4));
-    }
-    if ((rc = dmalloc(h, (void **)&h->d_best, (size_t)h->tp_size * h->num_sms * 8))) return rc;
+    for (int i = 0; i < 2; i++) h->part_buf[i] = (float *)(h->xchg + h->off_part[i]);
+    h->d_best = (unsigned long long *)(h->xchg + h->off_best);
+    h->d_flags = (unsigned int *)(h->xchg + h->off_flags);
     if ((rc = dmalloc(h, (void **)&h->d_bar, 64))) return rc;
-    if ((rc = dmalloc(h, (void **)&h->d_flags, 64 * 4))) return rc;
     CK(cudaMemset(h->d_bar, 0, 64));
-    CK(cudaMemset(h->d_flags, 0, 64 * 4));
     if ((rc = dmalloc(h, (void **)&h->d_status, 64))) return rc;
     CK(cudaMemset(h->d_status, 0, 64));
     int *d_status = h->d_status;
@@ -632,6 +634,11 @@ extern "C" int q3_debug_profile(q3_handle *h, int token, int pos, unsigned long 
 }
 
 static inline bool use_mega(const q3_handle *h) { return h->decode_path == 1 && h->mega_ok && !h->exact; }
+static int tp_ready(const q3_handle *h) {
+    if (h->tp_size > 1 && !h->tp_connected) return fail(Q3_ECOMM, "tensor-parallel handle used before q3_tp_connect");
+    if (h->tp_size > 1 && !use_mega(h)) return fail(Q3_EUNSUPPORTED, "under tensor parallelism only the persistent fast path is available");
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------
 // construction
@@ -741,7 +748,19 @@ static int create_impl(const char *path, int ctx_len, int device, int tp_rank, i
     TRY(dmalloc(h, (void **)&h->xb, (size_t)maxd * 4));
     TRY(dmalloc(h, (void **)&h->q, (size_t)h->AH_l * 4));
     TRY(dmalloc(h, (void **)&h->hb, (size_t)h->H_l * 4));
-    TRY(dmalloc(h, (void **)&h->logits, (size_t)c.vocab_size * 4));
+    {   // exchange buffer (see q3_handle::xchg); logits live inside it
+        auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        size_t o = 0;
+        h->off_part[0] = o; o = al(o + (size_t)tp_size * dim * 4);
+        h->off_part[1] = o; o = al(o + (size_t)tp_size * dim * 4);
+        h->off_best = o; o = al(o + (size_t)tp_size * h->num_sms * 8);
+        h->off_flags = o; o = al(o + 64 * 4);
+        h->off_logits = o; o = al(o + (size_t)c.vocab_size * 4);
+        h->xchg_bytes = o;
+        TRY(dmalloc(h, (void **)&h->xchg, o));
+        CKH(cudaMemset(h->xchg, 0, o));
+        h->logits = (float *)(h->xchg + h->off_logits);
+    }
     TRY(dmalloc(h, (void **)&h->xq, (size_t)maxd));
     TRY(dmalloc(h, (void **)&h->xs, (size_t)(maxd / gs + 1) * 4));
     TRY(dmalloc(h, (void **)&h->hq, (size_t)h->H_l));
@@ -778,12 +797,81 @@ extern "C" int q3_create(const char *path, int ctx_len, int device, q3_handle **
     return create_impl(path, ctx_len, device, 0, 1, out);
 }
 extern "C" int q3_create_tp(const char *path, int ctx_len, int device, int tp_rank, int tp_size, q3_handle **out) {
-    if (tp_size != 1) return fail(Q3_EUNSUPPORTED, "tensor parallel path not built yet");
-    return create_impl(path, ctx_len, device, tp_rank, tp_size, out);
+    if (tp_size > MEGA_MAX_TP) return fail(Q3_EUNSUPPORTED, "tp_size %d > %d", tp_size, MEGA_MAX_TP);
+    int rc = create_impl(path, ctx_len, device, tp_rank, tp_size, out);
+    if (rc) return rc;
+    if (tp_size > 1 && !(*out)->mega_ok) {
+        std::string why = (*out)->mega_why;
+        q3_destroy(*out);
+        *out = nullptr;
+        return fail(Q3_EUNSUPPORTED, "tensor parallelism needs the persistent decode kernel, unavailable here: %s", why.c_str());
+    }
+    return Q3_OK;
 }
+
+// blob exchanged between ranks (all-gathered by the host): who I am + how to map my exchange buffer
+struct TpBlob {
+    uint32_t magic, rank, tp_size, device;
+    uint64_t pid, raw_ptr, bytes;
+    cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(TpBlob) <= 256, "blob too large");
 extern "C" size_t q3_tp_blob_size(void) { return 256; }
-extern "C" int q3_tp_export(q3_handle *, void *) { return fail(Q3_EUNSUPPORTED, "tensor parallel path not built yet"); }
-extern "C" int q3_tp_connect(q3_handle *, const void *) { return fail(Q3_EUNSUPPORTED, "tensor parallel path not built yet"); }
+
+extern "C" int q3_tp_export(q3_handle *h, void *blob_out) {
+    if (!h || !blob_out) return fail(Q3_EINVAL, "null argument");
+    CK(cudaSetDevice(h->device));
+    memset(blob_out, 0, 256);
+    TpBlob b{};
+    b.magic = 0x51335450; // "Q3TP"
+    b.rank = h->tp_rank; b.tp_size = h->tp_size; b.device = h->device;
+    b.pid = (uint64_t)getpid();
+    b.raw_ptr = (uint64_t)(uintptr_t)h->xchg;
+    b.bytes = h->xchg_bytes;
+    CK(cudaIpcGetMemHandle(&b.ipc, h->xchg));
+    memcpy(blob_out, &b, sizeof b);
+    return Q3_OK;
+}
+
+extern "C" int q3_tp_connect(q3_handle *h, const void *blobs) {
+    if (!h || !blobs) return fail(Q3_EINVAL, "null argument");
+    if (h->tp_size == 1) return Q3_OK;
+    CK(cudaSetDevice(h->device));
+    MegaArgs &a = h->margs;
+    for (int r = 0; r < h->tp_size; r++) {
+        TpBlob b;
+        memcpy(&b, (const uint8_t *)blobs + (size_t)r * 256, sizeof b);
+        if (b.magic != 0x51335450 || (int)b.rank != r || (int)b.tp_size != h->tp_size || b.bytes != h->xchg_bytes)
+            return fail(Q3_ECOMM, "rank %d: bad exchange blob (rank %u, tp %u, %llu bytes)", r, b.rank, b.tp_size,
+                        (unsigned long long)b.bytes);
+        uint8_t *base = nullptr;
+        if (r == h->tp_rank) {
+            base = h->xchg;
+        } else if (b.pid == (uint64_t)getpid()) { // same process: plain peer access
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, h->device, (int)b.device));
+            if (!can) return fail(Q3_ECOMM, "device %d cannot access peer device %u", h->device, b.device);
+            cudaError_t e = cudaDeviceEnablePeerAccess((int)b.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(Q3_ECOMM, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            base = (uint8_t *)(uintptr_t)b.raw_ptr;
+        } else { // another process on this node: CUDA IPC over NVLink
+            void *p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, b.ipc, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return fail(Q3_ECOMM, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+            h->peer_maps.push_back(p);
+            base = (uint8_t *)p;
+        }
+        a.part[0][r] = (float *)(base + h->off_part[0]);
+        a.part[1][r] = (float *)(base + h->off_part[1]);
+        a.best[r] = (unsigned long long *)(base + h->off_best);
+        a.flags[r] = (unsigned int *)(base + h->off_flags);
+        a.logits[r] = (float *)(base + h->off_logits);
+    }
+    h->tp_connected = true;
+    return Q3_OK;
+}
 
 extern "C" void q3_destroy(q3_handle *h) {
     if (!h) return;
@@ -793,6 +881,7 @@ extern "C" void q3_destroy(q3_handle *h) {
         if (h->g_fwd[e]) cudaGraphExecDestroy(h->g_fwd[e]);
         if (h->g_greedy[e]) cudaGraphExecDestroy(h->g_greedy[e]);
     }
+    for (void *p : h->peer_maps) cudaIpcCloseMemHandle(p);
     for (void *p : h->allocs) cudaFree(p);
     if (h->h_logits) cudaFreeHost(h->h_logits);
     if (h->h_small) cudaFreeHost(h->h_small);
@@ -806,6 +895,7 @@ extern "C" int q3_launches_per_step(const q3_handle *h) { return h ? h->launches
 extern "C" int q3_set_decode_path(q3_handle *h, int path) {
     if (!h) return fail(Q3_EINVAL, "null handle");
     if (path != 0 && path != 1) return fail(Q3_EINVAL, "decode path %d unknown", path);
+    if (path == 0 && h->tp_size > 1) return fail(Q3_EUNSUPPORTED, "the multi-kernel path has no tensor-parallel exchange");
     if (path == 1 && !h->mega_ok)
         return fail(Q3_EUNSUPPORTED, "persistent decode kernel unavailable for this shape: %s", h->mega_why.c_str());
     h->decode_path = path;
@@ -816,6 +906,7 @@ extern "C" int q3_set_decode_path(q3_handle *h, int path) {
 extern "C" int q3_set_exact(q3_handle *h, int on) {
     if (!h) return fail(Q3_EINVAL, "null handle");
     CK(cudaSetDevice(h->device));
+    if (on && h->tp_size > 1) return fail(Q3_EUNSUPPORTED, "exact mode is single-GPU");
     h->exact = on ? 1 : 0;
     if (h->exact && h->cfg.dim > 16384) return fail(Q3_EUNSUPPORTED, "exact mode needs dim <= 16384");
     if (!h->g_fwd[h->exact]) return build_graphs(h);
@@ -824,6 +915,7 @@ extern "C" int q3_set_exact(q3_handle *h, int on) {
 
 static int check_tok_pos(const q3_handle *h, int token, int pos) {
     if (!h) return fail(Q3_EINVAL, "null handle");
+    if (int rc = tp_ready(h)) return rc;
     if (token < 0 || token >= h->cfg.vocab_size)
         return fail(Q3_EINVAL, "index out of bounds: token %d >= vocab_size %d", token, h->cfg.vocab_size);
     if (pos < 0 || pos >= h->cfg.seq_len)
@@ -1052,6 +1144,7 @@ extern "C" int q3_forward_layers(q3_handle *h, int pos, int layer0, int layer1, 
     if (layer0 < 0 || layer1 > h->cfg.n_layers || layer0 > layer1) return fail(Q3_EINVAL, "bad layer range");
     CK(cudaSetDevice(h->device));
     int rc;
+    if ((rc = tp_ready(h))) return rc;
     if ((rc = set_tok_pos(h, 0, pos))) return rc;
     CK(cudaMemcpyAsync(h->x, x_host, (size_t)h->cfg.dim * 4, cudaMemcpyHostToDevice, h->stream));
     if (use_mega(h)) {

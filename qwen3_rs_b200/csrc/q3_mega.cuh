@@ -32,7 +32,7 @@ constexpr int MEGA_MAX_KT = 4096;
 constexpr int MEGA_SCRATCH = 40960;                 // xq/xs or attention buffers
 constexpr int MEGA_MAX_TP = 8;
 constexpr int MEGA_MAX_SPLITS = ATTN_MAX_SPLITS;
-constexpr long long MEGA_L2_AHEAD = 0;              // bytes per CTA the L2 prefetch cursor runs ahead of the ring (0 = off:
+constexpr long long MEGA_L2_AHEAD = 0;                 // bytes per CTA the L2 prefetch cursor runs ahead of the ring (0 = off:
                                                     // measured SLOWER on B200 -- the extra L2 fill traffic delays the consumers' activation loads)
 
 enum { PH_QKV = 0, PH_O = 1, PH_GU = 2, PH_DN = 3, PH_HEAD = 4 };
@@ -682,7 +682,8 @@ __device__ __forceinline__ PhaseGeom phase_geom(const MegaArgs &a, const MegaSha
 
 template <int GS, int KVMUL>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_constant__ MegaArgs a) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t mega_smem[];
+    uint8_t *smem = mega_smem;
     // layout: [ring: NSTAGE x slot][scratch][barriers]
     const int slot_bytes = MEGA_GW * (MEGA_MAX_KT + 4 * (MEGA_MAX_KT / GS));
     uint8_t *ring = smem;

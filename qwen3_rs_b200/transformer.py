@@ -204,6 +204,16 @@ class Transformer:
     def launches_per_step(self) -> int:
         return load_library().q3_launches_per_step(self._h)
 
+    # -- tensor parallelism (one process per GPU; see tp_connect below) -------------------------
+    def tp_export(self) -> bytes:
+        n = load_library().q3_tp_blob_size()
+        buf = C.create_string_buffer(n)
+        _check(load_library().q3_tp_export(self._h, buf))
+        return buf.raw
+
+    def tp_connect_blobs(self, blobs: bytes) -> None:
+        _check(load_library().q3_tp_connect(self._h, C.create_string_buffer(blobs, len(blobs))))
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             load_library().q3_destroy(self._h)
@@ -251,6 +261,26 @@ class TransformerBuilder:
             rc = L.q3_create_tp(self.checkpoint_path.encode(), ctx, self.device, self.tp_rank, self.tp_size, C.byref(h))
         _check(rc)
         return Transformer(h.value)
+
+
+def tp_connect(m: Transformer, dist) -> None:
+    """Exchange the ranks' CUDA-IPC blobs over torch.distributed (plumbing only) and map the peers'
+    exchange buffers.  Every rank of the group must call this after build()."""
+    import torch
+
+    blob = m.tp_export()
+    world = dist.get_world_size()
+    if dist.get_backend() == "nccl":
+        mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
+        allb = torch.empty(world * len(blob), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allb, mine)
+        blobs = bytes(allb.cpu().numpy().tobytes())
+    else:
+        objs = [None] * world
+        dist.all_gather_object(objs, blob)
+        blobs = b"".join(objs)
+    m.tp_connect_blobs(blobs)
+    dist.barrier()
 
 
 # ---- operator-level entry points (tests) ---------------------------------------------------
