@@ -1,0 +1,77 @@
+//! qwen3-cuda: `impl Transformer` over libqwen3cuda (B200 / sm_100a).
+//!
+//! NOT COMPILED in this repository (no Rust toolchain in the image); it is the reference-side binding
+//! for include/qwen3_cuda.h.  It needs one line in qwen3-inference: `pub use
+//! crate::configuration::ModelConfig;` (ModelConfig lives in a private module, lib.rs:5).
+use anyhow::{bail, Result};
+use qwen3_inference::{ModelConfig, Transformer};
+use std::ffi::{c_char, c_float, c_int, CStr, CString};
+
+#[repr(C)]
+struct Q3Config {
+    architecture_id: i32, dim: i32, hidden_dim: i32, n_layers: i32, n_heads: i32, n_kv_heads: i32,
+    head_dim: i32, seq_len: i32, vocab_size: i32, group_size: i32, shared_classifier: i32,
+}
+#[repr(C)]
+struct Q3Handle { _private: [u8; 0] }
+
+extern "C" {
+    fn q3_create(path: *const c_char, ctx_len: c_int, device: c_int, out: *mut *mut Q3Handle) -> c_int;
+    fn q3_destroy(h: *mut Q3Handle);
+    fn q3_get_config(h: *const Q3Handle) -> *const Q3Config;
+    fn q3_forward(h: *mut Q3Handle, token: c_int, pos: c_int, logits_host: *mut c_float) -> c_int;
+    fn q3_last_error() -> *const c_char;
+}
+
+fn last_error() -> String {
+    unsafe { CStr::from_ptr(q3_last_error()).to_string_lossy().into_owned() }
+}
+
+/// Device-resident Qwen3 transformer; a drop-in for `Transformers::Qwen3` (models/mod.rs:20-37).
+pub struct CudaTransformer {
+    handle: *mut Q3Handle,
+    config: ModelConfig,
+    logits: Vec<f32>,
+}
+
+impl CudaTransformer {
+    /// `TransformerBuilder::new(path).with_ctx_length(ctx).build()` (models/mod.rs:46-73).
+    pub fn build(checkpoint_path: &str, ctx_length: Option<usize>, device: i32) -> Result<Self> {
+        let path = CString::new(checkpoint_path)?;
+        let mut handle = std::ptr::null_mut();
+        let rc = unsafe { q3_create(path.as_ptr(), ctx_length.unwrap_or(0) as c_int, device, &mut handle) };
+        if rc != 0 {
+            bail!("{}", last_error()); // same messages as configuration.rs:116-146 / models/mod.rs:57,71
+        }
+        let c = unsafe { &*q3_get_config(handle) };
+        let config = ModelConfig {
+            architecture_id: c.architecture_id as usize, dim: c.dim as usize, hidden_dim: c.hidden_dim as usize,
+            n_layers: c.n_layers as usize, n_heads: c.n_heads as usize, n_kv_heads: c.n_kv_heads as usize,
+            head_dim: c.head_dim as usize, seq_len: c.seq_len as usize, vocab_size: c.vocab_size as usize,
+            group_size: c.group_size as usize, shared_classifier: c.shared_classifier != 0,
+        };
+        let logits = vec![0.0; config.vocab_size];
+        Ok(Self { handle, config, logits })
+    }
+}
+
+impl Transformer for CudaTransformer {
+    fn forward(&mut self, token: usize, pos: usize) -> &[f32] {
+        let rc = unsafe { q3_forward(self.handle, token as c_int, pos as c_int, self.logits.as_mut_ptr()) };
+        if rc != 0 {
+            panic!("{}", last_error()); // the reference panics on out-of-range token/pos (slice index)
+        }
+        &self.logits
+    }
+    fn get_config(&self) -> &ModelConfig {
+        &self.config
+    }
+}
+
+impl Drop for CudaTransformer {
+    fn drop(&mut self) {
+        unsafe { q3_destroy(self.handle) }
+    }
+}
+// SAFETY: the handle is used through &mut self only (one caller at a time), like the reference.
+unsafe impl Send for CudaTransformer {}
