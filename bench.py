@@ -13,9 +13,11 @@ the repo's exporter (no checkpoints offline), i.e. BASELINE.json configs[3] at o
             feedback on the device, weights/KV resident in HBM.
   e2e     : the same tokens/s through the reference-facing call -- Transformer.forward(token, pos)
             -> host logits (vocab x f32 D2H every token) -> host argmax (sampler.rs semantics).
-  roofline: the dominant kernel (gate/up GEMV) timed alone, algorithmic weight+scale bytes per
-            launch / CUDA-event time, against MEASURED_PEAKS.json's HBM copy bandwidth; plus
-            `token_roofline` for the whole step (bytes per token / time per token).
+  roofline: the dominant kernel.  On the default path the whole decode step is ONE launch of the
+            persistent kernel k_mega_decode, so algorithmic bytes per launch = bytes per token
+            (weights + scales + f32 KV rows read) and the duration is the CUDA-event time per launch
+            over the timed region; peak = MEASURED_PEAKS.json's HBM copy bandwidth.  `graph_path_kernels`
+            lists the multi-kernel path's GEMVs timed alone for comparison.
   cpu_baseline: the CPU oracle (C restatement of the reference forward, OpenMP over rows/heads
             like the reference's rayon) on the same .bin and the box's host cores, bounded sample.
 
@@ -156,8 +158,7 @@ def ncu_traffic(kind: str):
 def cpu_decode_tok_s(path: str, ctx: int, n_tokens: int, threads: int = 0):
     from oracle import binding as orc
 
-    if threads:
-        orc.set_threads(threads)
+    orc.set_threads(threads or os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host core
     cores = orc.max_threads()
     m = orc.Model(path, ctx)
     tok = 1
@@ -178,6 +179,7 @@ def run_reference(args, rank: int, world: int):
     tps = max(1, min(args.tokens_per_step, args.ref_tokens_per_step))
     from oracle import binding as orc
 
+    orc.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host core
     cores = orc.max_threads()
     m = orc.Model(path, args.ctx)
     tok, pos = 1, 0
@@ -352,8 +354,9 @@ def main():
                     "achieved": token_roof["achieved"], "peak": peak, "unit": "GB/s", "frac": token_roof["frac"],
                     "traffic": ncu_traffic("mega"), "bytes_per_launch": btok, "us_per_launch": tok_ms * 1e3,
                     "peak_source": peak_src}
-        m.set_decode_path(0)
-        for kind in ("gate_up", "down", "qkv", "o_proj", "lm_head"):
+        if world == 1:
+            m.set_decode_path(0)
+        for kind in (("gate_up", "down", "qkv", "o_proj", "lm_head") if world == 1 else ()):
             ms, nbytes, n = m.bench_kernel(kind, 0, reps=3 if kind != "lm_head" else 1)
             kernels[kind] = {"us": ms * 1e3, "GBps": nbytes / ms / 1e6, "bytes": nbytes}
         if not persistent:
