@@ -344,7 +344,8 @@ def main():
                   "us_per_token": tok_ms * 1e3, "mean_pos": mean_pos}
     roof = None
     kernels = {}
-    persistent = m.launches_per_step == 1
+    launches_per_token = m.launches_per_step  # on the path that was timed (1 for the persistent kernel)
+    persistent = launches_per_token == 1
     try:
         if persistent:
             # the whole decode step is ONE launch of k_mega_decode: algorithmic bytes per launch = bytes per
@@ -387,8 +388,8 @@ def main():
         "wall_ms_per_step": wall_ms / args.steps,
         "e2e": {"value": e2e_val, "unit": "tok/s", "h2d_bytes_per_step": 16 * tps, "d2h_bytes_per_step": vocab * 4 * tps,
                 "tokens_timed": e2e_tokens, "path": "Transformer.forward -> host logits -> host argmax (sampler.rs)"},
-        "gpu_launches": m.launches_per_step * n_tok,
-        "launches_per_token": m.launches_per_step,
+        "gpu_launches": launches_per_token * n_tok,
+        "launches_per_token": launches_per_token,
         "clocks": clk, "roofline": roof, "token_roofline": token_roof, "graph_path_kernels": kernels, "cpu_baseline": cpu,
         "decode_path": "persistent" if persistent else "graph",
     }
