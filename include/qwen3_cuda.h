@@ -96,6 +96,10 @@ int q3_decode_greedy(q3_handle *h, int first_token, int pos0, int n, int *tokens
  * of the last token (NULL to skip). */
 int q3_prefill(q3_handle *h, const int *tokens, int n, int pos0, float *last_logits_host);
 
+/* Timing helper: one batched prefill of n tokens (after an untimed warm-up pass), CUDA events on the
+ * launch stream, inputs resident; milliseconds. */
+int q3_bench_prefill(q3_handle *h, const int *tokens, int n, int pos0, float *ms_out);
+
 /* Zero the KV cache (a freshly built reference transformer, qwen3.rs:439-440). */
 int q3_reset(q3_handle *h);
 
@@ -154,6 +158,12 @@ int q3_op_matmul(int device, const int8_t *xq, const float *xs, const int8_t *wq
                  int n, int d, int gs, int exact, float *out, int32_t *group_dots_out);
 /* glibc expf restated on the device (exact mode's exp); x, out: n f32. */
 int q3_op_expf(int device, const float *x, int n, float *out);
+/* T-token group-scaled int8 GEMM on the tensor cores (tcgen05.mma.kind::i8, TMEM accumulators, TMA
+ * operands): out[T][N] = per-token tensor.rs:23-62 matmul of x (int8[T][K] + f32[T][K/gs]) with
+ * row-major w (int8[N][K] + f32[N][K/gs]).  N, K multiples of 128.  Bit-identical to the per-token
+ * GEMV in exact mode (same per-group terms, groups added in order). */
+int q3_op_gemm_q8(int device, const int8_t *xq, const float *xs, const int8_t *wq, const float *ws,
+                  int T, int N, int K, int gs, float *out);
 /* layers.rs:109-119 RMSNorm::forward */
 int q3_op_rmsnorm(int device, const float *x, const float *w, int n, float *out);
 /* qwen3-export model_exporter.rs:104-161 quantize_q80 on the device. */

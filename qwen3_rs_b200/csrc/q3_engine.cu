@@ -7,6 +7,8 @@
 #include "../../include/qwen3_cuda.h"
 #include "q3_kernels.cuh"
 #include "q3_mega.cuh"
+#include "q3_prefill.cuh"
+#include <cudaTypedefs.h>
 
 #include <cuda_runtime.h>
 #include <fcntl.h>
@@ -53,6 +55,9 @@ struct DevQT { // device QuantizedTensor: row-major int8 [rows][K] + f32 scales 
     int8_t *q = nullptr;
     float *s = nullptr;
     int rows = 0, K = 0;
+    float *sT = nullptr;      // prefill: scales group-major [K/gs][rows]
+    CUtensorMap map{};        // prefill: TMA map over q, box 128 rows x 128 B, 128B swizzle
+    bool has_map = false;
 };
 
 struct LayerDev {
@@ -107,6 +112,13 @@ struct q3_handle {
     std::vector<void *> peer_maps;
     size_t mega_smem = 0;
     void *mega_fn = nullptr;
+    // batched prefill (tcgen05 GEMM) state
+    bool pf_ok = false;
+    std::string pf_why;
+    int pf_cap = 0;          // token capacity of the buffers below (multiple of 128)
+    float *pf_x = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_hb = nullptr, *pf_xsT = nullptr, *pf_hsT = nullptr;
+    int8_t *pf_xq = nullptr, *pf_hq = nullptr;
+    int *pf_tokens = nullptr;
     size_t dev_bytes = 0;
     std::vector<void *> allocs;
 };
@@ -641,6 +653,161 @@ static int tp_ready(const q3_handle *h) {
 }
 
 // ------------------------------------------------------------------------------------------
+// batched prefill: tcgen05 int8 GEMM (q3_prefill.cuh) + batched norm / rope / attention
+// ------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+    }
+    return fn;
+}
+// 2-D int8 matrix [rows][K] (row pitch K bytes), box = 128 rows x 128 bytes, 128B swizzle
+static int make_map_i8(CUtensorMap *map, const void *base, int rows, int K) {
+    auto enc = get_encode_fn();
+    if (!enc) return fail(Q3_ECUDA, "cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K};
+    cuuint32_t box[2] = {(cuuint32_t)PF_BK, (cuuint32_t)PF_BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(Q3_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows %d K %d", (int)r, rows, K);
+    return 0;
+}
+
+template <int GS, int EPI>
+static int launch_gemm_q8_t(const CUtensorMap &mx, const CUtensorMap &mw, const PrefillGemmArgs &a, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        CK(cudaFuncSetAttribute(k_gemm_q8<GS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+        attr = true;
+    }
+    dim3 grid(a.N / PF_BN, a.Tpad / PF_BM);
+    k_gemm_q8<GS, EPI><<<grid, PF_THREADS, PF_SMEM, s>>>(mx, mw, a);
+    return 0;
+}
+template <int EPI>
+static int launch_gemm_q8(int gs, const CUtensorMap &mx, const CUtensorMap &mw, const PrefillGemmArgs &a, cudaStream_t s) {
+    int rc = 0;
+    GS_DISPATCH(gs, (rc = launch_gemm_q8_t<GS, EPI>(mx, mw, a, s)));
+    return rc;
+}
+
+// group-major scales + TMA map for one weight tensor
+static int prefill_prepare_tensor(q3_handle *h, DevQT &t) {
+    if (t.has_map) return 0;
+    const int gs = h->cfg.group_size, ng = t.K / gs;
+    int rc;
+    if ((rc = dmalloc(h, (void **)&t.sT, (size_t)ng * t.rows * 4))) return rc;
+    dim3 grid((ng + 31) / 32, (t.rows + 31) / 32);
+    k_transpose_f32<<<grid, dim3(32, 8), 0, h->stream>>>(t.s, t.sT, t.rows, ng);
+    CK(cudaGetLastError());
+    if ((rc = make_map_i8(&t.map, t.q, t.rows, t.K))) return rc;
+    t.has_map = true;
+    return 0;
+}
+
+static int prefill_init(q3_handle *h) {
+    const q3_config &c = h->cfg;
+    h->pf_ok = false;
+    if (h->tp_size != 1) { h->pf_why = "batched prefill is single-GPU for now"; return 0; }
+    if (c.dim % 128 || h->AH_l % 128 || h->H_l % 128 || h->layers[0].qkv.rows % 128 || (2 * h->H_l) % 128) {
+        h->pf_why = "matrix dimensions must be multiples of 128";
+        return 0;
+    }
+    if (!get_encode_fn()) { h->pf_why = "cuTensorMapEncodeTiled unavailable"; return 0; }
+    int rc;
+    for (auto &W : h->layers) {
+        if ((rc = prefill_prepare_tensor(h, W.qkv))) return rc;
+        if ((rc = prefill_prepare_tensor(h, W.wo))) return rc;
+        if ((rc = prefill_prepare_tensor(h, W.w13))) return rc;
+        if ((rc = prefill_prepare_tensor(h, W.w2))) return rc;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->pf_ok = true;
+    return 0;
+}
+
+static int prefill_reserve(q3_handle *h, int T) {
+    const int Tpad = (T + 127) / 128 * 128;
+    if (Tpad <= h->pf_cap) return 0;
+    const q3_config &c = h->cfg;
+    const int gs = c.group_size, dim = c.dim, AH = h->AH_l, H = h->H_l;
+    const int maxd = AH > dim ? AH : dim;
+    for (void *p : {(void *)h->pf_x, (void *)h->pf_q, (void *)h->pf_att, (void *)h->pf_hb, (void *)h->pf_xsT, (void *)h->pf_hsT,
+                    (void *)h->pf_xq, (void *)h->pf_hq, (void *)h->pf_tokens})
+        if (p) cudaFree(p);
+    h->pf_cap = 0;
+    CK(cudaMalloc((void **)&h->pf_x, (size_t)Tpad * dim * 4));
+    CK(cudaMalloc((void **)&h->pf_q, (size_t)Tpad * AH * 4));
+    CK(cudaMalloc((void **)&h->pf_att, (size_t)Tpad * AH * 4));
+    CK(cudaMalloc((void **)&h->pf_hb, (size_t)Tpad * H * 4));
+    CK(cudaMalloc((void **)&h->pf_xsT, (size_t)(maxd / gs) * Tpad * 4));
+    CK(cudaMalloc((void **)&h->pf_hsT, (size_t)(H / gs) * Tpad * 4));
+    CK(cudaMalloc((void **)&h->pf_xq, (size_t)Tpad * maxd));
+    CK(cudaMalloc((void **)&h->pf_hq, (size_t)Tpad * H));
+    CK(cudaMalloc((void **)&h->pf_tokens, (size_t)Tpad * 4));
+    CK(cudaMemset(h->pf_xq, 0, (size_t)Tpad * maxd));
+    CK(cudaMemset(h->pf_hq, 0, (size_t)Tpad * H));
+    CK(cudaMemset(h->pf_xsT, 0, (size_t)(maxd / gs) * Tpad * 4));
+    CK(cudaMemset(h->pf_hsT, 0, (size_t)(H / gs) * Tpad * 4));
+    h->pf_cap = Tpad;
+    return 0;
+}
+
+// the whole batched forward for tokens at positions pos0..pos0+T-1; leaves x of the last token in h->x
+static int prefill_run(q3_handle *h, const int *tokens_host, int T, int pos0) {
+    const q3_config &c = h->cfg;
+    const int gs = c.group_size, dim = c.dim, AH = h->AH_l, KV = h->KV_l, H = h->H_l;
+    int rc;
+    if ((rc = prefill_reserve(h, T))) return rc;
+    const int Tpad = (T + 127) / 128 * 128;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(h->pf_tokens, tokens_host, (size_t)T * 4, cudaMemcpyHostToDevice, s));
+    CUtensorMap mx_dim, mx_ah, mx_h;
+    if ((rc = make_map_i8(&mx_dim, h->pf_xq, Tpad, dim))) return rc;
+    if ((rc = make_map_i8(&mx_ah, h->pf_xq, Tpad, AH))) return rc;
+    if ((rc = make_map_i8(&mx_h, h->pf_hq, Tpad, H))) return rc;
+    for (int l = 0; l < c.n_layers; l++) {
+        LayerDev &W = h->layers[l];
+        float *kc_l = h->kc + (size_t)l * c.seq_len * KV;
+        float *vc_l = h->vc + (size_t)l * c.seq_len * KV;
+        // attn_norm + quantize (qwen3.rs:134-136), embedding on layer 0
+        GS_DISPATCH(gs, (k_pf_norm_quant<GS><<<T, 256, 0, s>>>(h->pf_x, W.rms_att, h->pf_xq, h->pf_xsT, dim, Tpad,
+                                                              l == 0 ? h->embed.q : nullptr, h->embed.s, h->pf_tokens, 0)));
+        PrefillGemmArgs g{};
+        g.T = T; g.Tpad = Tpad; g.K = dim; g.N = W.qkv.rows; g.wsT = W.qkv.sT; g.xsT = h->pf_xsT;
+        g.q = h->pf_q; g.kc = kc_l; g.vc = vc_l; g.AH = AH; g.KV = KV; g.pos0 = pos0;
+        if ((rc = launch_gemm_q8<PF_EPI_QKV>(gs, mx_dim, W.qkv.map, g, s))) return rc;
+        dim3 rg((h->n_heads_l + h->n_kv_l + 3) / 4, T);
+        k_pf_qknorm_rope<<<rg, 128, 0, s>>>(h->pf_q, kc_l, W.q_ln, W.k_ln, h->rope, pos0, h->n_heads_l, h->n_kv_l, AH, KV);
+        dim3 ag(h->n_heads_l, (T + 3) / 4);
+        k_pf_attention<<<ag, 128, 0, s>>>(h->pf_q, kc_l, vc_l, h->pf_att, T, pos0, AH, KV, h->kv_mul);
+        GS_DISPATCH(gs, (k_pf_quantize<GS><<<T, 256, 0, s>>>(h->pf_att, h->pf_xq, h->pf_xsT, AH, Tpad)));
+        PrefillGemmArgs o{};
+        o.T = T; o.Tpad = Tpad; o.K = AH; o.N = dim; o.wsT = W.wo.sT; o.xsT = h->pf_xsT; o.out = h->pf_x; o.ld_out = dim;
+        if ((rc = launch_gemm_q8<PF_EPI_RESID>(gs, mx_ah, W.wo.map, o, s))) return rc;
+        GS_DISPATCH(gs, (k_pf_norm_quant<GS><<<T, 256, 0, s>>>(h->pf_x, W.rms_ffn, h->pf_xq, h->pf_xsT, dim, Tpad, nullptr, nullptr,
+                                                              nullptr, 0)));
+        PrefillGemmArgs gu{};
+        gu.T = T; gu.Tpad = Tpad; gu.K = dim; gu.N = W.w13.rows; gu.wsT = W.w13.sT; gu.xsT = h->pf_xsT; gu.out = h->pf_hb; gu.ld_out = H;
+        if ((rc = launch_gemm_q8<PF_EPI_SWIGLU>(gs, mx_dim, W.w13.map, gu, s))) return rc;
+        GS_DISPATCH(gs, (k_pf_quantize<GS><<<T, 256, 0, s>>>(h->pf_hb, h->pf_hq, h->pf_hsT, H, Tpad)));
+        PrefillGemmArgs dn{};
+        dn.T = T; dn.Tpad = Tpad; dn.K = H; dn.N = dim; dn.wsT = W.w2.sT; dn.xsT = h->pf_hsT; dn.out = h->pf_x; dn.ld_out = dim;
+        if ((rc = launch_gemm_q8<PF_EPI_RESID>(gs, mx_h, W.w2.map, dn, s))) return rc;
+    }
+    CK(cudaMemcpyAsync(h->x, h->pf_x + (size_t)(T - 1) * dim, (size_t)dim * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // construction
 // ------------------------------------------------------------------------------------------
 static int create_impl(const char *path, int ctx_len, int device, int tp_rank, int tp_size, q3_handle **out) {
@@ -788,6 +955,7 @@ static int create_impl(const char *path, int ctx_len, int device, int tp_rank, i
         h->decode_path = 1;
         h->launches_per_step = 1;
     }
+    TRY(prefill_init(h));
     CKH(cudaDeviceSynchronize());
     *out = h;
     return Q3_OK;
@@ -881,6 +1049,9 @@ extern "C" void q3_destroy(q3_handle *h) {
         if (h->g_fwd[e]) cudaGraphExecDestroy(h->g_fwd[e]);
         if (h->g_greedy[e]) cudaGraphExecDestroy(h->g_greedy[e]);
     }
+    for (void *p : {(void *)h->pf_x, (void *)h->pf_q, (void *)h->pf_att, (void *)h->pf_hb, (void *)h->pf_xsT, (void *)h->pf_hsT,
+                    (void *)h->pf_xq, (void *)h->pf_hq, (void *)h->pf_tokens})
+        if (p) cudaFree(p);
     for (void *p : h->peer_maps) cudaIpcCloseMemHandle(p);
     for (void *p : h->allocs) cudaFree(p);
     if (h->h_logits) cudaFreeHost(h->h_logits);
@@ -1098,13 +1269,60 @@ extern "C" int q3_bench_kernel(q3_handle *h, int kind, int pos, int reps, float 
 }
 
 extern "C" int q3_prefill(q3_handle *h, const int *tokens, int n, int pos0, float *last_logits_host) {
-    // Sequential on-device decode steps until the batched tcgen05 path lands: same results as n
-    // forwards by construction.
     if (!h || !tokens || n <= 0) return fail(Q3_EINVAL, "bad prefill arguments");
-    for (int i = 0; i < n; i++) {
-        int rc = q3_forward(h, tokens[i], pos0 + i, i == n - 1 ? last_logits_host : nullptr);
-        if (rc) return rc;
+    if (pos0 < 0 || pos0 + n > h->cfg.seq_len) return fail(Q3_EINVAL, "index out of bounds: pos0 + n = %d > seq_len %d", pos0 + n, h->cfg.seq_len);
+    for (int i = 0; i < n; i++)
+        if (tokens[i] < 0 || tokens[i] >= h->cfg.vocab_size) return fail(Q3_EINVAL, "index out of bounds: token %d", tokens[i]);
+    CK(cudaSetDevice(h->device));
+    if (!h->pf_ok || h->exact || getenv("Q3_NO_PREFILL_GEMM")) {
+        // sequential decode steps: same results as n forwards by construction (exact mode, TP, odd shapes)
+        for (int i = 0; i < n; i++) {
+            int rc = q3_forward(h, tokens[i], pos0 + i, i == n - 1 ? last_logits_host : nullptr);
+            if (rc) return rc;
+        }
+        return Q3_OK;
     }
+    int rc;
+    if ((rc = prefill_run(h, tokens, n, pos0))) return rc;
+    // final norm + quantize + lm_head on the last token only (qwen3.rs:72-76)
+    if ((rc = set_tok_pos(h, tokens[n - 1], pos0 + n - 1))) return rc;
+    if (use_mega(h)) {
+        if ((rc = launch_mega(h, 0, 0, false, true, false, last_logits_host != nullptr))) return rc;
+    } else {
+        launch_head(h, h->stream);
+    }
+    if (last_logits_host) {
+        CK(cudaMemcpyAsync(h->h_logits, h->logits, (size_t)h->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        memcpy(last_logits_host, h->h_logits, (size_t)h->cfg.vocab_size * 4);
+    } else {
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    CK(cudaGetLastError());
+    return mega_check(h);
+}
+
+extern "C" int q3_bench_prefill(q3_handle *h, const int *tokens, int n, int pos0, float *ms_out) {
+    if (!h || !tokens || n <= 0) return fail(Q3_EINVAL, "bad prefill arguments");
+    if (!h->pf_ok) return fail(Q3_EUNSUPPORTED, "batched prefill unavailable: %s", h->pf_why.c_str());
+    if (pos0 < 0 || pos0 + n > h->cfg.seq_len) return fail(Q3_EINVAL, "index out of bounds");
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = prefill_run(h, tokens, n, pos0))) return rc; // warm-up (also sizes the buffers)
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(e0, h->stream));
+    if ((rc = prefill_run(h, tokens, n, pos0))) return rc;
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_out) *ms_out = ms;
     return Q3_OK;
 }
 
@@ -1246,6 +1464,37 @@ extern "C" int q3_op_matmul(int device, const int8_t *xq, const float *xs, const
     CK(cudaGetLastError());
     CK(cudaMemcpy(out, dout.p, (size_t)d * 4, cudaMemcpyDeviceToHost));
     if (group_dots_out) CK(cudaMemcpy(group_dots_out, ddots.p, (size_t)d * ng * 4, cudaMemcpyDeviceToHost));
+    return Q3_OK;
+}
+
+extern "C" int q3_op_gemm_q8(int device, const int8_t *xq, const float *xs, const int8_t *wq, const float *ws, int T, int N,
+                             int K, int gs, float *out) {
+    int rc = op_prologue(device, gs);
+    if (rc) return rc;
+    if (T <= 0 || N % 128 || K % 128 || K % gs) return fail(Q3_EINVAL, "need N %% 128 == 0, K %% 128 == 0");
+    const int Tpad = (T + 127) / 128 * 128, ng = K / gs;
+    DevBuf dxq, dxsT, dwq, dws, dwsT, dout;
+    if ((rc = dxq.alloc((size_t)Tpad * K)) || (rc = dxsT.alloc((size_t)ng * Tpad * 4)) || (rc = dwq.alloc((size_t)N * K)) ||
+        (rc = dws.alloc((size_t)N * ng * 4)) || (rc = dwsT.alloc((size_t)N * ng * 4)) || (rc = dout.alloc((size_t)T * N * 4)))
+        return rc;
+    CK(cudaMemset(dxq.p, 0, (size_t)Tpad * K));
+    CK(cudaMemcpy(dxq.p, xq, (size_t)T * K, cudaMemcpyHostToDevice));
+    std::vector<float> xsT((size_t)ng * Tpad, 0.0f);
+    for (int t = 0; t < T; t++)
+        for (int g = 0; g < ng; g++) xsT[(size_t)g * Tpad + t] = xs[(size_t)t * ng + g];
+    CK(cudaMemcpy(dxsT.p, xsT.data(), xsT.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dwq.p, wq, (size_t)N * K, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dws.p, ws, (size_t)N * ng * 4, cudaMemcpyHostToDevice));
+    dim3 tg((ng + 31) / 32, (N + 31) / 32);
+    k_transpose_f32<<<tg, dim3(32, 8)>>>(dws.as<float>(), dwsT.as<float>(), N, ng);
+    CUtensorMap mx, mw;
+    if ((rc = make_map_i8(&mx, dxq.p, Tpad, K)) || (rc = make_map_i8(&mw, dwq.p, N, K))) return rc;
+    PrefillGemmArgs a{};
+    a.T = T; a.Tpad = Tpad; a.N = N; a.K = K; a.wsT = dwsT.as<float>(); a.xsT = dxsT.as<float>(); a.out = dout.as<float>(); a.ld_out = N;
+    if ((rc = launch_gemm_q8<PF_EPI_STORE>(gs, mx, mw, a, 0))) return rc;
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, dout.p, (size_t)T * N * 4, cudaMemcpyDeviceToHost));
     return Q3_OK;
 }
 

@@ -1,0 +1,394 @@
+// q3_prefill.cuh -- batched (T-token) group-scaled int8 GEMM on the 5th-gen tensor cores.
+//
+//   out[t, r] = sum_g ( (f32)(sum_{k in g} xq[t,k] * wq[r,k]) * ws[r,g] ) * xs[t,g]        (tensor.rs:41-61, T rows at once)
+//
+// The int32 accumulator is only meaningful within one quantisation group, so the K loop is cut at
+// every group: tcgen05.mma.kind::i8 (A, B int8 from shared memory via TMA, 128B swizzle; D int32
+// in TMEM) accumulates GS/32 K-steps into one of four TMEM accumulator buffers, commits, and
+// moves on to the next buffer while the epilogue warps drain the previous one
+// (tcgen05.ld -> cvt -> (dot*ws)*xs -> f32 add).  Each epilogue thread owns one token row and
+// adds its groups in order g = 0..ng-1 with unfused multiplies, i.e. exactly the reference's
+// left fold: the GEMM result is bit-identical to `matmul` applied token by token.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "q3_mega.cuh" // mbarrier helpers
+
+namespace q3 {
+
+constexpr int PF_BM = 128, PF_BN = 128, PF_BK = 128; // tile: tokens x weight rows x K bytes per stage
+constexpr int PF_STAGES = 4;
+constexpr int PF_NACC = 4; // TMEM accumulator buffers (128 columns each)
+constexpr int PF_THREADS = 320;
+constexpr int PF_SMEM = PF_STAGES * (PF_BM * PF_BK + PF_BN * PF_BK) + 1024 + 256;
+
+enum { PF_EPI_STORE = 0, PF_EPI_QKV = 1, PF_EPI_RESID = 2, PF_EPI_SWIGLU = 3 };
+
+struct PrefillGemmArgs {
+    const float *wsT;  // [K/GS][N]  weight scales, group-major (transposed at load)
+    const float *xsT;  // [K/GS][Tpad] activation scales, group-major
+    int T, Tpad, N, K;
+    float *out;        // STORE: [T][N]; RESID: x[T][N] += ; SWIGLU: hb[T][N/2]
+    int ld_out;
+    // QKV epilogue
+    float *q;          // [T][AH]
+    float *kc, *vc;    // layer base of the caches [seq][KV]
+    int AH, KV, pos0;
+};
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+    // K-major, SWIZZLE_128B: 8-row atoms of 128 B, atoms 1024 B apart (SBO), LBO unused (=1), version 1
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ULL << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46) | (2ULL << 61);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity) {
+    long long t0 = clock64();
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap(); // never hang the GPU
+    }
+}
+
+template <int GS, int EPI>
+__global__ void __launch_bounds__(PF_THREADS, 1)
+    k_gemm_q8(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const PrefillGemmArgs a) {
+    extern __shared__ __align__(1024) uint8_t pf_smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(pf_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;                                  // [STAGES][128 rows][128 B]
+    uint8_t *sB = smem + PF_STAGES * PF_BM * PF_BK;      // [STAGES][128 rows][128 B]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + PF_STAGES * (PF_BM + PF_BN) * PF_BK);
+    uint64_t *empty = full + PF_STAGES;
+    uint64_t *tfull = empty + PF_STAGES;
+    uint64_t *tempty = tfull + PF_NACC;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + PF_NACC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * PF_BN, m0 = blockIdx.y * PF_BM;
+    const int nkb = a.K / PF_BK;
+    constexpr int GPS = PF_BK / GS; // groups per stage
+    constexpr int KPG = GS / 32;    // MMA K-steps per group
+    const int ng = a.K / GS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PF_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < PF_NACC; b++) {
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], 8); // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) { // TMEM: all 512 columns = 4 accumulator buffers of 128 x 128 int32
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------- TMA producer -------------------------------
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % PF_STAGES;
+                mbar_wait_spin(&empty[s], ((kb / PF_STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[s], (PF_BM + PF_BN) * PF_BK);
+                tma_load_2d(sA + (size_t)s * PF_BM * PF_BK, &map_x, kb * PF_BK, m0, &full[s]);
+                tma_load_2d(sB + (size_t)s * PF_BN * PF_BK, &map_w, kb * PF_BK, n0, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------- MMA issuer -------------------------------
+        if (lane == 0) {
+            // instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 128, M = 128
+            constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((PF_BN >> 3) << 17) | ((PF_BM >> 4) << 24);
+            int gi = 0;
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % PF_STAGES;
+                mbar_wait_spin(&full[s], (kb / PF_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_s = smem_u32(sA + (size_t)s * PF_BM * PF_BK);
+                const uint32_t b_s = smem_u32(sB + (size_t)s * PF_BN * PF_BK);
+#pragma unroll
+                for (int gg = 0; gg < GPS; gg++, gi++) {
+                    const int buf = gi % PF_NACC;
+                    mbar_wait_spin(&tempty[buf], ((gi / PF_NACC) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int kk = 0; kk < KPG; kk++) {
+                        const uint32_t koff = gg * GS + kk * 32; // bytes along K inside the 128 B swizzle span
+                        umma_i8(tmem_base + buf * PF_BN, umma_desc_k_sw128(a_s + koff), umma_desc_k_sw128(b_s + koff), IDESC, kk > 0);
+                    }
+                    umma_commit(&tfull[buf]); // accumulator of group gi complete -> epilogue
+                }
+                umma_commit(&empty[s]); // all MMAs reading this stage retired -> TMA may refill it
+            }
+        }
+    } else {
+        // ------------------------------- epilogue -------------------------------
+        const int quad = warp & 3;         // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
+        const int half = (warp - 2) >> 2;  // which 64 accumulator columns
+        const int m = quad * 32 + lane;    // row of the tile = token
+        const int t = m0 + m;
+        float acc[64];
+#pragma unroll
+        for (int j = 0; j < 64; j++) acc[j] = 0.0f;
+        const float *ws_col = a.wsT + n0 + half * 64;
+        for (int gi = 0; gi < ng; gi++) {
+            const int buf = gi % PF_NACC;
+            const float xs = a.xsT[(size_t)gi * a.Tpad + t];
+            mbar_wait_spin(&tfull[buf], (gi / PF_NACC) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t d[64];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * PF_BN + half * 64;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+                "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+                : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]),
+                  "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]), "=r"(d[16]), "=r"(d[17]), "=r"(d[18]),
+                  "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]), "=r"(d[23]), "=r"(d[24]), "=r"(d[25]), "=r"(d[26]), "=r"(d[27]),
+                  "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31]), "=r"(d[32]), "=r"(d[33]), "=r"(d[34]), "=r"(d[35]), "=r"(d[36]),
+                  "=r"(d[37]), "=r"(d[38]), "=r"(d[39]), "=r"(d[40]), "=r"(d[41]), "=r"(d[42]), "=r"(d[43]), "=r"(d[44]), "=r"(d[45]),
+                  "=r"(d[46]), "=r"(d[47]), "=r"(d[48]), "=r"(d[49]), "=r"(d[50]), "=r"(d[51]), "=r"(d[52]), "=r"(d[53]), "=r"(d[54]),
+                  "=r"(d[55]), "=r"(d[56]), "=r"(d[57]), "=r"(d[58]), "=r"(d[59]), "=r"(d[60]), "=r"(d[61]), "=r"(d[62]), "=r"(d[63])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]); // buffer drained into registers: MMA may reuse it
+            const float4 *wsg = reinterpret_cast<const float4 *>(ws_col + (size_t)gi * a.N);
+#pragma unroll
+            for (int j4 = 0; j4 < 16; j4++) {
+                const float4 w = __ldg(wsg + j4);
+                // (dot as f32 * weight_scale) * input_scale, then the left-fold add (tensor.rs:59-61)
+                acc[4 * j4 + 0] = __fadd_rn(acc[4 * j4 + 0], __fmul_rn(__fmul_rn((float)(int)d[4 * j4 + 0], w.x), xs));
+                acc[4 * j4 + 1] = __fadd_rn(acc[4 * j4 + 1], __fmul_rn(__fmul_rn((float)(int)d[4 * j4 + 1], w.y), xs));
+                acc[4 * j4 + 2] = __fadd_rn(acc[4 * j4 + 2], __fmul_rn(__fmul_rn((float)(int)d[4 * j4 + 2], w.z), xs));
+                acc[4 * j4 + 3] = __fadd_rn(acc[4 * j4 + 3], __fmul_rn(__fmul_rn((float)(int)d[4 * j4 + 3], w.w), xs));
+            }
+        }
+        // ---- write the 64 outputs of this token row ----
+        if (t < a.T) {
+            const int c0 = n0 + half * 64;
+            if (EPI == PF_EPI_STORE) {
+                float4 *dst = reinterpret_cast<float4 *>(a.out + (size_t)t * a.ld_out + c0);
+#pragma unroll
+                for (int j4 = 0; j4 < 16; j4++) dst[j4] = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
+            } else if (EPI == PF_EPI_RESID) { // x += (layers.rs:249-259)
+                float4 *dst = reinterpret_cast<float4 *>(a.out + (size_t)t * a.ld_out + c0);
+#pragma unroll
+                for (int j4 = 0; j4 < 16; j4++) {
+                    float4 o = dst[j4];
+                    o.x = __fadd_rn(o.x, acc[4 * j4]);
+                    o.y = __fadd_rn(o.y, acc[4 * j4 + 1]);
+                    o.z = __fadd_rn(o.z, acc[4 * j4 + 2]);
+                    o.w = __fadd_rn(o.w, acc[4 * j4 + 3]);
+                    dst[j4] = o;
+                }
+            } else if (EPI == PF_EPI_SWIGLU) { // rows interleaved (gate_j, up_j): layers.rs:472-475
+                float2 *dst = reinterpret_cast<float2 *>(a.out + (size_t)t * a.ld_out + c0 / 2);
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float g0 = acc[2 * j], u0 = acc[2 * j + 1], g1 = acc[2 * j + 2], u1 = acc[2 * j + 3];
+                    float s0 = __fmul_rn(g0, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-g0))));
+                    float s1 = __fmul_rn(g1, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-g1))));
+                    dst[j / 2] = make_float2(__fmul_rn(s0, u0), __fmul_rn(s1, u1));
+                }
+            } else { // PF_EPI_QKV: rows [0,AH) -> q[t], [AH,AH+KV) -> K cache row pos0+t, then V (layers.rs:334-336)
+                float *dst;
+                if (c0 < a.AH) dst = a.q + (size_t)t * a.AH + c0;
+                else if (c0 < a.AH + a.KV) dst = a.kc + (size_t)(a.pos0 + t) * a.KV + (c0 - a.AH);
+                else dst = a.vc + (size_t)(a.pos0 + t) * a.KV + (c0 - a.AH - a.KV);
+                float4 *d4 = reinterpret_cast<float4 *>(dst);
+#pragma unroll
+                for (int j4 = 0; j4 < 16; j4++) d4[j4] = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// batched helpers around the GEMM
+// ------------------------------------------------------------------------------------------
+// per-token RMSNorm (+ embedding gather) + group quantise; scales written group-major [ng][Tpad].
+// grid = T, block = 256.  (layers.rs:72-76, 109-130; tensor.rs:91-119)
+template <int GS>
+__global__ void __launch_bounds__(256) k_pf_norm_quant(float *x, const float *w, int8_t *q, float *sT, int n, int Tpad,
+                                                       const int8_t *embed_q, const float *embed_s, const int *tokens, int write_normed) {
+    __shared__ float red[8];
+    __shared__ float s_f;
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *xr = x + (size_t)t * n;
+    const int n4 = n >> 2;
+    constexpr int MAXV = 16; // n <= 16384
+    float4 v[MAXV];
+    float ss = 0.0f;
+#pragma unroll
+    for (int k = 0; k < MAXV; k++) {
+        int i4 = tid + k * 256;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i4 < n4) {
+            if (embed_q) {
+                size_t base = (size_t)tokens[t] * n + (size_t)i4 * 4;
+                char4 e = *reinterpret_cast<const char4 *>(embed_q + base);
+                float sc = embed_s[base / GS];
+                v[k] = make_float4((float)e.x * sc, (float)e.y * sc, (float)e.z * sc, (float)e.w * sc);
+                reinterpret_cast<float4 *>(xr)[i4] = v[k];
+            } else {
+                v[k] = reinterpret_cast<const float4 *>(xr)[i4];
+            }
+            ss += __fmul_rn(v[k].x, v[k].x);
+            ss += __fmul_rn(v[k].y, v[k].y);
+            ss += __fmul_rn(v[k].z, v[k].z);
+            ss += __fmul_rn(v[k].w, v[k].w);
+        }
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    if (tid == 0) {
+        float tsum = 0.0f;
+        for (int i = 0; i < 8; i++) tsum += red[i];
+        s_f = __fdiv_rn(1.0f, sqrtf(__fadd_rn(__fdiv_rn(tsum, (float)n), NORM_EPS)));
+    }
+    __syncthreads();
+    const float f = s_f;
+#pragma unroll
+    for (int k = 0; k < MAXV; k++) {
+        int i4 = tid + k * 256;
+        if (i4 - lane < n4) {
+            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i4 < n4) {
+                float4 wv = __ldg(reinterpret_cast<const float4 *>(w) + i4);
+                y.x = __fmul_rn(wv.x, __fmul_rn(f, v[k].x));
+                y.y = __fmul_rn(wv.y, __fmul_rn(f, v[k].y));
+                y.z = __fmul_rn(wv.z, __fmul_rn(f, v[k].z));
+                y.w = __fmul_rn(wv.w, __fmul_rn(f, v[k].w));
+            }
+            uint32_t packed;
+            float scale;
+            quantize_group4<GS>(y, packed, scale);
+            if (i4 < n4) {
+                reinterpret_cast<uint32_t *>(q + (size_t)t * n)[i4] = packed;
+                if ((i4 % (GS / 4)) == 0) sT[(size_t)(i4 / (GS / 4)) * Tpad + t] = scale;
+                if (write_normed) reinterpret_cast<float4 *>(xr)[i4] = y;
+            }
+        }
+    }
+}
+
+// per-token group quantise of [T][n] f32; scales group-major.  grid = T.
+template <int GS>
+__global__ void __launch_bounds__(256) k_pf_quantize(const float *__restrict__ x, int8_t *q, float *sT, int n, int Tpad) {
+    const int t = blockIdx.x, lane = threadIdx.x & 31;
+    const int n4 = n >> 2;
+    const float *xr = x + (size_t)t * n;
+    for (int base = threadIdx.x - lane; base < n4; base += 256) {
+        int i4 = base + lane;
+        float4 y = (i4 < n4) ? reinterpret_cast<const float4 *>(xr)[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t packed;
+        float scale;
+        quantize_group4<GS>(y, packed, scale);
+        if (i4 < n4) {
+            reinterpret_cast<uint32_t *>(q + (size_t)t * n)[i4] = packed;
+            if ((i4 % (GS / 4)) == 0) sT[(size_t)(i4 / (GS / 4)) * Tpad + t] = scale;
+        }
+    }
+}
+
+// QK-norm + RoPE for T tokens: grid = (ceil((n_heads + n_kv)/4), T), block 128 (one warp per head).
+__global__ void __launch_bounds__(128) k_pf_qknorm_rope(float *q, float *kc_layer, const float *q_ln, const float *k_ln,
+                                                        const float *rope, int pos0, int n_heads, int n_kv, int AH, int KV) {
+    const int lane = threadIdx.x & 31;
+    const int head = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int t = blockIdx.y;
+    if (head >= n_heads + n_kv) return;
+    const int pos = pos0 + t;
+    float *p = head < n_heads ? q + (size_t)t * AH + (size_t)head * HEAD_DIM
+                              : kc_layer + (size_t)pos * KV + (size_t)(head - n_heads) * HEAD_DIM;
+    float4 v = reinterpret_cast<float4 *>(p)[lane];
+    float4 r = qk_norm_rope(v, head < n_heads ? q_ln : k_ln, rope + (size_t)pos * HEAD_DIM, lane);
+    reinterpret_cast<float4 *>(p)[lane] = r;
+}
+
+// Causal attention for T query tokens over the cache (positions 0..pos0+t), f32, one warp per
+// (token, head), online softmax; output [T][AH].  grid = (n_heads, ceil(T/4)), block 128.
+// (layers.rs:374-419.)  Simple and exact-ish; not the prefill bottleneck at the sizes tested.
+__global__ void __launch_bounds__(128) k_pf_attention(const float *__restrict__ q, const float *__restrict__ kc,
+                                                      const float *__restrict__ vc, float *out, int T, int pos0, int AH, int KV,
+                                                      int kv_mul) {
+    const int head = blockIdx.x, lane = threadIdx.x & 31;
+    const int t = blockIdx.y * 4 + (threadIdx.x >> 5);
+    if (t >= T) return;
+    const int kvh = head / kv_mul;
+    const float scale = __fdiv_rn(1.0f, sqrtf((float)HEAD_DIM));
+    const float4 qv = reinterpret_cast<const float4 *>(q + (size_t)t * AH + (size_t)head * HEAD_DIM)[lane];
+    const float *kb = kc + (size_t)kvh * HEAD_DIM + lane * 4;
+    const float *vb = vc + (size_t)kvh * HEAD_DIM + lane * 4;
+    float m = -INFINITY, l = 0.0f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int n = pos0 + t + 1;
+    for (int p = 0; p < n; p++) {
+        const float4 kv = *reinterpret_cast<const float4 *>(kb + (size_t)p * KV);
+        const float4 vv = *reinterpret_cast<const float4 *>(vb + (size_t)p * KV);
+        float s = qv.x * kv.x + qv.y * kv.y + qv.z * kv.z + qv.w * kv.w;
+        s = __fmul_rn(warp_sum(s), scale);
+        const float mn = fmaxf(m, s);
+        const float corr = expf(m - mn), pe = expf(s - mn);
+        l = l * corr + pe;
+        acc.x = acc.x * corr + pe * vv.x;
+        acc.y = acc.y * corr + pe * vv.y;
+        acc.z = acc.z * corr + pe * vv.z;
+        acc.w = acc.w * corr + pe * vv.w;
+        m = mn;
+    }
+    const float inv = __fdiv_rn(1.0f, l);
+    reinterpret_cast<float4 *>(out + (size_t)t * AH + (size_t)head * HEAD_DIM)[lane] =
+        make_float4(__fmul_rn(acc.x, inv), __fmul_rn(acc.y, inv), __fmul_rn(acc.z, inv), __fmul_rn(acc.w, inv));
+}
+
+// [rows][ng] -> [ng][rows] (weight scales, once at load)
+__global__ void k_transpose_f32(const float *__restrict__ in, float *out, int rows, int cols) {
+    __shared__ float tile[32][33];
+    int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 32 + threadIdx.y;
+    for (int j = 0; j < 32; j += 8)
+        if (r + j < rows && c < cols) tile[threadIdx.y + j][threadIdx.x] = in[(size_t)(r + j) * cols + c];
+    __syncthreads();
+    int oc = blockIdx.y * 32 + threadIdx.x, orow = blockIdx.x * 32 + threadIdx.y;
+    for (int j = 0; j < 32; j += 8)
+        if (orow + j < cols && oc < rows) out[(size_t)(orow + j) * rows + oc] = tile[threadIdx.x][threadIdx.y + j];
+}
+
+} // namespace q3

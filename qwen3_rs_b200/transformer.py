@@ -68,6 +68,7 @@ ABI = {
     "q3_forward_argmax": (_i, [_vp, _i, _i, C.POINTER(_i)]),
     "q3_decode_greedy": (_i, [_vp, _i, _i, _i, _vp]),
     "q3_prefill": (_i, [_vp, _vp, _i, _i, _vp]),
+    "q3_bench_prefill": (_i, [_vp, _vp, _i, _i, C.POINTER(_f)]),
     "q3_reset": (_i, [_vp]),
     "q3_logits_device": (_vp, [_vp]),
     "q3_kv_read": (_i, [_vp, _i, _i, _i, _vp, _vp]),
@@ -82,6 +83,7 @@ ABI = {
     "q3_op_quantize": (_i, [_i, _vp, _i, _i, _vp, _vp]),
     "q3_op_matmul": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "q3_op_expf": (_i, [_i, _vp, _i, _vp]),
+    "q3_op_gemm_q8": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "q3_op_rmsnorm": (_i, [_i, _vp, _vp, _i, _vp]),
     "q3_op_quantize_q80": (_i, [_i, _vp, _sz, _i, _vp, _vp]),
     "q3_last_error": (C.c_char_p, []),
@@ -151,6 +153,12 @@ class Transformer:
         t = np.ascontiguousarray(tokens, np.int32)
         _check(load_library().q3_prefill(self._h, _ptr(t), t.size, int(pos0), _ptr(self._logits) if want_logits else None))
         return self._logits.copy() if want_logits else None
+
+    def bench_prefill(self, tokens: Sequence[int], pos0: int = 0) -> float:
+        t = np.ascontiguousarray(tokens, np.int32)
+        ms = C.c_float(0)
+        _check(load_library().q3_bench_prefill(self._h, _ptr(t), t.size, int(pos0), C.byref(ms)))
+        return ms.value
 
     def reset(self) -> None:
         _check(load_library().q3_reset(self._h))
@@ -308,6 +316,16 @@ def op_matmul(xq, xs, wq, ws, n: int, d: int, gs: int, want_dots: bool = False, 
     dots = np.empty((d, n // gs), np.int32) if want_dots else None
     _check(load_library().q3_op_matmul(device, _ptr(xq), _ptr(xs), _ptr(wq), _ptr(ws), n, d, gs, int(exact), _ptr(out), _ptr(dots)))
     return (out, dots) if want_dots else out
+
+
+def op_gemm_q8(xq, xs, wq, ws, T: int, N: int, K: int, gs: int, device: int = 0):
+    xq = np.ascontiguousarray(xq, np.int8)
+    xs = np.ascontiguousarray(xs, np.float32)
+    wq = np.ascontiguousarray(wq, np.int8)
+    ws = np.ascontiguousarray(ws, np.float32)
+    out = np.empty((T, N), np.float32)
+    _check(load_library().q3_op_gemm_q8(device, _ptr(xq), _ptr(xs), _ptr(wq), _ptr(ws), T, N, K, gs, _ptr(out)))
+    return out
 
 
 def op_rmsnorm(x, w, device: int = 0):

@@ -21,6 +21,7 @@ import pytest
 from conftest import GOLDEN_CASES
 from oracle import binding as orc
 from qwen3_rs_b200 import generation, transformer as T
+from qwen3_rs_b200 import transformer as T_mod
 from qwen3_rs_b200.sampler import Sampler, argmax_last
 
 pytestmark = pytest.mark.gpu
@@ -446,3 +447,55 @@ def test_qwen3_06b_fast_mode_free_running_vs_noise_floor(q06, ckpt):
           f"argmax agreement {agree}/64")
     assert mism == 0
     assert np.median(gpu_err) <= 3 * np.median(noise_err) + LOGIT_TOL
+
+
+# ---- batched prefill: tcgen05 int8 GEMM -----------------------------------------------------------
+@pytest.mark.parametrize("T,N,K,gs", [(128, 128, 128, 64), (37, 256, 512, 64), (300, 384, 1024, 32), (130, 128, 2560, 128),
+                                      (257, 512, 4096, 64)])
+def test_tensor_core_gemm_bit_identical_to_reference_matmul(T, N, K, gs):
+    """tcgen05.mma.kind::i8 with per-group TMEM drains: every output equals the oracle's per-token matmul
+    bit for bit (exact int32 group dots, identical f32 terms, groups added in order)."""
+    rng = np.random.default_rng(T + N + K)
+    wq = rng.integers(-127, 128, size=N * K, dtype=np.int8)
+    ws = (rng.random(N * K // gs) * 0.02).astype(np.float32)
+    xq = np.empty((T, K), np.int8)
+    xs = np.empty((T, K // gs), np.float32)
+    for t in range(T):
+        xq[t], xs[t] = orc.quantize(rng.standard_normal(K).astype(np.float32) * (1 + t % 3), gs)
+    xq[0, :] = 127  # extreme row
+    wq[:K] = -127
+    out = T_mod.op_gemm_q8(xq, xs, wq, ws, T, N, K, gs)
+    ref = np.stack([orc.matmul(xq[t], xs[t], wq, ws, K, N, gs) for t in range(T)])
+    assert np.array_equal(out, ref), float(np.abs(out - ref).max())
+
+
+@pytest.mark.parametrize("name,gs,seed,T", [("tiny-untied", 64, 1, 37), ("small", 128, 2, 130), ("tiny", 64, 0, 5)])
+def test_prefill_matches_sequential_forwards(models, name, gs, seed, T):
+    """q3_prefill (batched tensor-core path) leaves the KV cache and the last-token logits as T sequential
+    forwards would, up to fast-mode float reassociation."""
+    m = models(name, gs, seed)
+    c = m.get_config()
+    rng = np.random.default_rng(T)
+    toks = rng.integers(0, c.vocab_size, T).tolist()
+    m.reset()
+    for p, t in enumerate(toks):
+        lg_seq = m.forward(t, p)
+    kv_seq = [m.kv_read(l, 0, T) for l in range(c.n_layers)]
+    m.reset()
+    lg_pf = m.prefill(toks, 0)
+    kv_pf = [m.kv_read(l, 0, T) for l in range(c.n_layers)]
+    # layer 0 depends only on embedding -> norm -> QKV GEMM -> QK-norm/RoPE: no cascade possible
+    np.testing.assert_allclose(kv_pf[0][0], kv_seq[0][0], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(kv_pf[0][1], kv_seq[0][1], rtol=0, atol=2e-3)
+    assert np.median(np.abs(kv_pf[0][1] - kv_seq[0][1])) <= 1e-6
+    for l in range(c.n_layers):
+        assert np.abs(kv_pf[l][1] - kv_seq[l][1]).max() <= 0.05 * np.abs(kv_seq[l][1]).max() + 1e-2
+        k, v = m.kv_read(l, T, 1)
+        assert not k.any() and not v.any()
+    err = float(np.abs(lg_pf - lg_seq).max())
+    print(f"{name} prefill T={T}: max|dlogit| {err:.2e}")
+    assert err <= 0.05 * float(np.abs(lg_seq).max()) + LOGIT_TOL
+    # decode continues seamlessly from the prefilled cache
+    nxt = argmax_last(lg_pf)
+    a = m.forward(nxt, T)
+    assert np.isfinite(a).all()
