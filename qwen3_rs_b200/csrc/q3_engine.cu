@@ -721,6 +721,10 @@ static int prefill_init(q3_handle *h) {
         return 0;
     }
     if (!get_encode_fn()) { h->pf_why = "cuTensorMapEncodeTiled unavailable"; return 0; }
+    CK(cudaFuncSetAttribute(k_pf_attention<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFA_SMEM));
+    CK(cudaFuncSetAttribute(k_pf_attention<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFA_SMEM));
+    CK(cudaFuncSetAttribute(k_pf_attention<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFA_SMEM));
+    CK(cudaFuncSetAttribute(k_pf_attention<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFA_SMEM));
     int rc;
     for (auto &W : h->layers) {
         if ((rc = prefill_prepare_tensor(h, W.qkv))) return rc;
@@ -786,8 +790,16 @@ static int prefill_run(q3_handle *h, const int *tokens_host, int T, int pos0) {
         if ((rc = launch_gemm_q8<PF_EPI_QKV>(gs, mx_dim, W.qkv.map, g, s))) return rc;
         dim3 rg((h->n_heads_l + h->n_kv_l + 3) / 4, T);
         k_pf_qknorm_rope<<<rg, 128, 0, s>>>(h->pf_q, kc_l, W.q_ln, W.k_ln, h->rope, pos0, h->n_heads_l, h->n_kv_l, AH, KV);
-        dim3 ag(h->n_heads_l, (T + 3) / 4);
-        k_pf_attention<<<ag, 128, 0, s>>>(h->pf_q, kc_l, vc_l, h->pf_att, T, pos0, AH, KV, h->kv_mul);
+        {
+            const int bq = PFA_R / h->kv_mul;
+            dim3 ag(h->n_kv_l, (T + bq - 1) / bq);
+            switch (h->kv_mul) {
+            case 1: k_pf_attention<1><<<ag, 256, PFA_SMEM, s>>>(h->pf_q, kc_l, vc_l, h->pf_att, T, pos0, AH, KV); break;
+            case 2: k_pf_attention<2><<<ag, 256, PFA_SMEM, s>>>(h->pf_q, kc_l, vc_l, h->pf_att, T, pos0, AH, KV); break;
+            case 4: k_pf_attention<4><<<ag, 256, PFA_SMEM, s>>>(h->pf_q, kc_l, vc_l, h->pf_att, T, pos0, AH, KV); break;
+            case 8: k_pf_attention<8><<<ag, 256, PFA_SMEM, s>>>(h->pf_q, kc_l, vc_l, h->pf_att, T, pos0, AH, KV); break;
+            }
+        }
         GS_DISPATCH(gs, (k_pf_quantize<GS><<<T, 256, 0, s>>>(h->pf_att, h->pf_xq, h->pf_xsT, AH, Tpad)));
         PrefillGemmArgs o{};
         o.T = T; o.Tpad = Tpad; o.K = AH; o.N = dim; o.wsT = W.wo.sT; o.xsT = h->pf_xsT; o.out = h->pf_x; o.ld_out = dim;

@@ -343,40 +343,125 @@ __global__ void __launch_bounds__(128) k_pf_qknorm_rope(float *q, float *kc_laye
     reinterpret_cast<float4 *>(p)[lane] = r;
 }
 
-// Causal attention for T query tokens over the cache (positions 0..pos0+t), f32, one warp per
-// (token, head), online softmax; output [T][AH].  grid = (n_heads, ceil(T/4)), block 128.
-// (layers.rs:374-419.)  Simple and exact-ish; not the prefill bottleneck at the sizes tested.
-__global__ void __launch_bounds__(128) k_pf_attention(const float *__restrict__ q, const float *__restrict__ kc,
-                                                      const float *__restrict__ vc, float *out, int T, int pos0, int AH, int KV,
-                                                      int kv_mul) {
-    const int head = blockIdx.x, lane = threadIdx.x & 31;
-    const int t = blockIdx.y * 4 + (threadIdx.x >> 5);
-    if (t >= T) return;
-    const int kvh = head / kv_mul;
+// Causal attention for T query tokens over the cache (key positions 0..pos0+t for query t), f32 on the
+// CUDA cores, flash-attention tiling (layers.rs:374-419 with an online softmax).  One CTA = one kv head
+// x a tile of BQ = 64/KVMUL query tokens, i.e. 64 query rows (token, head-in-group) that all share the
+// same K/V stream; key tiles of 32 positions go through shared memory.  256 threads: thread (ty, tx)
+// owns a 4-row x 2-key micro-tile of the score tile and a 4-row x 8-dim micro-tile of the output.
+constexpr int PFA_R = 64, PFA_BK = 32, PFA_LD = HEAD_DIM + 4, PFA_LDP = PFA_BK + 4;
+constexpr int PFA_SMEM = (PFA_R * PFA_LD + 2 * PFA_BK * PFA_LD + PFA_R * PFA_LDP) * 4;
+
+template <int KVMUL>
+__global__ void __launch_bounds__(256, 2) k_pf_attention(const float *__restrict__ q, const float *__restrict__ kc,
+                                                         const float *__restrict__ vc, float *out, int T, int pos0, int AH, int KV) {
+    extern __shared__ __align__(16) float pfa_smem[];
+    float *Qs = pfa_smem;                 // [64][132]
+    float *Ks = Qs + PFA_R * PFA_LD;      // [32][132]
+    float *Vs = Ks + PFA_BK * PFA_LD;     // [32][132]
+    float *Ps = Vs + PFA_BK * PFA_LD;     // [64][36]
+    constexpr int BQ = PFA_R / KVMUL;
+    const int kvh = blockIdx.x, q0 = blockIdx.y * BQ;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const float scale = __fdiv_rn(1.0f, sqrtf((float)HEAD_DIM));
-    const float4 qv = reinterpret_cast<const float4 *>(q + (size_t)t * AH + (size_t)head * HEAD_DIM)[lane];
-    const float *kb = kc + (size_t)kvh * HEAD_DIM + lane * 4;
-    const float *vb = vc + (size_t)kvh * HEAD_DIM + lane * 4;
-    float m = -INFINITY, l = 0.0f;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int n = pos0 + t + 1;
-    for (int p = 0; p < n; p++) {
-        const float4 kv = *reinterpret_cast<const float4 *>(kb + (size_t)p * KV);
-        const float4 vv = *reinterpret_cast<const float4 *>(vb + (size_t)p * KV);
-        float s = qv.x * kv.x + qv.y * kv.y + qv.z * kv.z + qv.w * kv.w;
-        s = __fmul_rn(warp_sum(s), scale);
-        const float mn = fmaxf(m, s);
-        const float corr = expf(m - mn), pe = expf(s - mn);
-        l = l * corr + pe;
-        acc.x = acc.x * corr + pe * vv.x;
-        acc.y = acc.y * corr + pe * vv.y;
-        acc.z = acc.z * corr + pe * vv.z;
-        acc.w = acc.w * corr + pe * vv.w;
-        m = mn;
+    // Q tile: row r <-> (token q0 + r / KVMUL, head kvh*KVMUL + r % KVMUL)
+    for (int i = tid; i < PFA_R * 32; i += 256) {
+        const int r = i >> 5, c4 = i & 31;
+        const int tq = q0 + r / KVMUL;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tq < T) v = reinterpret_cast<const float4 *>(q + (size_t)tq * AH + (size_t)(kvh * KVMUL + r % KVMUL) * HEAD_DIM)[c4];
+        *reinterpret_cast<float4 *>(Qs + r * PFA_LD + c4 * 4) = v;
     }
-    const float inv = __fdiv_rn(1.0f, l);
-    reinterpret_cast<float4 *>(out + (size_t)t * AH + (size_t)head * HEAD_DIM)[lane] =
-        make_float4(__fmul_rn(acc.x, inv), __fmul_rn(acc.y, inv), __fmul_rn(acc.z, inv), __fmul_rn(acc.w, inv));
+    float m[4], l[4], acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        m[i] = -INFINITY;
+        l[i] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
+    }
+    int last_q = q0 + BQ - 1;
+    if (last_q > T - 1) last_q = T - 1;
+    const int nkeys = pos0 + last_q + 1; // causal horizon of the last query in the tile
+    const float *kb = kc + (size_t)kvh * HEAD_DIM, *vb = vc + (size_t)kvh * HEAD_DIM;
+    for (int k0 = 0; k0 < nkeys; k0 += PFA_BK) {
+        __syncthreads(); // previous tile fully consumed (also orders the Q tile stores on the first pass)
+        for (int i = tid; i < PFA_BK * 32; i += 256) {
+            const int p = i >> 5, c4 = i & 31;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (k0 + p < nkeys) {
+                kv = reinterpret_cast<const float4 *>(kb + (size_t)(k0 + p) * KV)[c4];
+                vv = reinterpret_cast<const float4 *>(vb + (size_t)(k0 + p) * KV)[c4];
+            }
+            *reinterpret_cast<float4 *>(Ks + p * PFA_LD + c4 * 4) = kv;
+            *reinterpret_cast<float4 *>(Vs + p * PFA_LD + c4 * 4) = vv;
+        }
+        __syncthreads();
+        // scores: rows 4*ty..+3, keys 2*tx, 2*tx+1
+        float sc[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; i++) sc[i][0] = sc[i][1] = 0.0f;
+#pragma unroll 8
+        for (int d4 = 0; d4 < 32; d4++) {
+            float4 kq[2], qq[4];
+#pragma unroll
+            for (int j = 0; j < 2; j++) kq[j] = *reinterpret_cast<const float4 *>(Ks + (2 * tx + j) * PFA_LD + d4 * 4);
+#pragma unroll
+            for (int i = 0; i < 4; i++) qq[i] = *reinterpret_cast<const float4 *>(Qs + (4 * ty + i) * PFA_LD + d4 * 4);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+                    sc[i][j] += qq[i].x * kq[j].x + qq[i].y * kq[j].y + qq[i].z * kq[j].z + qq[i].w * kq[j].w;
+        }
+        // online softmax per row (a row's 32 scores live in the 16 lanes that share ty)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int r = 4 * ty + i;
+            const int qpos = pos0 + q0 + r / KVMUL;
+            float s0 = (k0 + 2 * tx <= qpos) ? __fmul_rn(sc[i][0], scale) : -INFINITY;
+            float s1 = (k0 + 2 * tx + 1 <= qpos) ? __fmul_rn(sc[i][1], scale) : -INFINITY;
+            float mx = fmaxf(s0, s1);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const float mn = fmaxf(m[i], mx);
+            const float corr = (mn == -INFINITY) ? 1.0f : expf(m[i] - mn);
+            const float p0 = (s0 == -INFINITY) ? 0.0f : expf(s0 - mn);
+            const float p1 = (s1 == -INFINITY) ? 0.0f : expf(s1 - mn);
+            float ps = p0 + p1;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+            l[i] = l[i] * corr + ps;
+            m[i] = mn;
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[i][j] *= corr;
+            Ps[r * PFA_LDP + 2 * tx] = p0;
+            Ps[r * PFA_LDP + 2 * tx + 1] = p1;
+        }
+        __syncthreads();
+        // out[r][8*tx .. +7] += sum_p P[r][p] * V[p][8*tx .. +7]
+#pragma unroll 4
+        for (int p = 0; p < PFA_BK; p++) {
+            const float4 v0 = *reinterpret_cast<const float4 *>(Vs + p * PFA_LD + 8 * tx);
+            const float4 v1 = *reinterpret_cast<const float4 *>(Vs + p * PFA_LD + 8 * tx + 4);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float pr = Ps[(4 * ty + i) * PFA_LDP + p];
+                acc[i][0] += pr * v0.x; acc[i][1] += pr * v0.y; acc[i][2] += pr * v0.z; acc[i][3] += pr * v0.w;
+                acc[i][4] += pr * v1.x; acc[i][5] += pr * v1.y; acc[i][6] += pr * v1.z; acc[i][7] += pr * v1.w;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = 4 * ty + i;
+        const int tq = q0 + r / KVMUL;
+        if (tq < T) {
+            const float inv = __fdiv_rn(1.0f, l[i]);
+            float *dst = out + (size_t)tq * AH + (size_t)(kvh * KVMUL + r % KVMUL) * HEAD_DIM + 8 * tx;
+            reinterpret_cast<float4 *>(dst)[0] = make_float4(__fmul_rn(acc[i][0], inv), __fmul_rn(acc[i][1], inv), __fmul_rn(acc[i][2], inv), __fmul_rn(acc[i][3], inv));
+            reinterpret_cast<float4 *>(dst)[1] = make_float4(__fmul_rn(acc[i][4], inv), __fmul_rn(acc[i][5], inv), __fmul_rn(acc[i][6], inv), __fmul_rn(acc[i][7], inv));
+        }
+    }
 }
 
 // [rows][ng] -> [ng][rows] (weight scales, once at load)
