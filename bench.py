@@ -44,6 +44,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Exactly ONE JSON line may reach stdout, but native libraries write there too (NCCL prints its version
+# banner to fd 1).  So fd 1 is pointed at stderr for the whole run and the result line goes to a saved
+# duplicate of the original stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 # ---------------------------------------------------------------------------------------------
 # checkpoint (synthetic, exported by the repo's exporter)
 # ---------------------------------------------------------------------------------------------
@@ -205,7 +216,7 @@ def run_reference(args, rank: int, world: int):
         "gpu_launches": 0,
         "note": "reference = C restatement of qwen3-rs's CPU forward (oracle/q3_oracle.c); the Rust toolchain is absent so the reference itself cannot be built",
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(args, n_gpus: int, where: str) -> dict:
@@ -260,6 +271,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the forward path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -393,7 +405,7 @@ def main():
         "clocks": clk, "roofline": roof, "token_roofline": token_roof, "graph_path_kernels": kernels, "cpu_baseline": cpu,
         "decode_path": "persistent" if persistent else "graph",
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     m.close()
     if world > 1:
         dist.destroy_process_group()

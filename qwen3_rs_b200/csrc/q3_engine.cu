@@ -98,8 +98,7 @@ struct q3_handle {
     bool mega_ok = false;
     std::string mega_why;
     MegaArgs margs{};
-    unsigned long long bar_base = 0;
-    unsigned int xepoch = 0;
+    unsigned long long bar_base = 0, xbar_base = 0;
     int *d_status = nullptr;  // device abort flag raised by a timed-out wait inside the kernel
     float *x2 = nullptr, *kraw = nullptr, *part_buf[2] = {nullptr, nullptr};
     unsigned long long *d_best = nullptr, *d_bar = nullptr;
@@ -579,7 +578,7 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
     // until q3_tp_connect every "peer" slot points at this rank's own buffers
     for (int r = 0; r < MEGA_MAX_TP; r++) {
         a.part[0][r] = h->part_buf[0]; a.part[1][r] = h->part_buf[1];
-        a.logits[r] = h->logits; a.best[r] = h->d_best; a.flags[r] = h->d_flags;
+        a.logits[r] = h->logits; a.best[r] = h->d_best; a.xbar[r] = (unsigned long long *)h->d_flags;
     }
     GS_DISPATCH(gs, (h->mega_fn = mega_kernel_for<GS>(h->kv_mul)));
     if (!h->mega_fn) { h->mega_why = "no kernel for this GQA factor"; return 0; }
@@ -599,13 +598,13 @@ static int launch_mega(q3_handle *h, int l0, int l1, bool from_embed, bool run_h
     a.layer0 = l0; a.layer1 = l1; a.from_embed = from_embed; a.run_head = run_head; a.feedback = feedback;
     a.gather_logits = gather && h->tp_size > 1;
     a.bar_base = h->bar_base;
-    a.xepoch_base = h->xepoch;
+    a.xbar_base = h->xbar_base;
     const int nbar = 5 * (l1 - l0) + (run_head ? 1 : 0);
-    const int nx = 2 * (l1 - l0) + (run_head ? 1 : 0);
+    const int nx = h->tp_size > 1 ? 2 * (l1 - l0) + (run_head ? 1 : 0) : 0; // exchange points use the cross-GPU counter
     void *params[] = {&a};
     CK(cudaLaunchCooperativeKernel(h->mega_fn, dim3(h->num_sms), dim3(MEGA_THREADS), params, h->mega_smem, h->stream));
-    h->bar_base += (unsigned long long)nbar * h->num_sms;
-    h->xepoch += nx;
+    h->bar_base += (unsigned long long)(nbar - nx) * h->num_sms;
+    h->xbar_base += (unsigned long long)nx * h->tp_size * h->num_sms;
     return 0;
 }
 
@@ -617,7 +616,9 @@ static int mega_check(q3_handle *h) {
     if (code) {
         cudaMemset(h->d_status, 0, 64);
         h->bar_base = 0;
+        h->xbar_base = 0;
         cudaMemset(h->d_bar, 0, 64);
+        cudaMemset(h->d_flags, 0, 64 * 4);
         return fail(Q3_ECUDA, "persistent decode kernel: a wait timed out (status %d: 1 grid barrier, 2 stage ring, 3 peer flag)", code);
     }
     return 0;
@@ -1046,7 +1047,7 @@ extern "C" int q3_tp_connect(q3_handle *h, const void *blobs) {
         a.part[0][r] = (float *)(base + h->off_part[0]);
         a.part[1][r] = (float *)(base + h->off_part[1]);
         a.best[r] = (unsigned long long *)(base + h->off_best);
-        a.flags[r] = (unsigned int *)(base + h->off_flags);
+        a.xbar[r] = (unsigned long long *)(base + h->off_flags);
         a.logits[r] = (float *)(base + h->off_logits);
     }
     h->tp_connected = true;

@@ -61,8 +61,8 @@ struct MegaArgs {
     unsigned long long *best[MEGA_MAX_TP]; // [tp][grid] argmax candidates of every rank
     unsigned long long *bar;         // grid barrier counter (monotonic, never reset)
     unsigned long long bar_base;     // counter value when this launch starts (host-tracked)
-    unsigned int *flags[MEGA_MAX_TP]; // cross-GPU barrier flags of every rank: [tp]
-    unsigned int xepoch_base;        // cross-GPU exchange epochs completed before this launch (host-tracked)
+    unsigned long long *xbar[MEGA_MAX_TP]; // cross-GPU barrier counter of every rank (peer memory under TP)
+    unsigned long long xbar_base;    // value of the cross counters when this launch starts (host-tracked)
     int *tokpos, *history;
     int *status;                     // != 0: a wait timed out (kernel aborts)
     int layer0, layer1, from_embed, run_head, feedback, gather_logits;
@@ -603,57 +603,57 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
 // grid barrier (+ cross-GPU flag exchange under TP)
 // ------------------------------------------------------------------------------------------
 struct BarState {
-    unsigned long long target; // next value the local counter must reach
-    unsigned int xepoch;       // cross-GPU epoch of the next exchange barrier
+    unsigned long long target;  // next value the local counter must reach
+    unsigned long long xtarget; // next value this rank's cross-GPU counter must reach
 };
 
+// Grid barrier.  Local: every CTA adds 1 to this GPU's counter and waits for gridDim.x arrivals.
+// Cross (tensor parallel exchange points): every CTA of every rank adds 1 to the counter of EVERY
+// rank (remote reductions over NVLink) and waits for tp * gridDim.x arrivals on its own -- one
+// system-scope fence and one NVLink one-way trip, no second hop through a leader CTA.
 __device__ __noinline__ void grid_barrier(const MegaArgs &a, BarState &bs, bool cross) {
     csync();
+    const bool x = cross && a.tp_size > 1;
     if (threadIdx.x == 0) {
-        // one release-reduction (no return value to wait for); bar.sync above makes the other threads'
-        // stores cumulative with it
-        if (cross && a.tp_size > 1) __threadfence_system();
-        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(a.bar), "l"(1ULL) : "memory");
         long long t0 = clock64();
         volatile int *st = a.status;
         unsigned spins = 0;
-        while (true) {
-            unsigned long long v;
-            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
-            if (v >= bs.target) break;
-            if ((++spins & 1023u) == 0) {
-                if (*st) break;
-                if (clock64() - t0 > 4000000000LL) {
-                    atomicExch(a.status, 1);
-                    break;
+        if (x) {
+            __threadfence_system(); // this CTA's stores (cumulative over bar.sync), incl. the P2P ones, before the arrivals
+            for (int r = 0; r < a.tp_size; r++)
+                asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(a.xbar[r]), "l"(1ULL) : "memory");
+            while (true) {
+                unsigned long long v;
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.xbar[a.tp_rank]) : "memory");
+                if (v >= bs.xtarget) break;
+                if ((++spins & 1023u) == 0) {
+                    if (*st) break;
+                    if (clock64() - t0 > 8000000000LL) {
+                        atomicExch(a.status, 3);
+                        break;
+                    }
                 }
             }
-        }
-        if (cross && a.tp_size > 1) {
-            const unsigned int e = bs.xepoch;
-            if (blockIdx.x == 0) { // everyone on this GPU has arrived (and fenced): tell the peers
-                __threadfence_system();
-                for (int r = 0; r < a.tp_size; r++)
-                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[r] + a.tp_rank), "r"(e) : "memory");
-            }
-            for (int r = 0; r < a.tp_size; r++) {
-                while (true) {
-                    unsigned int v;
-                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flags[a.tp_rank] + r) : "memory");
-                    if ((int)(v - e) >= 0) break;
-                    if ((++spins & 1023u) == 0) {
-                        if (*st) break;
-                        if (clock64() - t0 > 8000000000LL) {
-                            atomicExch(a.status, 3);
-                            break;
-                        }
+        } else {
+            // one release-reduction (no return value to wait for); bar.sync above makes the other threads'
+            // stores cumulative with it
+            asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(a.bar), "l"(1ULL) : "memory");
+            while (true) {
+                unsigned long long v;
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
+                if (v >= bs.target) break;
+                if ((++spins & 1023u) == 0) {
+                    if (*st) break;
+                    if (clock64() - t0 > 4000000000LL) {
+                        atomicExch(a.status, 1);
+                        break;
                     }
                 }
             }
         }
     }
-    bs.target += gridDim.x;
-    if (cross) bs.xepoch += 1;
+    if (x) bs.xtarget += (unsigned long long)a.tp_size * gridDim.x;
+    else bs.target += gridDim.x;
     csync();
 }
 
@@ -830,7 +830,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
     unsigned it = 0;
     BarState bs;
     bs.target = a.bar_base + gridDim.x;
-    bs.xepoch = a.xepoch_base + 1;
+    bs.xtarget = a.xbar_base + (unsigned long long)a.tp_size * gridDim.x;
     const int pos = a.tokpos[1];
     const int grp = warp / MEGA_GW, wl = warp % MEGA_GW; // consumer group and warp-in-group (= row tile in a stage)
     int cur = 0;
