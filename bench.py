@@ -246,6 +246,7 @@ def main():
     ap.add_argument("--ref-tokens-per-step", type=int, default=2)
     ap.add_argument("--cpu-sample-tokens", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefill", action="store_true")
     ap.add_argument("--decode-path", type=int, default=-1)
     args = ap.parse_args()
     if args.warmup < 3:
@@ -381,6 +382,23 @@ def main():
     except Exception as e:  # noqa: BLE001
         log(f"[bench] kernel roofline failed: {e}")
 
+    # ---- batched prefill (tcgen05 int8 GEMM path), secondary metric of BASELINE.json ----
+    prefill = None
+    if world == 1 and not args.no_prefill:
+        try:
+            Tn = min(2048, args.ctx)
+            ptoks = np.random.default_rng(0).integers(0, shape.vocab_size, Tn).tolist()
+            m.reset()
+            pms = m.bench_prefill(ptoks, 0)
+            ah, kvd = shape.n_heads * shape.head_dim, shape.n_kv_heads * shape.head_dim
+            ops = 2.0 * Tn * shape.n_layers * (2 * shape.dim * ah + 2 * shape.dim * kvd + 3 * shape.dim * shape.hidden_dim)
+            prefill = {"tokens": Tn, "ms": pms, "value": Tn / pms * 1e3, "unit": "tok/s", "gemm_int8_TOPS": ops / pms / 1e9,
+                       "frac_of_int8_peak_4500_TOPS_spec": ops / pms / 1e9 / 4500.0,
+                       "note": "whole prefill (norm/quantize, tcgen05 GEMMs with per-group TMEM drains, f32 causal attention); "
+                               "GEMM TOPS counts the int8 MACs only; peak is the datasheet figure (no measured int8 peak available)"}
+        except Exception as e:  # noqa: BLE001
+            log(f"[bench] prefill measurement failed: {e}")
+
     cpu = None
     if not args.no_cpu_baseline:
         try:
@@ -403,7 +421,7 @@ def main():
         "gpu_launches": launches_per_token * n_tok,
         "launches_per_token": launches_per_token,
         "clocks": clk, "roofline": roof, "token_roofline": token_roof, "graph_path_kernels": kernels, "cpu_baseline": cpu,
-        "decode_path": "persistent" if persistent else "graph",
+        "decode_path": "persistent" if persistent else "graph", "prefill": prefill,
     }
     emit(out)
     m.close()

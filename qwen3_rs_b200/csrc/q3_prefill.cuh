@@ -10,8 +10,10 @@
 // adds its groups in order g = 0..ng-1 with unfused multiplies, i.e. exactly the reference's
 // left fold: the GEMM result is bit-identical to `matmul` applied token by token.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..9 = epilogue (TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4).
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..17 = epilogue (TMEM lane quadrant = warp % 4, column quarter = (warp - 2) / 4): 32 accumulator
+// columns per thread keep the register count low enough for 4 epilogue warps per scheduler, which the
+// latency-bound drain (tcgen05.ld -> cvt -> 2 mul -> add per element) needs to fill the issue slots.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -24,7 +26,9 @@ namespace q3 {
 constexpr int PF_BM = 128, PF_BN = 128, PF_BK = 128; // tile: tokens x weight rows x K bytes per stage
 constexpr int PF_STAGES = 4;
 constexpr int PF_NACC = 4; // TMEM accumulator buffers (128 columns each)
-constexpr int PF_THREADS = 320;
+constexpr int PF_EPI_WARPS = 16;                   // 4 TMEM lane quadrants x 4 column quarters
+constexpr int PF_THREADS = (2 + PF_EPI_WARPS) * 32;
+constexpr int PF_COLS = PF_BN / (PF_EPI_WARPS / 4); // accumulator columns per epilogue thread (32)
 constexpr int PF_SMEM = PF_STAGES * (PF_BM * PF_BK + PF_BN * PF_BK) + 1024 + 256;
 
 enum { PF_EPI_STORE = 0, PF_EPI_QKV = 1, PF_EPI_RESID = 2, PF_EPI_SWIGLU = 3 };
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1)
         }
         for (int b = 0; b < PF_NACC; b++) {
             mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], 8); // one arrive per epilogue warp
+            mbar_init(&tempty[b], PF_EPI_WARPS); // one arrive per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -150,32 +154,28 @@ __global__ void __launch_bounds__(PF_THREADS, 1)
         }
     } else {
         // ------------------------------- epilogue -------------------------------
-        const int quad = warp & 3;         // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
-        const int half = (warp - 2) >> 2;  // which 64 accumulator columns
-        const int m = quad * 32 + lane;    // row of the tile = token
+        const int quad = warp & 3;          // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
+        const int part = (warp - 2) >> 2;   // which PF_COLS accumulator columns
+        const int m = quad * 32 + lane;     // row of the tile = token
         const int t = m0 + m;
-        float acc[64];
+        float acc[PF_COLS];
 #pragma unroll
-        for (int j = 0; j < 64; j++) acc[j] = 0.0f;
-        const float *ws_col = a.wsT + n0 + half * 64;
+        for (int j = 0; j < PF_COLS; j++) acc[j] = 0.0f;
+        const float *ws_col = a.wsT + n0 + part * PF_COLS;
         for (int gi = 0; gi < ng; gi++) {
             const int buf = gi % PF_NACC;
             const float xs = a.xsT[(size_t)gi * a.Tpad + t];
             mbar_wait_spin(&tfull[buf], (gi / PF_NACC) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t d[64];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * PF_BN + half * 64;
+            uint32_t d[PF_COLS];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * PF_BN + part * PF_COLS;
             asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
-                "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]),
                   "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]), "=r"(d[16]), "=r"(d[17]), "=r"(d[18]),
                   "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]), "=r"(d[23]), "=r"(d[24]), "=r"(d[25]), "=r"(d[26]), "=r"(d[27]),
-                  "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31]), "=r"(d[32]), "=r"(d[33]), "=r"(d[34]), "=r"(d[35]), "=r"(d[36]),
-                  "=r"(d[37]), "=r"(d[38]), "=r"(d[39]), "=r"(d[40]), "=r"(d[41]), "=r"(d[42]), "=r"(d[43]), "=r"(d[44]), "=r"(d[45]),
-                  "=r"(d[46]), "=r"(d[47]), "=r"(d[48]), "=r"(d[49]), "=r"(d[50]), "=r"(d[51]), "=r"(d[52]), "=r"(d[53]), "=r"(d[54]),
-                  "=r"(d[55]), "=r"(d[56]), "=r"(d[57]), "=r"(d[58]), "=r"(d[59]), "=r"(d[60]), "=r"(d[61]), "=r"(d[62]), "=r"(d[63])
+                  "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
                 : "r"(taddr)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1)
             if (lane == 0) mbar_arrive(&tempty[buf]); // buffer drained into registers: MMA may reuse it
             const float4 *wsg = reinterpret_cast<const float4 *>(ws_col + (size_t)gi * a.N);
 #pragma unroll
-            for (int j4 = 0; j4 < 16; j4++) {
+            for (int j4 = 0; j4 < PF_COLS / 4; j4++) {
                 const float4 w = __ldg(wsg + j4);
                 // (dot as f32 * weight_scale) * input_scale, then the left-fold add (tensor.rs:59-61)
                 acc[4 * j4 + 0] = __fadd_rn(acc[4 * j4 + 0], __fmul_rn(__fmul_rn((float)(int)d[4 * j4 + 0], w.x), xs));
@@ -193,17 +193,17 @@ __global__ void __launch_bounds__(PF_THREADS, 1)
                 acc[4 * j4 + 3] = __fadd_rn(acc[4 * j4 + 3], __fmul_rn(__fmul_rn((float)(int)d[4 * j4 + 3], w.w), xs));
             }
         }
-        // ---- write the 64 outputs of this token row ----
+        // ---- write the PF_COLS outputs of this token row ----
         if (t < a.T) {
-            const int c0 = n0 + half * 64;
+            const int c0 = n0 + part * PF_COLS;
             if (EPI == PF_EPI_STORE) {
                 float4 *dst = reinterpret_cast<float4 *>(a.out + (size_t)t * a.ld_out + c0);
 #pragma unroll
-                for (int j4 = 0; j4 < 16; j4++) dst[j4] = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
+                for (int j4 = 0; j4 < PF_COLS / 4; j4++) dst[j4] = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
             } else if (EPI == PF_EPI_RESID) { // x += (layers.rs:249-259)
                 float4 *dst = reinterpret_cast<float4 *>(a.out + (size_t)t * a.ld_out + c0);
 #pragma unroll
-                for (int j4 = 0; j4 < 16; j4++) {
+                for (int j4 = 0; j4 < PF_COLS / 4; j4++) {
                     float4 o = dst[j4];
                     o.x = __fadd_rn(o.x, acc[4 * j4]);
                     o.y = __fadd_rn(o.y, acc[4 * j4 + 1]);
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1)
             } else if (EPI == PF_EPI_SWIGLU) { // rows interleaved (gate_j, up_j): layers.rs:472-475
                 float2 *dst = reinterpret_cast<float2 *>(a.out + (size_t)t * a.ld_out + c0 / 2);
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
+                for (int j = 0; j < PF_COLS / 2; j += 2) {
                     float g0 = acc[2 * j], u0 = acc[2 * j + 1], g1 = acc[2 * j + 2], u1 = acc[2 * j + 3];
                     float s0 = __fmul_rn(g0, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-g0))));
                     float s1 = __fmul_rn(g1, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-g1))));
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1)
                 else dst = a.vc + (size_t)(a.pos0 + t) * a.KV + (c0 - a.AH - a.KV);
                 float4 *d4 = reinterpret_cast<float4 *>(dst);
 #pragma unroll
-                for (int j4 = 0; j4 < 16; j4++) d4[j4] = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
+                for (int j4 = 0; j4 < PF_COLS / 4; j4++) d4[j4] = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
             }
         }
     }
@@ -396,7 +396,8 @@ __global__ void __launch_bounds__(256, 2) k_pf_attention(const float *__restrict
             *reinterpret_cast<float4 *>(Vs + p * PFA_LD + c4 * 4) = vv;
         }
         __syncthreads();
-        // scores: rows 4*ty..+3, keys 2*tx, 2*tx+1
+        // scores: rows 4*ty..+3, keys tx and tx+16 (adjacent lanes read adjacent rows: with the 132-float
+        // row pitch that is the conflict-free pattern for 128-bit shared loads)
         float sc[4][2];
 #pragma unroll
         for (int i = 0; i < 4; i++) sc[i][0] = sc[i][1] = 0.0f;
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(256, 2) k_pf_attention(const float *__restrict
         for (int d4 = 0; d4 < 32; d4++) {
             float4 kq[2], qq[4];
 #pragma unroll
-            for (int j = 0; j < 2; j++) kq[j] = *reinterpret_cast<const float4 *>(Ks + (2 * tx + j) * PFA_LD + d4 * 4);
+            for (int j = 0; j < 2; j++) kq[j] = *reinterpret_cast<const float4 *>(Ks + (tx + 16 * j) * PFA_LD + d4 * 4);
 #pragma unroll
             for (int i = 0; i < 4; i++) qq[i] = *reinterpret_cast<const float4 *>(Qs + (4 * ty + i) * PFA_LD + d4 * 4);
 #pragma unroll
@@ -418,8 +419,8 @@ __global__ void __launch_bounds__(256, 2) k_pf_attention(const float *__restrict
         for (int i = 0; i < 4; i++) {
             const int r = 4 * ty + i;
             const int qpos = pos0 + q0 + r / KVMUL;
-            float s0 = (k0 + 2 * tx <= qpos) ? __fmul_rn(sc[i][0], scale) : -INFINITY;
-            float s1 = (k0 + 2 * tx + 1 <= qpos) ? __fmul_rn(sc[i][1], scale) : -INFINITY;
+            float s0 = (k0 + tx <= qpos) ? __fmul_rn(sc[i][0], scale) : -INFINITY;
+            float s1 = (k0 + tx + 16 <= qpos) ? __fmul_rn(sc[i][1], scale) : -INFINITY;
             float mx = fmaxf(s0, s1);
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -434,8 +435,8 @@ __global__ void __launch_bounds__(256, 2) k_pf_attention(const float *__restrict
             m[i] = mn;
 #pragma unroll
             for (int j = 0; j < 8; j++) acc[i][j] *= corr;
-            Ps[r * PFA_LDP + 2 * tx] = p0;
-            Ps[r * PFA_LDP + 2 * tx + 1] = p1;
+            Ps[r * PFA_LDP + tx] = p0;
+            Ps[r * PFA_LDP + tx + 16] = p1;
         }
         __syncthreads();
         // out[r][8*tx .. +7] += sum_p P[r][p] * V[p][8*tx .. +7]

@@ -28,7 +28,7 @@ for gs in gss:
         m.bench_decode(1, pos0, 4)
         ms = m.bench_decode(1, pos0, steps) / steps
         b = shape.bytes_per_token(gs, pos0 + steps // 2)
-        print(json.dumps({"model": model, "group_size": gs, "context": label, "pos": pos0, "us_per_token": ms * 1e3,
-                          "tok_s": 1e3 / ms, "bytes_per_token_GB": b / 1e9, "achieved_GBps": b / ms / 1e6,
-                          "frac_of_measured_peak": b / ms / 1e6 / peak, "frac_of_8TBps": b / ms / 1e6 / 8000}), flush=True)
+        bench.emit({"model": model, "group_size": gs, "context": label, "pos": pos0, "us_per_token": ms * 1e3,
+                    "tok_s": 1e3 / ms, "bytes_per_token_GB": b / 1e9, "achieved_GBps": b / ms / 1e6,
+                    "frac_of_measured_peak": b / ms / 1e6 / peak, "frac_of_8TBps": b / ms / 1e6 / 8000})
     m.close()

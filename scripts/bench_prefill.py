@@ -24,4 +24,4 @@ out = {"model": model, "group_size": gs, "prefill_tokens": Tn, "prefill_ms": ms,
        "prefill_e2e_ms_incl_logits_d2h": e2e_ms, "decode_tokens": ndec, "decode_tok_s": ndec / dec_ms * 1e3,
        "decode_us_per_token": dec_ms / ndec * 1e3,
        "note": "prefill time includes batched norm/quantize, QK-norm+RoPE and f32 causal attention, not only the GEMMs"}
-print(json.dumps(out))
+bench.emit(out)
