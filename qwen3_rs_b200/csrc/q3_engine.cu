@@ -583,7 +583,7 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
     GS_DISPATCH(gs, (h->mega_fn = mega_kernel_for<GS>(h->kv_mul)));
     if (!h->mega_fn) { h->mega_why = "no kernel for this GQA factor"; return 0; }
     const size_t slot = (size_t)MEGA_GW * (MEGA_MAX_KT + 4 * (MEGA_MAX_KT / gs));
-    h->mega_smem = MEGA_NSTAGE * slot + MEGA_SCRATCH + 128 + sizeof(MegaShared) + 64;
+    h->mega_smem = MEGA_NSTAGE * slot + MEGA_SCRATCH + 192 + sizeof(MegaShared) + 64;
     CK(cudaFuncSetAttribute(h->mega_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mega_smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->mega_fn, MEGA_THREADS, h->mega_smem));

@@ -26,7 +26,7 @@ constexpr int MEGA_GW = 8;                          // consumer warps per group 
 constexpr int MEGA_GROUPS = 2;                      // consumer groups; stages alternate between them
 constexpr int MEGA_NCW = MEGA_GW * MEGA_GROUPS;     // 16 consumer warps
 constexpr int MEGA_CTHREADS = MEGA_NCW * 32;        // 512 consumer threads
-constexpr int MEGA_THREADS = MEGA_CTHREADS + 32;    // + producer warp
+constexpr int MEGA_THREADS = MEGA_CTHREADS + 32 * MEGA_GROUPS; // + one producer warp per consumer group
 constexpr int MEGA_NSTAGE = 5;
 constexpr int MEGA_MAX_KT = 4096;
 constexpr int MEGA_SCRATCH = 40960;                 // xq/xs or attention buffers
@@ -696,7 +696,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
     // other group's use of a slot and mistake the phase before it for its own.
     uint64_t *full = reinterpret_cast<uint64_t *>(scratch + MEGA_SCRATCH); // [MEGA_GROUPS][MEGA_NSTAGE]
     uint64_t *empty = full + MEGA_GROUPS * MEGA_NSTAGE;                    // [MEGA_NSTAGE]
-    MegaShared &sh = *reinterpret_cast<MegaShared *>(scratch + MEGA_SCRATCH + 128);
+    MegaShared &sh = *reinterpret_cast<MegaShared *>(scratch + MEGA_SCRATCH + 192);
+    volatile unsigned *issued = reinterpret_cast<volatile unsigned *>(scratch + MEGA_SCRATCH + 128); // [MEGA_NSTAGE] uses issued per slot
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
@@ -704,6 +705,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
             mbar_init(&full[s], 1);
             mbar_init(&full[MEGA_NSTAGE + s], 1);
             mbar_init(&empty[s], MEGA_GW);
+            issued[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #pragma unroll 1
@@ -727,9 +729,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
 
     const int L0 = a.layer0, L1 = a.layer1;
 
-    if (warp == MEGA_NCW) {
-        // =============================== PRODUCER ===============================
+    if (warp >= MEGA_NCW) {
+        // =============================== PRODUCERS ===============================
+        // One producer thread per consumer group: the serial wait -> expect_tx -> bulk-copy loop of a single
+        // thread (~0.6 us per stage) capped how fast the ring could refill; two threads issue independently,
+        // each feeding the stages its group owns.
         if (lane != 0) return;
+        const int pw = warp - MEGA_NCW;
         uint64_t policy;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
         unsigned it = 0;
@@ -742,6 +748,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
         int pf_l = L0, pf_ph = PH_QKV; // segment the cursor is in (PH_HEAD: pf_l unused)
         const uint8_t *pf_ptr = nullptr;
         long long pf_left = 0;
+        long long pf_ahead = 0; // bytes the cursor is in front of the ring's fill pointer
         bool pf_done = false;
         auto pf_open = [&]() {
             PhaseGeom pg = phase_geom(a, sh, pf_ph, pf_ph == PH_HEAD ? 0 : pf_l);
@@ -769,20 +776,46 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                 pf_ptr += chunk;
                 pf_left -= chunk;
                 bytes -= chunk;
+                pf_ahead += chunk;
             }
         };
         if (L1 > L0) pf_open();
         else if (a.run_head) { pf_ph = PH_HEAD; pf_open(); }
         else pf_done = true;
-        if (MEGA_L2_AHEAD > 0) pf_advance(MEGA_L2_AHEAD + (long long)MEGA_NSTAGE * slot_bytes);
         auto push = [&](const uint8_t *src, int nr, int tile_bytes, int owner) {
+            if (owner != pw) { // the other producer's stage
+                it++;
+                return;
+            }
             const int slot = it % MEGA_NSTAGE;
-            mbar_wait(&empty[slot], ((it / MEGA_NSTAGE) & 1) ^ 1, a.status);
             const uint32_t bytes = (uint32_t)nr * tile_bytes;
+            // The two producers share the slots.  A waiter can only tell adjacent mbarrier phases apart, so
+            // before waiting for "use n-1 of this slot released" make sure use n-1 has been ISSUED (by the
+            // other producer) -- otherwise an early arrival would mistake use n-3's release for it.
+            {
+                const unsigned use = it / MEGA_NSTAGE;
+                long long t0 = clock64();
+                while (issued[slot] != use) {
+                    if (clock64() - t0 > 4000000000LL) { atomicExch(a.status, 4); break; }
+                }
+            }
+            if (MEGA_L2_AHEAD > 0) {
+                // the cursor must at least cover what is about to be copied; beyond that it only advances
+                // while the ring is full (consumers in a barrier / prologue), i.e. exactly when HBM would idle
+                if (pf_ahead < (long long)bytes) pf_advance(bytes - pf_ahead);
+                const uint32_t par = ((it / MEGA_NSTAGE) & 1) ^ 1;
+                while (!mbar_try_wait(&empty[slot], par)) {
+                    if (pf_ahead < MEGA_L2_AHEAD && !pf_done) pf_advance(16384);
+                    else { mbar_wait(&empty[slot], par, a.status); break; }
+                }
+                pf_ahead -= bytes;
+            } else
+            mbar_wait(&empty[slot], ((it / MEGA_NSTAGE) & 1) ^ 1, a.status);
             uint64_t *fb = &full[owner * MEGA_NSTAGE + slot];
             mbar_expect_tx(fb, bytes);
             bulk_g2s(ring + (size_t)slot * slot_bytes, src, bytes, fb, policy);
-            if (MEGA_L2_AHEAD > 0) pf_advance(bytes);
+            __threadfence_block();
+            issued[slot] = it / MEGA_NSTAGE + 1;
             it++;
         };
         auto plain = [&](int ph, int layer) {
