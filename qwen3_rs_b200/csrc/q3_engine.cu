@@ -482,7 +482,7 @@ static int prepare_exact_kernels() {
 // ------------------------------------------------------------------------------------------
 static int pick_n_kt(int K, int gs) {
     for (int n = (K + MEGA_MAX_KT - 1) / MEGA_MAX_KT; n <= 64; n++)
-        if (K % (n * gs) == 0 && ((K / n) / gs) % 4 == 0 && K / n <= MEGA_MAX_KT) return n;
+        if (K % (n * gs) == 0 && (K / n) % 16 == 0 && K / n <= MEGA_MAX_KT) return n;
     return 0;
 }
 
@@ -505,7 +505,7 @@ static int build_stream(q3_handle *h, MegaGemv &g, const std::vector<const DevQT
     if (!g.n_kt) return fail(Q3_EUNSUPPORTED, "no K tiling for K=%d gs=%d", K, gs);
     g.KT = K / g.n_kt;
     g.G = g.KT / gs;
-    g.tile_bytes = g.KT + 4 * g.G;
+    g.tile_bytes = g.KT + ((4 * g.G + 15) & ~15);
     const size_t rows = (size_t)units * (pair ? 2 : 1);
     g.layer_stride = (long long)(rows * g.n_kt * g.tile_bytes);
     uint8_t *buf = nullptr;
@@ -526,7 +526,6 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
     const int gs = c.group_size, L = c.n_layers, dim = c.dim;
     h->mega_ok = false;
     if (dim > MEGA_MAX_KT) { h->mega_why = "dim > 4096 (QKV/gate-up/lm_head phases need a single K tile)"; return 0; }
-    if ((dim / gs) % 4) { h->mega_why = "dim/group_size not a multiple of 4"; return 0; }
     if (!pick_n_kt(h->AH_l, gs) || !pick_n_kt(h->H_l, gs)) { h->mega_why = "no K tiling for o_proj/down"; return 0; }
     if (h->AH_l > 16384 || h->H_l > 16384 || dim > 16384) { h->mega_why = "activation vector > 16384"; return 0; }
     if (c.vocab_size % h->tp_size) { h->mega_why = "vocab not divisible by tp"; return 0; }

@@ -42,7 +42,7 @@ struct MegaGemv {
     long long layer_stride;  // bytes between layers
     int units;               // rows, or (gate, up) PAIRS for PH_GU
     int K, n_kt, KT, G;      // columns, K tiles per row, columns per tile, groups per tile
-    int tile_bytes;          // KT + 4*G
+    int tile_bytes;          // KT + 4*G rounded up to 16 B (bulk copies move 16-byte units)
 };
 
 struct MegaArgs {
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) k_build_stream(const int8_t *__restrict__
                                                       uint8_t *dst, int units, int K, int n_kt, int nctas, int pair) {
     constexpr int CPG = GS / 16;
     const int u = blockIdx.x, kt = blockIdx.y;
-    const int KT = K / n_kt, G = KT / GS, tile_bytes = KT + 4 * G;
+    const int KT = K / n_kt, G = KT / GS, tile_bytes = KT + ((4 * G + 15) & ~15); // scale area padded to 16 B
     const int base = units / nctas, rem = units % nctas;
     int c, j;
     if (u < rem * (base + 1)) {
