@@ -573,6 +573,7 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
     int *d_status = h->d_status;
     a.x[0] = h->x; a.x[1] = h->x2;
     a.q = h->q; a.kraw = h->kraw; a.hb = h->hb; a.attn_part = h->attn_part;
+    a.dbg = getenv("Q3_MEGA_DBG") ? atoi(getenv("Q3_MEGA_DBG")) : 0;
     a.bar = h->d_bar; a.status = d_status; a.tokpos = h->d_tokpos; a.history = h->d_history;
     // until q3_tp_connect every "peer" slot points at this rank's own buffers
     for (int r = 0; r < MEGA_MAX_TP; r++) {
@@ -629,7 +630,7 @@ extern "C" int q3_debug_profile(q3_handle *h, int token, int pos, unsigned long 
     h->h_small[0] = token; h->h_small[1] = pos; h->h_small[2] = 0; h->h_small[3] = 0;
     CK(cudaMemcpyAsync(h->d_tokpos, h->h_small, 16, cudaMemcpyHostToDevice, h->stream));
     unsigned long long *d = nullptr;
-    size_t bytes = (size_t)h->num_sms * MEGA_PROF_EVENTS * 8;
+    size_t bytes = (size_t)3 * h->num_sms * MEGA_PROF_EVENTS * 8; // consumer thread 0 rows, producer-0 rows, consumer group-1 rows
     CK(cudaMalloc((void **)&d, bytes));
     CK(cudaMemsetAsync(d, 0, bytes, h->stream));
     h->margs.prof = d;
@@ -641,7 +642,7 @@ extern "C" int q3_debug_profile(q3_handle *h, int token, int pos, unsigned long 
         if (e != cudaSuccess) rc = fail(Q3_ECUDA, "profile run failed: %s", cudaGetErrorString(e));
     }
     cudaFree(d);
-    if (n_events_out) *n_events_out = 1 + 15 * h->cfg.n_layers + 3;
+    if (n_events_out) *n_events_out = MEGA_PROF_EVENTS;
     return rc;
 }
 

@@ -22,18 +22,59 @@
 
 namespace q3 {
 
-constexpr int MEGA_GW = 8;                          // consumer warps per group = row tiles per stage
+#ifndef MEGA_GW_
+#define MEGA_GW_ 8
+#endif
+constexpr int MEGA_GW = MEGA_GW_;                    // consumer warps per group = row tiles per stage
+constexpr int MEGA_BATCH = 4 * MEGA_GW;             // rows per batch of a row phase (up to 4 stages per K tile)
 constexpr int MEGA_GROUPS = 2;                      // consumer groups; stages alternate between them
 constexpr int MEGA_NCW = MEGA_GW * MEGA_GROUPS;     // 16 consumer warps
 constexpr int MEGA_CTHREADS = MEGA_NCW * 32;        // 512 consumer threads
-constexpr int MEGA_THREADS = MEGA_CTHREADS + 32 * MEGA_GROUPS; // + one producer warp per consumer group
-constexpr int MEGA_NSTAGE = 5;
+#ifndef MEGA_SETMAXNREG
+#define MEGA_SETMAXNREG 0   // producers sit in their own warpgroup and hand registers to the consumers (setmaxnreg)
+#endif
+// + one producer warp per consumer group; with setmaxnreg the producers fill a whole warpgroup (4 warps, 2 of them idle)
+constexpr int MEGA_THREADS = MEGA_CTHREADS + (MEGA_SETMAXNREG ? 128 : 32 * MEGA_GROUPS);
+constexpr int MEGA_REG_PRODUCER = 24, MEGA_REG_CONSUMER = 120; // per SM sub-partition: 32 * (24 + 4 * 120) <= 16384
+#ifndef MEGA_NSTAGE_
+#define MEGA_NSTAGE_ 4
+#endif
+constexpr int MEGA_NSTAGE = MEGA_NSTAGE_;
 constexpr int MEGA_MAX_KT = 4096;
 constexpr int MEGA_SCRATCH = 40960;                 // xq/xs or attention buffers
 constexpr int MEGA_MAX_TP = 8;
 constexpr int MEGA_MAX_SPLITS = ATTN_MAX_SPLITS;
 constexpr long long MEGA_L2_AHEAD = 0;                 // bytes per CTA the L2 prefetch cursor runs ahead of the ring (0 = off:
                                                     // measured SLOWER on B200 -- the extra L2 fill traffic delays the consumers' activation loads)
+
+// tuning switches (compile-time; scripts/ab_variants.py builds and times the alternatives on one box)
+#ifndef MEGA_PREFETCH_W
+#define MEGA_PREFETCH_W 0   // L2-prefetch the next norm / QK-norm / RoPE weights before entering a grid barrier
+#endif
+#ifndef MEGA_PREFETCH_KV
+#define MEGA_PREFETCH_KV 0  // L2-prefetch this CTA's K/V cache slice before the qkv barrier
+#endif
+#ifndef MEGA_ATTN_NP
+#define MEGA_ATTN_NP 2      // positions per warp iteration in the attention loop
+#endif
+#ifndef MEGA_FUSED_RES
+#define MEGA_FUSED_RES 1    // single GPU: o_proj / down epilogue adds the residual
+#endif
+#ifndef MEGA_QUANT_U
+#define MEGA_QUANT_U 1      // float4 loads in flight per thread in prologue_quant
+#endif
+#ifndef MEGA_AO_UNROLL
+#define MEGA_AO_UNROLL 1    // unroll factor of the attention-output quantiser loop (nsplit == 1 path)
+#endif
+#ifndef MEGA_PSLEEP
+#define MEGA_PSLEEP 0       // ns the producers sleep per iteration while waiting for their turn on a slot
+#endif
+#ifndef MEGA_RELAXED_POLL
+#define MEGA_RELAXED_POLL 0 // grid barrier: poll with relaxed loads, one acquire fence at the end
+#endif
+#ifndef MEGA_X_ONCE
+#define MEGA_X_ONCE 0       // load the activation registers once per phase when n_kt == 1
+#endif
 
 enum { PH_QKV = 0, PH_O = 1, PH_GU = 2, PH_DN = 3, PH_HEAD = 4 };
 
@@ -67,13 +108,19 @@ struct MegaArgs {
     int *status;                     // != 0: a wait timed out (kernel aborts)
     int layer0, layer1, from_embed, run_head, feedback, gather_logits;
     unsigned long long *prof;        // optional [grid][MEGA_PROF_EVENTS] clock64 stamps (thread 0 of each CTA)
+    int dbg;                         // timing experiments only (env Q3_MEGA_DBG; results are garbage): 1 = every bulk copy reads the
+                                     // same L2-resident bytes (no HBM traffic), 2 = grid barriers skipped, 4 = prologues skipped
 };
-constexpr int MEGA_PROF_EVENTS = 1024;
-__device__ __forceinline__ void prof_mark(const MegaArgs &a, int &ev) {
-    if (a.prof && threadIdx.x == 0 && ev < MEGA_PROF_EVENTS) {
-        a.prof[(size_t)blockIdx.x * MEGA_PROF_EVENTS + ev] = (unsigned long long)clock64();
-    }
-    ev++;
+// In-kernel profiler: thread 0 of every CTA appends (clock64 << 8 | tag).  Tags: 0 start; 1 + 3*kind + {0 prologue done,
+// 1 GEMV done, 2 barrier done} for step kinds 0..5; >= 32 finer marks inside the prologues and the grid barrier.
+// The last slot of a CTA's row holds its event count.
+constexpr int MEGA_PROF_EVENTS = 4096;
+struct Prof {
+    unsigned long long *row;
+    int ev;
+};
+__device__ __forceinline__ void prof_mark(Prof &p, int tag) {
+    if (p.row && p.ev < MEGA_PROF_EVENTS - 1) p.row[p.ev++] = ((unsigned long long)clock64() << 8) | (unsigned)tag;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -159,15 +206,15 @@ __global__ void __launch_bounds__(256) k_build_stream(const int8_t *__restrict__
     for (int half = 0; half < (pair ? 2 : 1); half++) {
         long long tile_index;
         size_t src_row;
-        if (pair) { // blocks of 8 pairs: [gate x np][up x np]
-            int blk = j / 8, w = j % 8, np = n_c - 8 * blk;
-            if (np > 8) np = 8;
-            tile_index = (long long)start * 2 + 16 * blk + half * np + w;
+        if (pair) { // blocks of MEGA_GW pairs: [gate x np][up x np]
+            int blk = j / MEGA_GW, w = j % MEGA_GW, np = n_c - MEGA_GW * blk;
+            if (np > MEGA_GW) np = MEGA_GW;
+            tile_index = (long long)start * 2 + 2 * MEGA_GW * blk + half * np + w;
             src_row = (size_t)2 * u + half;
         } else { // batches of 32 rows: [kt][row]
-            int b = j / 32, jb = j % 32, nb = n_c - 32 * b;
-            if (nb > 32) nb = 32;
-            tile_index = ((long long)start + 32 * b) * n_kt + (long long)kt * nb + jb;
+            int b = j / MEGA_BATCH, jb = j % MEGA_BATCH, nb = n_c - MEGA_BATCH * b;
+            if (nb > MEGA_BATCH) nb = MEGA_BATCH;
+            tile_index = ((long long)start + MEGA_BATCH * b) * n_kt + (long long)kt * nb + jb;
             src_row = (size_t)u;
         }
         uint8_t *tile = dst + tile_index * tile_bytes;
@@ -187,33 +234,6 @@ __global__ void __launch_bounds__(256) k_build_stream(const int8_t *__restrict__
 // ------------------------------------------------------------------------------------------
 // consumer-side building blocks
 // ------------------------------------------------------------------------------------------
-template <int GS>
-struct XRegs { // this lane's groups of the current K tile: MEGA_MAX_KT/128 = 32 registers + scales
-    static constexpr int CPG = GS / 16;
-    static constexpr int NBLK = MEGA_MAX_KT / (32 * GS);
-    int4 x[NBLK][CPG];
-    float s[NBLK];
-};
-
-template <int GS>
-__device__ __forceinline__ void load_x(XRegs<GS> &xr, const uint8_t *sxq, const float *sxs, int kt, int KT, int G, int lane) {
-#pragma unroll
-    for (int b = 0; b < XRegs<GS>::NBLK; b++) {
-        int g = b * 32 + lane;
-        bool ok = g < G;
-        xr.s[b] = ok ? sxs[kt * G + g] : 0.0f;
-#pragma unroll
-        for (int p = 0; p < XRegs<GS>::CPG; p++)
-            xr.x[b][p] = ok ? *reinterpret_cast<const int4 *>(sxq + (size_t)kt * KT + (size_t)g * GS + p * 16) : make_int4(0, 0, 0, 0);
-    }
-}
-
-// dot of one row tile (in shared memory) with the register-resident activation slice.
-// Per group: exact int32 dot, then (dot as f32 * weight_scale) * input_scale (tensor.rs:47-59).
-// All 128-bit shared loads of the tile are issued before the first dp4a (explicit ld.shared.v4:
-// left to itself the compiler split them into 32-bit loads under the 96-register cap), and each
-// block runs two independent dp4a chains.  FULL: every block has 32 groups (G % 32 == 0), so all
-// offsets are immediates and no lane is predicated off.
 __device__ __forceinline__ int4 lds128(uint32_t saddr) {
     int4 r;
     asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
@@ -224,6 +244,53 @@ __device__ __forceinline__ float lds_f32(uint32_t saddr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(saddr));
     return r;
 }
+template <int GS>
+struct XRegs { // this lane's groups of the current K tile: MEGA_MAX_KT/128 = 32 registers + scales
+    static constexpr int CPG = GS / 16;
+    static constexpr int NBLK = MEGA_MAX_KT / (32 * GS);
+    int4 x[NBLK][CPG];
+    float s[NBLK];
+};
+
+// The quantised activation sits in shared memory in the SAME chunk permutation as a weight row tile
+// (lane l owns groups l, l+32, ...; its 16-byte chunks are 16*ngb bytes apart), so the 128-bit loads
+// below are conflict-free.  (Element order would put consecutive lanes GS bytes apart: a 16-way bank
+// conflict -- ~1 us per call with 16 warps, 7 calls per layer.)
+template <int GS>
+__device__ __forceinline__ void xq_store(uint8_t *sxq, int i4, uint32_t packed, int KT, int G) {
+    int r = i4 * 4, off = 0;
+    while (r >= KT) { // K tile (at most 4)
+        r -= KT;
+        off += KT;
+    }
+    const int g = r / GS, b = g >> 5, l = g & 31;
+    int ngb = G - 32 * b;
+    ngb = ngb > 32 ? 32 : ngb;
+    const int p = (r % GS) >> 4;
+    *reinterpret_cast<uint32_t *>(sxq + off + b * 32 * GS + (p * ngb + l) * 16 + (r & 15)) = packed;
+}
+template <int GS>
+__device__ __forceinline__ void load_x(XRegs<GS> &xr, const uint8_t *sxq, const float *sxs, int kt, int KT, int G, int lane) {
+    const uint32_t base = smem_u32(sxq) + kt * KT + lane * 16;
+#pragma unroll
+    for (int b = 0; b < XRegs<GS>::NBLK; b++) {
+        int ngb = G - 32 * b;
+        ngb = ngb > 32 ? 32 : ngb;
+        const bool ok = lane < ngb;
+        if (ngb < 1) ngb = 1;
+        xr.s[b] = ok ? sxs[kt * G + b * 32 + lane] : 0.0f;
+#pragma unroll
+        for (int p = 0; p < XRegs<GS>::CPG; p++)
+            xr.x[b][p] = ok ? lds128(base + b * 32 * GS + p * ngb * 16) : make_int4(0, 0, 0, 0);
+    }
+}
+
+// dot of one row tile (in shared memory) with the register-resident activation slice.
+// Per group: exact int32 dot, then (dot as f32 * weight_scale) * input_scale (tensor.rs:47-59).
+// All 128-bit shared loads of the tile are issued before the first dp4a (explicit ld.shared.v4:
+// left to itself the compiler split them into 32-bit loads under the 96-register cap), and each
+// block runs two independent dp4a chains.  FULL: every block has 32 groups (G % 32 == 0), so all
+// offsets are immediates and no lane is predicated off.
 template <int GS, bool FULL>
 __device__ __forceinline__ float tile_dot(uint32_t tile, const XRegs<GS> &xr, int KT, int G, int lane) {
     constexpr int CPG = XRegs<GS>::CPG;
@@ -260,10 +327,10 @@ __device__ __forceinline__ float tile_dot(uint32_t tile, const XRegs<GS> &xr, in
 // summed in rank order so every rank computes bit-identical x) and gathers the embedding row.
 template <int GS>
 __device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, bool from_embed, const float *const *parts,
-                                              int &cur, uint8_t *sxq, float *sxs, float *sred, bool write_normed) {
+                                              int &cur, uint8_t *sxq, float *sxs, float *sred, bool write_normed, int KT, int G, Prof &pr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n4 = a.dim >> 2;
-    constexpr int MAXV = MEGA_MAX_KT / (4 * MEGA_CTHREADS); // dim <= 4096 on this path
+    constexpr int MAXV = (MEGA_MAX_KT + 4 * MEGA_CTHREADS - 1) / (4 * MEGA_CTHREADS); // dim <= 4096 on this path
     float4 v[MAXV];
     float ss = 0.0f;
     const float *xin = a.x[cur];
@@ -300,6 +367,7 @@ __device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, bo
         }
     }
     if (merge && !from_embed) cur ^= 1;
+    prof_mark(pr, 32); // x (+ partial sums) arrived
     float4 wv[MAXV]; // norm weights: issue the loads before the reduction so their latency overlaps it
 #pragma unroll
     for (int k = 0; k < MAXV; k++) {
@@ -313,6 +381,7 @@ __device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, bo
 #pragma unroll
     for (int i = 0; i < MEGA_NCW; i++) t += sred[i];
     const float f = __fdiv_rn(1.0f, sqrtf(__fadd_rn(__fdiv_rn(t, (float)a.dim), NORM_EPS)));
+    prof_mark(pr, 33); // sum of squares reduced
 #pragma unroll
     for (int k = 0; k < MAXV; k++) {
         int i4 = tid + k * MEGA_CTHREADS;
@@ -328,35 +397,52 @@ __device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, bo
             float scale;
             quantize_group4<GS>(y, packed, scale);
             if (i4 < n4) {
-                reinterpret_cast<uint32_t *>(sxq)[i4] = packed;
+                xq_store<GS>(sxq, i4, packed, KT, G);
                 if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
                 if (write_normed && blockIdx.x == 0) reinterpret_cast<float4 *>(a.x[cur])[i4] = y;
             }
         }
     }
+    prof_mark(pr, 34); // quantised
     csync();
 }
 
 // quantise an f32 vector in global memory (written by other CTAs) into shared memory.
-// Rolled loop (one copy of the quantiser in the instruction stream) with the next load in flight
-// while the current float4 is processed.
+// Loads run two batches of 4 ahead of the quantiser (every load of a <= 16 K vector is in flight at
+// once: one L2 round trip instead of one per 2048 elements); the quantiser exists 4x in the code.
 template <int GS>
-__device__ __noinline__ void prologue_quant(const float *src, int n, uint8_t *sxq, float *sxs) {
+__device__ __noinline__ void prologue_quant(const float *src, int n, uint8_t *sxq, float *sxs, int KT, int G) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int n4 = n >> 2;
-    int i4 = tid;
-    float4 nxt = (i4 < n4) ? ldcg_f4(src + (size_t)i4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int U = MEGA_QUANT_U;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 nxt[U];
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+        const int i4 = tid + j * MEGA_CTHREADS;
+        nxt[j] = (i4 < n4) ? ldcg_f4(src + (size_t)i4 * 4) : zero;
+    }
 #pragma unroll 1
-    for (; i4 - lane < n4; i4 += MEGA_CTHREADS) {
-        const float4 y = nxt;
-        const int j4 = i4 + MEGA_CTHREADS;
-        nxt = (j4 < n4) ? ldcg_f4(src + (size_t)j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t packed;
-        float scale;
-        quantize_group4<GS>(y, packed, scale);
-        if (i4 < n4) {
-            reinterpret_cast<uint32_t *>(sxq)[i4] = packed;
-            if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
+    for (int base = tid; base - lane < n4; base += U * MEGA_CTHREADS) {
+        float4 cur[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            cur[j] = nxt[j];
+            const int i4 = base + (U + j) * MEGA_CTHREADS;
+            nxt[j] = (i4 < n4) ? ldcg_f4(src + (size_t)i4 * 4) : zero;
+        }
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const int i4 = base + j * MEGA_CTHREADS;
+            if (i4 - lane < n4) { // warp-uniform
+                uint32_t packed;
+                float scale;
+                quantize_group4<GS>(cur[j], packed, scale);
+                if (i4 < n4) {
+                    xq_store<GS>(sxq, i4, packed, KT, G);
+                    if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
+                }
+            }
         }
     }
     csync();
@@ -364,7 +450,7 @@ __device__ __noinline__ void prologue_quant(const float *src, int n, uint8_t *sx
 
 // merge the attention split partials (k_attn_combine_quant's math) and quantise into shared memory
 template <int GS>
-__device__ __noinline__ void prologue_attn_out(const MegaArgs &a, int nsplit, uint8_t *sxq, float *sxs) {
+__device__ __noinline__ void prologue_attn_out(const MegaArgs &a, int nsplit, uint8_t *sxq, float *sxs, int KT, int G) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int n4 = a.AH_l >> 2;
     if (nsplit == 1) { // short context: one partial per head; exp(m - M) == 1.  Rolled, next loads in flight.
@@ -376,7 +462,8 @@ __device__ __noinline__ void prologue_attn_out(const MegaArgs &a, int nsplit, ui
             An = ldcg_f4(pb + (i4 & 31) * 4);
             Ln = ldcg_f(pb + HEAD_DIM + 1);
         }
-#pragma unroll 1
+        constexpr int AO_UNROLL = MEGA_AO_UNROLL;
+#pragma unroll AO_UNROLL
         for (; i4 - lane < n4; i4 += MEGA_CTHREADS) {
             const float4 A = An;
             const float Lc = Ln;
@@ -393,7 +480,7 @@ __device__ __noinline__ void prologue_attn_out(const MegaArgs &a, int nsplit, ui
             float scale;
             quantize_group4<GS>(y, packed, scale);
             if (i4 < n4) {
-                reinterpret_cast<uint32_t *>(sxq)[i4] = packed;
+                xq_store<GS>(sxq, i4, packed, KT, G);
                 if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
             }
         }
@@ -428,7 +515,7 @@ __device__ __noinline__ void prologue_attn_out(const MegaArgs &a, int nsplit, ui
         float scale;
         quantize_group4<GS>(y, packed, scale);
         if (i4 < n4) {
-            reinterpret_cast<uint32_t *>(sxq)[i4] = packed;
+            xq_store<GS>(sxq, i4, packed, KT, G);
             if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
         }
     }
@@ -484,7 +571,7 @@ __device__ __forceinline__ int mega_nsplit(int pos, int n_kv_l, int grid) {
 // attention phase for one (kv head, split) work item; all 256 consumer threads.
 template <int KVMUL>
 __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int pos, int kvh, int split, int nsplit,
-                                               uint8_t *scratch) {
+                                               uint8_t *scratch, Prof &pr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NATT = (KVMUL * MEGA_NCW * 512 + 8192 <= MEGA_SCRATCH) ? MEGA_NCW : MEGA_GW; // warps in the position loop
     float4 *sq = reinterpret_cast<float4 *>(scratch);                 // [KVMUL][32]
@@ -514,6 +601,7 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
         }
     }
     csync();
+    prof_mark(pr, 35); // q / k normalised + rotated
     const float scale = __fdiv_rn(1.0f, sqrtf((float)HEAD_DIM));
     float4 qv[KVMUL];
     float m[KVMUL], l[KVMUL];
@@ -527,42 +615,54 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
     }
     const float *kbase = kc_l + (size_t)kvh * HEAD_DIM + lane * 4;
     const float *vbase = vc_l + (size_t)kvh * HEAD_DIM + lane * 4;
-    // two positions per iteration: both K/V row loads are in flight before either is used
-    for (int t = t0 + warp; t < t1 && warp < NATT; t += 2 * NATT) {
-        const int tb = t + NATT;
-        const bool hasb = tb < t1;
-        float4 kva = (t == pos) ? sk[lane] : ldcg_f4(kbase + (size_t)t * a.KV_l);
-        float4 vva = ldcg_f4(vbase + (size_t)t * a.KV_l);
-        float4 kvb = make_float4(0.f, 0.f, 0.f, 0.f), vvb = kvb;
-        if (hasb) {
-            kvb = (tb == pos) ? sk[lane] : ldcg_f4(kbase + (size_t)tb * a.KV_l);
-            vvb = ldcg_f4(vbase + (size_t)tb * a.KV_l);
+    // four positions per iteration: all eight K/V row loads are in flight before any is used (a 64-position
+    // split is one memory round trip for every warp)
+    constexpr int NP = MEGA_ATTN_NP;
+    for (int t = t0 + warp; t < t1 && warp < NATT; t += NP * NATT) {
+        float4 kv[NP], vv[NP];
+#pragma unroll
+        for (int j = 0; j < NP; j++) {
+            const int tj = t + j * NATT;
+            kv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            vv[j] = kv[j];
+            if (tj < t1) {
+                kv[j] = (tj == pos) ? sk[lane] : ldcg_f4(kbase + (size_t)tj * a.KV_l);
+                vv[j] = ldcg_f4(vbase + (size_t)tj * a.KV_l);
+            }
         }
-        float sa[KVMUL], sb[KVMUL];
+        float sc[NP][KVMUL];
+#pragma unroll
+        for (int j = 0; j < NP; j++)
+#pragma unroll
+            for (int h = 0; h < KVMUL; h++) sc[j][h] = qv[h].x * kv[j].x + qv[h].y * kv[j].y + qv[h].z * kv[j].z + qv[h].w * kv[j].w;
+#pragma unroll
+        for (int j = 0; j < NP; j++)
+#pragma unroll
+            for (int h = 0; h < KVMUL; h++) sc[j][h] = (t + j * NATT < t1) ? __fmul_rn(warp_sum(sc[j][h]), scale) : -INFINITY;
 #pragma unroll
         for (int h = 0; h < KVMUL; h++) {
-            sa[h] = qv[h].x * kva.x + qv[h].y * kva.y + qv[h].z * kva.z + qv[h].w * kva.w;
-            sb[h] = qv[h].x * kvb.x + qv[h].y * kvb.y + qv[h].z * kvb.z + qv[h].w * kvb.w;
-        }
+            float mn = m[h];
 #pragma unroll
-        for (int h = 0; h < KVMUL; h++) {
-            sa[h] = __fmul_rn(warp_sum(sa[h]), scale);
-            sb[h] = hasb ? __fmul_rn(warp_sum(sb[h]), scale) : -INFINITY;
-        }
+            for (int j = 0; j < NP; j++) mn = fmaxf(mn, sc[j][h]);
+            const float corr = expf(m[h] - mn);
+            l[h] *= corr;
+            acc[h].x *= corr;
+            acc[h].y *= corr;
+            acc[h].z *= corr;
+            acc[h].w *= corr;
 #pragma unroll
-        for (int h = 0; h < KVMUL; h++) {
-            float mn = fmaxf(m[h], fmaxf(sa[h], sb[h]));
-            float corr = expf(m[h] - mn);
-            float pa = expf(sa[h] - mn);
-            float pb = hasb ? expf(sb[h] - mn) : 0.0f;
-            l[h] = l[h] * corr + pa + pb;
-            acc[h].x = acc[h].x * corr + pa * vva.x + pb * vvb.x;
-            acc[h].y = acc[h].y * corr + pa * vva.y + pb * vvb.y;
-            acc[h].z = acc[h].z * corr + pa * vva.z + pb * vvb.z;
-            acc[h].w = acc[h].w * corr + pa * vva.w + pb * vvb.w;
+            for (int j = 0; j < NP; j++) {
+                const float pj = expf(sc[j][h] - mn); // exp(-inf) = 0 for the positions past the end
+                l[h] += pj;
+                acc[h].x += pj * vv[j].x;
+                acc[h].y += pj * vv[j].y;
+                acc[h].z += pj * vv[j].z;
+                acc[h].w += pj * vv[j].w;
+            }
             m[h] = mn;
         }
     }
+    prof_mark(pr, 36); // position loop done
     if (warp < NATT) {
 #pragma unroll
         for (int h = 0; h < KVMUL; h++) {
@@ -611,8 +711,10 @@ struct BarState {
 // Cross (tensor parallel exchange points): every CTA of every rank adds 1 to the counter of EVERY
 // rank (remote reductions over NVLink) and waits for tp * gridDim.x arrivals on its own -- one
 // system-scope fence and one NVLink one-way trip, no second hop through a leader CTA.
-__device__ __noinline__ void grid_barrier(const MegaArgs &a, BarState &bs, bool cross) {
+__device__ __noinline__ void grid_barrier(const MegaArgs &a, BarState &bs, bool cross, Prof &pr) {
     csync();
+    if (a.dbg & 2) return;
+    prof_mark(pr, 40); // all consumer warps of this CTA done
     const bool x = cross && a.tp_size > 1;
     if (threadIdx.x == 0) {
         long long t0 = clock64();
@@ -640,8 +742,12 @@ __device__ __noinline__ void grid_barrier(const MegaArgs &a, BarState &bs, bool 
             asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(a.bar), "l"(1ULL) : "memory");
             while (true) {
                 unsigned long long v;
-                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
-                if (v >= bs.target) break;
+                if (MEGA_RELAXED_POLL) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
+                else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
+                if (v >= bs.target) {
+                    if (MEGA_RELAXED_POLL) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                    break;
+                }
                 if ((++spins & 1023u) == 0) {
                     if (*st) break;
                     if (clock64() - t0 > 4000000000LL) {
@@ -654,6 +760,7 @@ __device__ __noinline__ void grid_barrier(const MegaArgs &a, BarState &bs, bool 
     }
     if (x) bs.xtarget += (unsigned long long)a.tp_size * gridDim.x;
     else bs.target += gridDim.x;
+    prof_mark(pr, 41); // all CTAs arrived (seen by thread 0)
     csync();
 }
 
@@ -729,6 +836,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
 
     const int L0 = a.layer0, L1 = a.layer1;
 
+#if MEGA_SETMAXNREG
+    if (warp >= MEGA_NCW) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MEGA_REG_PRODUCER));
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MEGA_REG_CONSUMER));
+#endif
+    if (warp >= MEGA_NCW + MEGA_GROUPS) return; // idle warps of the producer warpgroup
     if (warp >= MEGA_NCW) {
         // =============================== PRODUCERS ===============================
         // One producer thread per consumer group: the serial wait -> expect_tx -> bulk-copy loop of a single
@@ -739,6 +851,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
         uint64_t policy;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
         unsigned it = 0;
+        Prof pr; // producer 0 logs every stage it issues (tag 64 + slot) into a second row per CTA
+        pr.row = (a.prof && pw == 0) ? a.prof + (size_t)(gridDim.x + blockIdx.x) * MEGA_PROF_EVENTS : nullptr;
+        pr.ev = 0;
         // L2 prefetch cursor.  The shared-memory ring alone (5 x 34 KB per SM) cannot keep enough
         // bytes in flight to saturate HBM at its loaded latency, and it stalls whenever the consumers
         // sit in a barrier or a prologue.  So a second cursor walks the same byte stream
@@ -796,6 +911,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                 const unsigned use = it / MEGA_NSTAGE;
                 long long t0 = clock64();
                 while (issued[slot] != use) {
+                    if (MEGA_PSLEEP) __nanosleep(MEGA_PSLEEP);
                     if (clock64() - t0 > 4000000000LL) { atomicExch(a.status, 4); break; }
                 }
             }
@@ -813,21 +929,22 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
             mbar_wait(&empty[slot], ((it / MEGA_NSTAGE) & 1) ^ 1, a.status);
             uint64_t *fb = &full[owner * MEGA_NSTAGE + slot];
             mbar_expect_tx(fb, bytes);
-            bulk_g2s(ring + (size_t)slot * slot_bytes, src, bytes, fb, policy);
+            bulk_g2s(ring + (size_t)slot * slot_bytes, (a.dbg & 1) ? a.g[0].base + (size_t)blockIdx.x * 36864 : src, bytes, fb, policy);
             __threadfence_block();
             issued[slot] = it / MEGA_NSTAGE + 1;
+            prof_mark(pr, 64 + slot);
             it++;
         };
         auto plain = [&](int ph, int layer) {
             const MegaGemv &g = a.g[ph];
             PhaseGeom pg = phase_geom(a, sh, ph, layer);
             const uint8_t *src = pg.seg;
-            for (int b0 = 0; b0 < pg.count; b0 += 32) {
-                int nb = pg.count - b0 < 32 ? pg.count - b0 : 32;
+            for (int b0 = 0; b0 < pg.count; b0 += MEGA_BATCH) {
+                int nb = pg.count - b0 < MEGA_BATCH ? pg.count - b0 : MEGA_BATCH;
                 for (int kt = 0; kt < g.n_kt; kt++)
-                    for (int s = 0; s < nb; s += 8) {
-                        int nr = nb - s < 8 ? nb - s : 8;
-                        push(src, nr, g.tile_bytes, (s >> 3) & 1);
+                    for (int s = 0, si = 0; s < nb; s += MEGA_GW, si++) {
+                        int nr = nb - s < MEGA_GW ? nb - s : MEGA_GW;
+                        push(src, nr, g.tile_bytes, si & 1);
                         src += (size_t)nr * g.tile_bytes;
                     }
             }
@@ -836,10 +953,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
             const MegaGemv &g = a.g[PH_GU];
             PhaseGeom pg = phase_geom(a, sh, PH_GU, layer);
             const uint8_t *src = pg.seg;
-            for (int p0 = 0; p0 < pg.count; p0 += 8) {
-                int np = pg.count - p0 < 8 ? pg.count - p0 : 8;
+            for (int p0 = 0, bi = 0; p0 < pg.count; p0 += MEGA_GW, bi++) {
+                int np = pg.count - p0 < MEGA_GW ? pg.count - p0 : MEGA_GW;
                 for (int half = 0; half < 2; half++) {
-                    push(src, np, g.tile_bytes, (p0 >> 3) & 1);
+                    push(src, np, g.tile_bytes, bi & 1);
                     src += (size_t)np * g.tile_bytes;
                 }
             }
@@ -851,6 +968,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
             plain(PH_DN, l);
         }
         if (a.run_head) plain(PH_HEAD, 0);
+        if (pr.row) pr.row[MEGA_PROF_EVENTS - 1] = (unsigned long long)pr.ev;
         return;
     }
 
@@ -867,15 +985,21 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
     const int pos = a.tokpos[1];
     const int grp = warp / MEGA_GW, wl = warp % MEGA_GW; // consumer group and warp-in-group (= row tile in a stage)
     int cur = 0;
-    int ev = 0;
+    Prof pr;
+    pr.row = (a.prof && (tid == 0 || tid == MEGA_GW * 32)) ? a.prof + (size_t)((tid ? 2 * gridDim.x : 0) + blockIdx.x) * MEGA_PROF_EVENTS : nullptr; // + first lane of group 1
+    pr.ev = 0;
     unsigned fullp = 0; // bit s: parity of this group's next use of slot s
     uint64_t *myfull = full + grp * MEGA_NSTAGE;
     XRegs<GS> xr;
-    prof_mark(a, ev); // 0: start
+    prof_mark(pr, 0);
     long long best = (long long)0x8000000000000000LL;
     const int n_layer_steps = 5 * (L1 - L0);
     const int n_steps = n_layer_steps + (a.run_head ? 1 : 0);
     int nsplit = 1;
+    // Single GPU: the o_proj / down epilogue adds the residual itself (x_new[r] = x[r] + row result, the
+    // same single f32 add as ResidualConnection, layers.rs:249-259) so the next prologue reads one vector
+    // instead of x and the partial sums.  Under TP the partial sums of all ranks are merged in the prologue.
+    const bool fused_res = MEGA_FUSED_RES && a.tp_size == 1;
 
     for (int step = 0; step < n_steps; step++) {
         const bool head = step >= n_layer_steps;
@@ -884,28 +1008,32 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
         bool cross = false;
         int ph = PH_QKV;
         // ------------------------------ prologue ------------------------------
-        if (kind == 0 || kind == 3 || kind == 5) {
+        if (a.dbg & 4) {
+            ph = kind == 0 ? PH_QKV : kind == 2 ? PH_O : kind == 3 ? PH_GU : kind == 4 ? PH_DN : PH_HEAD;
+        } else if (kind == 0 || kind == 3 || kind == 5) {
             // RMSNorm + quantize of the residual stream (qwen3.rs:134-136, 159-161, 72-75)
             const float *w = kind == 0 ? a.rms_att + (size_t)l * a.dim : kind == 3 ? a.rms_ffn + (size_t)l * a.dim : a.rms_final;
             const bool emb = kind == 0 && l == L0 && a.from_embed;
             const float *const *parts = nullptr;
-            if (kind == 3) parts = (const float *const *)sh.part[0];
-            else if (kind == 0 ? l > L0 : L1 > L0) parts = (const float *const *)sh.part[1];
-            prologue_norm<GS>(a, w, emb, parts, cur, sxq, sxs, sred, kind == 5);
+            if (kind == 3 || (kind == 0 ? l > L0 : L1 > L0)) { // a row-parallel GEMV (o_proj / down) has just run
+                if (fused_res) cur ^= 1;                       // single GPU: its epilogue already wrote x + result
+                else parts = (const float *const *)sh.part[kind == 3 ? 0 : 1];
+            }
             ph = kind == 0 ? PH_QKV : kind == 3 ? PH_GU : PH_HEAD;
+            prologue_norm<GS>(a, w, emb, parts, cur, sxq, sxs, sred, kind == 5, a.g[ph].KT, a.g[ph].G, pr);
         } else if (kind == 1) {
             // QK-norm + RoPE + attention (layers.rs:339-343)
             nsplit = mega_nsplit(pos, a.n_kv_l, gridDim.x);
             if ((int)blockIdx.x < a.n_kv_l * nsplit)
-                attention_item<KVMUL>(a, l, pos, blockIdx.x % a.n_kv_l, blockIdx.x / a.n_kv_l, nsplit, scratch);
+                attention_item<KVMUL>(a, l, pos, blockIdx.x % a.n_kv_l, blockIdx.x / a.n_kv_l, nsplit, scratch, pr);
         } else if (kind == 2) {
-            prologue_attn_out<GS>(a, nsplit, sxq, sxs); // quantize(att), qwen3.rs:152
+            prologue_attn_out<GS>(a, nsplit, sxq, sxs, a.g[PH_O].KT, a.g[PH_O].G); // quantize(att), qwen3.rs:152
             ph = PH_O;
         } else {
-            prologue_quant<GS>(a.hb, a.H_l, sxq, sxs); // quantize(hb), layers.rs:478
+            prologue_quant<GS>(a.hb, a.H_l, sxq, sxs, a.g[PH_DN].KT, a.g[PH_DN].G); // quantize(hb), layers.rs:478
             ph = PH_DN;
         }
-        prof_mark(a, ev);
+        prof_mark(pr, 1 + 3 * kind);
         // ------------------------------ GEMV ------------------------------
         if (kind != 1) {
             const MegaGemv &g = a.g[ph];
@@ -916,9 +1044,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
             if (kind == 3) {
                 // gate/up + SwiGLU (layers.rs:468-475): blocks of 8 pairs, a gate stage then an up stage
                 load_x<GS>(xr, sxq, sxs, 0, g.KT, g.G, lane);
-                for (int p0 = 0; p0 < count; p0 += 8) {
-                    const int np = count - p0 < 8 ? count - p0 : 8;
-                    if (((p0 >> 3) & 1) != grp) { // blocks alternate between the consumer groups
+                for (int p0 = 0, bi = 0; p0 < count; p0 += MEGA_GW, bi++) {
+                    const int np = count - p0 < MEGA_GW ? count - p0 : MEGA_GW;
+                    if ((bi & 1) != grp) { // blocks alternate between the consumer groups
                         it += 2;
                         continue;
                     }
@@ -927,6 +1055,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                         const int slot = it % MEGA_NSTAGE;
                         mbar_wait(&myfull[slot], (fullp >> slot) & 1, a.status);
                         fullp ^= 1u << slot;
+                        prof_mark(pr, 48 + slot);
                         {   // every warp runs the dot (warp-convergent shuffles); a warp without a row reads stale smem and drops the value
                             const uint32_t tile = ring_s + slot * slot_bytes + wl * g.tile_bytes;
                             float v = full_blocks ? tile_dot<GS, true>(tile, xr, g.KT, g.G, lane) : tile_dot<GS, false>(tile, xr, g.KT, g.G, lane);
@@ -944,22 +1073,33 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                 }
             } else {
                 // row phases: batches of 32 rows x n_kt K tiles x up to 4 stages of 8 rows
-                for (int b0 = 0; b0 < count; b0 += 32) {
-                    const int nb = count - b0 < 32 ? count - b0 : 32;
+                const bool x_once = MEGA_X_ONCE && g.n_kt == 1; // the whole activation fits the registers: load it once per phase
+                if (x_once) load_x<GS>(xr, sxq, sxs, 0, g.KT, g.G, lane);
+                for (int b0 = 0; b0 < count; b0 += MEGA_BATCH) {
+                    const int nb = count - b0 < MEGA_BATCH ? count - b0 : MEGA_BATCH;
                     float acc0 = 0.f, acc1 = 0.f; // this warp's rows in its (up to) two stages of the batch
+                    float xres0 = 0.f, xres1 = 0.f;
+                    if (fused_res && (kind == 2 || kind == 4) && lane == 0) { // residual values, in flight behind the GEMV
+                        const int r0 = b0 + MEGA_GW * grp + wl, r1 = r0 + 2 * MEGA_GW;
+                        if (r0 < b0 + nb) xres0 = ldcg_f(a.x[cur] + start + r0);
+                        if (r1 < b0 + nb) xres1 = ldcg_f(a.x[cur] + start + r1);
+                    }
                     for (int kt = 0; kt < g.n_kt; kt++) {
-                        load_x<GS>(xr, sxq, sxs, kt, g.KT, g.G, lane);
-                        for (int sidx = 0; 8 * sidx < nb; sidx++) {
+                        if (!x_once) load_x<GS>(xr, sxq, sxs, kt, g.KT, g.G, lane);
+                        prof_mark(pr, 58);
+                        for (int sidx = 0; MEGA_GW * sidx < nb; sidx++) {
                             if ((sidx & 1) == grp) { // stages alternate between the two consumer groups
                                 const int slot = it % MEGA_NSTAGE;
                                 mbar_wait(&myfull[slot], (fullp >> slot) & 1, a.status);
                                 fullp ^= 1u << slot;
+                                prof_mark(pr, 48 + slot);
                                 {
                                     const uint32_t tile = ring_s + slot * slot_bytes + wl * g.tile_bytes;
                                     float v = full_blocks ? tile_dot<GS, true>(tile, xr, g.KT, g.G, lane) : tile_dot<GS, false>(tile, xr, g.KT, g.G, lane);
-                                    v = (8 * sidx + wl < nb) ? v : 0.0f; // warp without a row: stale smem, value dropped
+                                    v = (MEGA_GW * sidx + wl < nb) ? v : 0.0f; // warp without a row: stale smem, value dropped
                                     acc0 += sidx < 2 ? v : 0.0f;
                                     acc1 += sidx < 2 ? 0.0f : v;
+                                    prof_mark(pr, 59);
                                 }
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive(&empty[slot]);
@@ -971,17 +1111,21 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                     if (lane == 0) {
                         for (int j = 0; j < 2; j++) {
                             const int sidx = grp + 2 * j;
-                            if (8 * sidx + wl >= nb) break;
-                            const int r = start + b0 + 8 * sidx + wl;
+                            if (MEGA_GW * sidx + wl >= nb) break;
+                            const int r = start + b0 + MEGA_GW * sidx + wl;
                             const float v = j == 0 ? acc0 : acc1;
                             if (kind == 0) { // layers.rs:334-336
                                 if (r < a.AH_l) a.q[r] = v;
                                 else if (r < a.AH_l + a.KV_l) a.kraw[r - a.AH_l] = v;
                                 else vrow[r - a.AH_l - a.KV_l] = v;
-                            } else if (kind == 2 || kind == 4) { // row-parallel partial sums -> every rank's landing zone
-                                float *const *dst = sh.part[kind == 2 ? 0 : 1];
+                            } else if (kind == 2 || kind == 4) {
+                                if (fused_res) {
+                                    a.x[cur ^ 1][r] = __fadd_rn(j == 0 ? xres0 : xres1, v);
+                                } else { // row-parallel partial sums -> every rank's landing zone
+                                    float *const *dst = sh.part[kind == 2 ? 0 : 1];
 #pragma unroll 1
-                                for (int p = 0; p < a.tp_size; p++) dst[p][(size_t)a.tp_rank * a.dim + r] = v;
+                                    for (int p = 0; p < a.tp_size; p++) dst[p][(size_t)a.tp_rank * a.dim + r] = v;
+                                }
                             } else { // lm_head (qwen3.rs:76) + greedy argmax candidate (sampler.rs:57-59)
                                 const int row = a.vocab_row0 + r;
                                 sh.logits[a.tp_rank][row] = v;
@@ -999,7 +1143,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
             }
             cross = kind == 2 || kind == 4 || kind == 5;
         }
-        prof_mark(a, ev);
+        prof_mark(pr, 2 + 3 * kind);
         if (kind == 5) {
             long long *sbest = reinterpret_cast<long long *>(sred + 32);
             if (lane == 0) sbest[warp] = best;
@@ -1010,10 +1154,38 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                 for (int p = 0; p < a.tp_size; p++) sh.best[p][(size_t)a.tp_rank * gridDim.x + blockIdx.x] = (unsigned long long)best;
             }
         }
-        grid_barrier(a, bs, cross);
-        prof_mark(a, ev);
+        // pull what the next step's first instructions will miss on (static weights, HBM-cold) into L2 while
+        // this CTA waits in the barrier: the next RMSNorm weight, or the QK-norm weights + this position's RoPE row
+        if (MEGA_PREFETCH_W && (kind == 2 || kind == 4)) {
+            const float *wn = kind == 2 ? a.rms_ffn + (size_t)l * a.dim : (l + 1 < L1 ? a.rms_att + (size_t)(l + 1) * a.dim : a.rms_final);
+            if (tid * 32 < a.dim) asm volatile("prefetch.global.L2 [%0];" ::"l"(wn + tid * 32));
+        } else if (kind == 0) {
+            if (MEGA_PREFETCH_W && tid < 12) {
+                const float *wn = tid < 4 ? a.q_ln + (size_t)l * HEAD_DIM + tid * 32 : tid < 8 ? a.k_ln + (size_t)l * HEAD_DIM + (tid - 4) * 32
+                                                                                       : a.rope + (size_t)pos * HEAD_DIM + (tid - 8) * 32;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(wn));
+            }
+            // ... and the head of this CTA's slice of the K/V cache for the attention step (cold beyond a few hundred positions)
+            const int ns = mega_nsplit(pos, a.n_kv_l, gridDim.x);
+            if (MEGA_PREFETCH_KV && (int)blockIdx.x < a.n_kv_l * ns) {
+                const int kvh = blockIdx.x % a.n_kv_l, split = blockIdx.x / a.n_kv_l;
+                const int per = (pos + 1 + ns - 1) / ns;
+                const int t0 = split * per;
+                int cnt = pos - t0; // rows before `pos` (row `pos` is written in this step)
+                cnt = cnt > per ? per : cnt;
+                cnt = cnt > 256 ? 256 : cnt;
+                const size_t lbase = (size_t)l * a.seq_len * a.KV_l + (size_t)kvh * HEAD_DIM;
+                for (int i = tid; i < cnt * 8; i += MEGA_CTHREADS) {
+                    const float *base = (i & 4) ? a.vc : a.kc;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + lbase + (size_t)(t0 + (i >> 3)) * a.KV_l + (i & 3) * 32));
+                }
+            }
+        }
+        grid_barrier(a, bs, cross, pr);
+        prof_mark(pr, 3 + 3 * kind);
     }
 
+    if (pr.row) pr.row[MEGA_PROF_EVENTS - 1] = (unsigned long long)pr.ev;
     if (a.run_head) {
         if (blockIdx.x == 0 && warp == 0) {
             long long b = (long long)0x8000000000000000LL;
@@ -1040,7 +1212,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
         }
     } else {
         // teacher-forced layer range: materialise x = x + pending partial sums into x[0]
-        if (blockIdx.x == 0 && L1 > L0) {
+        if (fused_res) {
+            if (L1 > L0) cur ^= 1; // the last down epilogue wrote the merged stream
+            if (blockIdx.x == 0 && cur != 0)
+                for (int i = tid; i < a.dim; i += MEGA_CTHREADS) a.x[0][i] = ldcg_f(a.x[cur] + i);
+        } else if (blockIdx.x == 0 && L1 > L0) {
             for (int i = tid; i < a.dim; i += MEGA_CTHREADS) {
                 float v = ldcg_f(a.x[cur] + i);
 #pragma unroll 1

@@ -99,7 +99,7 @@ def load_library():
     """dlopen libqwen3cuda.so (building it first if nvcc is present and it is stale)."""
     global _lib
     if _lib is None:
-        path = _build.LIB
+        path = os.environ.get("Q3_LIB") or _build.LIB  # Q3_LIB: a tuning variant built by scripts/ab_variants.py
         if not os.path.exists(path):
             path = _build.build()
         L = C.CDLL(path)
@@ -202,8 +202,11 @@ class Transformer:
         return ms.value / max(n.value, 1), b.value, n.value
 
     def debug_profile(self, token: int, pos: int, num_sms: int = 148) -> np.ndarray:
-        """Per-CTA phase timestamps (ns) of one persistent-kernel decode step: [num_sms, n_events]."""
-        buf = np.zeros((num_sms, 1024), np.uint64)
+        """Per-CTA tagged clock stamps of one persistent-kernel decode step: [3 * num_sms, 4096] of (clock64 << 8 | tag),
+        rows [0, num_sms) from consumer thread 0, [num_sms, 2 num_sms) from producer 0, [2 num_sms, 3 num_sms) from the
+        first lane of consumer group 1 (same SM clock);
+        the last column is the row's event count (see prof_mark in csrc/q3_mega.cuh)."""
+        buf = np.zeros((3 * num_sms, 4096), np.uint64)
         n = C.c_int(0)
         _check(load_library().q3_debug_profile(self._h, token, pos, _ptr(buf), C.byref(n)))
         return buf[:, : n.value]

@@ -1,5 +1,6 @@
-"""Phase-level timeline of the persistent decode kernel from in-kernel clock64 stamps."""
+"""Phase-level timeline of the persistent decode kernel from its in-kernel tagged clock64 stamps (prof_mark in q3_mega.cuh)."""
 import os, sys
+from collections import defaultdict
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
@@ -12,20 +13,77 @@ path = bench.bench_checkpoint(model, 64)
 m = T.TransformerBuilder.new(path).with_ctx_length(max(256, pos + 8)).build()
 for p in range(4):
     m.forward_argmax(1, p)
-t = m.debug_profile(1, pos).astype(np.int64)
+raw = m.debug_profile(1, pos)
+np.save("gpurun_out/mega_profile_%s_pos%d.npy" % (model, pos), raw)
+
+KINDS = ["qkv", "att", "o", "gu", "dn", "head"]
+MAIN = ["pro", "gemv", "bar"]
+FINE = {32: "load", 33: "reduce", 34: "quant", 35: "qknorm", 36: "positions", 40: "cta_sync", 41: "grid"}
+order = []
+acc = defaultdict(list)       # label -> list over CTAs of per-CTA mean us
+total = []
+NS = raw.shape[0] // 3
+for c in range(NS):
+    n = int(raw[c, -1])
+    t = (raw[c, :n] >> np.uint64(8)).astype(np.int64)
+    tag = (raw[c, :n] & np.uint64(255)).astype(np.int64)
+    total.append((t[-1] - t[0]) / (GHZ * 1e3))
+    per = defaultdict(list)
+    pend = []
+    seen_layers = 0
+    tprev = t[0]
+    for i in range(1, n):
+        d = (t[i] - tprev) / (GHZ * 1e3)
+        if tag[i] >= 48:
+            continue  # stage-ready marks: timeline view only
+        tprev = t[i]
+        if tag[i] >= 32:
+            pend.append((FINE.get(int(tag[i]), str(tag[i])), d))
+            continue
+        k, sub = divmod(int(tag[i]) - 1, 3)
+        base = "%s_%s" % (KINDS[k], MAIN[sub])
+        if k == 0 and sub == 0:
+            seen_layers += 1
+        skip = k < 5 and seen_layers <= 2  # first layers: cold start
+        for name, dd in pend:
+            if not skip: per[base + "." + name].append(dd)
+            if c == 0 and base + "." + name not in order: order.append(base + "." + name)
+        if not skip: per[base + (".rest" if pend else "")].append(d)
+        lab = base + (".rest" if pend else "")
+        if c == 0 and lab not in order: order.append(lab)
+        pend = []
+    for k2, v in per.items():
+        acc[k2].append(np.mean(v))
 L = m.get_config().n_layers
-names = ["qkv_pro", "qkv_gemv", "qkv_bar", "att", "att_-", "att_bar", "o_pro", "o_gemv", "o_bar", "gu_pro", "gu_gemv", "gu_bar",
-         "dn_pro", "dn_gemv", "dn_bar"]
-E = len(names)
-ev = t[:, 1:1 + E * L].reshape(t.shape[0], L, E)
-start = np.concatenate([t[:, :1], ev[:, :-1, -1]], axis=1)[:, :, None]        # [cta, L, 1] end of previous layer
-d = np.diff(np.concatenate([start, ev], axis=2), axis=2) / (GHZ * 1e3)         # us, [cta, L, 14]
-tot = (t[:, 1 + E * L + 2] - t[:, 0]) / (GHZ * 1e3)
-print(f"{model} pos {pos}: kernel {tot.mean():.1f} us (per CTA mean); per layer {d[:, 1:-1].sum(axis=2).mean():.2f} us")
-print("phase      mean_us  [min..max over CTAs of the per-CTA mean]   layer-1 only")
-for i, n in enumerate(names):
-    x = d[:, 2:-1, i].mean(axis=1)
-    print(f"{n:9s} {x.mean():7.2f}   [{x.min():6.2f} .. {x.max():6.2f}]   {d[:, 1, i].mean():7.2f}")
-h = np.diff(np.concatenate([ev[:, -1, -1:], t[:, 1 + E * L: 1 + E * L + 3]], axis=1), axis=1) / (GHZ * 1e3)
-print("head: prologue %.1f gemv %.1f barrier %.1f us" % tuple(h.mean(0)))
-np.save("gpurun_out/mega_profile_%s_pos%d.npy" % (model, pos), t)
+print(f"{model} pos {pos}: kernel {np.mean(total):.1f} us (per-CTA mean)")
+print("step                    mean_us  [min .. max over CTAs of the per-CTA mean]")
+layer_sum = 0.0
+for lab in order:
+    x = np.array(acc[lab])
+    if not lab.startswith("head"): layer_sum += x.mean()
+    print(f"{lab:22s} {x.mean():7.2f}   [{x.min():6.2f} .. {x.max():6.2f}]")
+print(f"per layer (sum of the means above, head excluded): {layer_sum:.2f} us")
+
+# merged consumer/producer timeline of one CTA for one mid-model layer
+def timeline(c, layer=5):
+    rows = []
+    for r, who in ((c, "C"), (NS + c, "P"), (2 * NS + c, "      D")):
+        n = int(raw[r, -1])
+        for e in raw[r, :n]:
+            rows.append((int(e >> np.uint64(8)), who, int(e & np.uint64(255))))
+    rows.sort()
+    # find layer boundaries on the consumer row: tag 1 (qkv_pro done) occurrences
+    starts = [t for t, who, tag in rows if who == "C" and tag == 3 + 3 * 4]  # dn_bar done = layer end
+    t0, t1 = starts[layer - 1], starts[layer]
+    print(f"--- CTA {c}, layer {layer}: timeline (us from the end of the previous layer) ---")
+    for t, who, tag in rows:
+        if t0 <= t <= t1:
+            if tag >= 64: name = "issue slot %d" % (tag - 64)
+            elif tag == 58: name = "x loaded"
+            elif tag == 59: name = "tile done"
+            elif tag >= 48: name = "ready slot %d" % (tag - 48)
+            elif tag >= 32: name = FINE.get(tag, str(tag))
+            else: name = "%s_%s done" % (KINDS[(tag - 1) // 3], MAIN[(tag - 1) % 3])
+            print(f"{(t - t0) / (GHZ * 1e3):8.2f}  {who}  {name}")
+timeline(0)
+timeline(77)
