@@ -487,30 +487,37 @@ __device__ __noinline__ void prologue_attn_out(const MegaArgs &a, int nsplit, ui
         csync();
         return;
     }
+    // A warp handles one head per iteration (32 float4 = 128 dims).  Lane s first fetches the statistics of split s
+    // (one memory round trip for all splits instead of one per split), then the partial accumulators are pulled
+    // four splits at a time.
 #pragma unroll 1
     for (int base = tid - lane; base < n4; base += MEGA_CTHREADS) {
-        int i4 = base + lane;
-        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i4 < n4) {
-            int head = i4 >> 5, d4 = i4 & 31;
-            const float *pb = a.attn_part + (size_t)head * MEGA_MAX_SPLITS * ATTN_PART_STRIDE;
-            float M = -INFINITY;
-            for (int s = 0; s < nsplit; s++) M = fmaxf(M, ldcg_f(pb + s * ATTN_PART_STRIDE + HEAD_DIM));
-            float L = 0.0f;
-            float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int s = 0; s < nsplit; s++) {
-                const float *ps = pb + s * ATTN_PART_STRIDE;
-                float c = expf(ldcg_f(ps + HEAD_DIM) - M);
-                L += ldcg_f(ps + HEAD_DIM + 1) * c;
-                float4 p = ldcg_f4(ps + d4 * 4);
-                A.x += p.x * c;
-                A.y += p.y * c;
-                A.z += p.z * c;
-                A.w += p.w * c;
+        const int i4 = base + lane;
+        const int head = base >> 5; // warp-uniform
+        const float *pb = a.attn_part + (size_t)head * MEGA_MAX_SPLITS * ATTN_PART_STRIDE;
+        const float ms = lane < nsplit ? ldcg_f(pb + lane * ATTN_PART_STRIDE + HEAD_DIM) : -INFINITY;
+        const float ls = lane < nsplit ? ldcg_f(pb + lane * ATTN_PART_STRIDE + HEAD_DIM + 1) : 0.0f;
+        const float M = warp_max(ms);
+        const float cs = lane < nsplit ? expf(ms - M) : 0.0f;
+        const float L = warp_sum(ls * cs);
+        float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int s0 = 0; s0 < nsplit; s0 += 4) {
+            float4 pv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                pv[j] = (s0 + j < nsplit) ? ldcg_f4(pb + (s0 + j) * ATTN_PART_STRIDE + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float c = __shfl_sync(0xffffffffu, cs, (s0 + j) & 31);
+                A.x += pv[j].x * c;
+                A.y += pv[j].y * c;
+                A.z += pv[j].z * c;
+                A.w += pv[j].w * c;
             }
-            float inv = __fdiv_rn(1.0f, L);
-            y = make_float4(__fmul_rn(A.x, inv), __fmul_rn(A.y, inv), __fmul_rn(A.z, inv), __fmul_rn(A.w, inv));
         }
+        const float inv = __fdiv_rn(1.0f, L);
+        const float4 y = make_float4(__fmul_rn(A.x, inv), __fmul_rn(A.y, inv), __fmul_rn(A.z, inv), __fmul_rn(A.w, inv));
         uint32_t packed;
         float scale;
         quantize_group4<GS>(y, packed, scale);
@@ -558,7 +565,10 @@ __device__ __forceinline__ float4 qk_norm_rope(float4 v, const float *w, const f
     return r;
 }
 
-constexpr int MEGA_ATTN_CHUNK = 64; // positions per split before another CTA is recruited
+#ifndef MEGA_ATTN_CHUNK_
+#define MEGA_ATTN_CHUNK_ 64
+#endif
+constexpr int MEGA_ATTN_CHUNK = MEGA_ATTN_CHUNK_; // positions per split before another CTA is recruited
 __device__ __forceinline__ int mega_nsplit(int pos, int n_kv_l, int grid) {
     int n = pos + 1;
     int ns = (n + MEGA_ATTN_CHUNK - 1) / MEGA_ATTN_CHUNK;

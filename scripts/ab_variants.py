@@ -35,7 +35,7 @@ else:
     ntok = int(sys.argv[4]) if len(sys.argv) > 4 else 32
     libs = sorted(glob.glob(os.path.join(VDIR, "variant_*.so")))
     res = {l: [] for l in libs}
-    for rep in range(2):
+    for rep in range(int(os.environ.get('AB_REPS', '2'))):
         for l in libs:
             r = subprocess.run([sys.executable, __file__, "child", model, str(pos0), str(ntok)], env=dict(os.environ, Q3_LIB=l),
                                capture_output=True, text=True, timeout=300)

@@ -449,6 +449,36 @@ def test_qwen3_06b_fast_mode_free_running_vs_noise_floor(q06, ckpt):
     assert np.median(gpu_err) <= 3 * np.median(noise_err) + LOGIT_TOL
 
 
+def test_chat_turns_through_one_prefill_each(models):
+    """generation.chat (the reference's chat loop on token ids) with one q3_prefill per user turn: positions, KV rows
+    and sampler RNG advance exactly as the reference's token-by-token loop; the first reply token agrees whenever
+    the sequential path's top-2 margin is wider than the fast-mode noise."""
+    m = models("small", 64, 3)
+    V = m.get_config().vocab_size
+    turns = [[5, 9, 200, 31, 77, 3], [7, 7, 300]]
+    m.reset()
+    sa = Sampler(V, 0.8, 0.9, 7)
+    ra = generation.chat(m, sa, turns, use_prefill=False, max_new_per_turn=4)
+    kv_a = m.kv_read(0, 0, 17)
+    m.reset()
+    sb = Sampler(V, 0.8, 0.9, 7)
+    rb = generation.chat(m, sb, turns, use_prefill=True, max_new_per_turn=4)
+    kv_b = m.kv_read(0, 0, 17)
+    assert [len(r) for r in ra] == [len(r) for r in rb] == [4, 4]
+    assert sa.rng_state == sb.rng_state  # same number of draws
+    # layer-0 K/V rows of the first turn depend only on the tokens: identical up to reassociation
+    np.testing.assert_allclose(kv_b[0][:6], kv_a[0][:6], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(kv_b[1][:6], kv_a[1][:6], rtol=0, atol=2e-3)
+    m.reset()
+    for p, t in enumerate(turns[0]):
+        lg = m.forward(t, p)
+    top = np.sort(lg)[-2:]
+    m.reset()
+    g1 = generation.chat(m, Sampler(V, 0.0, 0.9, 0), turns[:1], use_prefill=True, max_new_per_turn=1)[0]
+    if top[1] - top[0] > 0.5:
+        assert g1 == [argmax_last(lg)]
+
+
 # ---- batched prefill: tcgen05 int8 GEMM -----------------------------------------------------------
 @pytest.mark.parametrize("T,N,K,gs", [(128, 128, 128, 64), (37, 256, 512, 64), (300, 384, 1024, 32), (130, 128, 2560, 128),
                                       (257, 512, 4096, 64)])

@@ -87,3 +87,49 @@ def test_generate_stops_on_eos_and_seq_len(ckpt):
     assert got == orc.Model(path).generate([9], 10, eos=full[k])
     m = orc.Model(path, 6)
     assert len(m.generate([9], 100)) == 6  # pos < seq_len (generation.rs:25)
+
+
+class _ReplayPrefill(_Replay):
+    """+ q3_prefill's contract: cache and last-token logits as after sequential forwards."""
+
+    def __init__(self, path):
+        super().__init__(path)
+        self.prefills = []
+
+    def prefill(self, tokens, pos0):
+        self.prefills.append((list(tokens), pos0))
+        for i, t in enumerate(tokens):
+            lg = self.o.forward(t, pos0 + i)
+        return lg
+
+
+@pytest.mark.parametrize("temperature,topp", [(0.0, 0.9), (0.8, 0.9), (1.0, 1.0)])
+def test_chat_with_one_prefill_per_turn_matches_the_reference_loop(ckpt, temperature, topp):
+    """generation.rs:95-126 forwards and samples every prompt token; the drop-in runs q3_prefill once per turn
+    and advances the sampler's RNG by the draws the discarded samples would have consumed: same replies,
+    same RNG state afterwards."""
+    path = ckpt("tiny", 64, seed=2)
+    turns = [[5, 9, 200, 31], [7, 7, 300], [11]]
+    V = orc.Model(path).config["vocab_size"]
+    a, b = _ReplayPrefill(path), _ReplayPrefill(path)
+    sa, sb = Sampler(V, temperature, topp, 42), Sampler(V, temperature, topp, 42)
+    ra = generation.chat(a, sa, turns, use_prefill=False, max_new_per_turn=5)
+    rb = generation.chat(b, sb, turns, use_prefill=True, max_new_per_turn=5)
+    assert ra == rb and [len(r) for r in ra] == [5, 5, 5]
+    assert sa.rng_state == sb.rng_state
+    assert not a.prefills and [p[1] for p in b.prefills] == [0, 4 + 5, 4 + 5 + 3 + 5]  # one call per turn, at the turn's position
+    assert len(a.calls) == len(b.calls) + sum(len(t) for t in turns)
+
+
+def test_chat_stops_a_turn_on_eos_and_resets_on_a_full_window(ckpt):
+    path = ckpt("tiny", 64, seed=2)
+    t = _ReplayPrefill(path)
+    V, S = t.get_config().vocab_size, t.get_config().seq_len
+    free = generation.chat(t, Sampler(V, 0.0, 0.9, 0), [[5, 9]], max_new_per_turn=6)[0]
+    eos = free[3]
+    stopped = generation.chat(_ReplayPrefill(path), Sampler(V, 0.0, 0.9, 0), [[5, 9]], eos_token_id=eos)[0]
+    assert stopped == free[:free.index(eos)]  # the terminating token is not emitted (generation.rs:136-141)
+    # no cap and no eos: generation runs to the end of the window, then the position resets and the next turn starts at 0
+    t2 = _ReplayPrefill(path)
+    r = generation.chat(t2, Sampler(V, 0.0, 0.9, 0), [[5, 9], [7]])
+    assert len(r[0]) == S - 2 and t2.prefills[1] == ([7], 0)
