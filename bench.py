@@ -154,11 +154,13 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kind: str):
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+def ncu_traffic(kind: str, workload: str = ""):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture; null when the capture
+    was taken on another workload (model / group size / GPUs) than the one being timed."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get(kind)
+            d = json.load(f)
+        return d.get(kind) if d.get("workload", "") == workload else None
     except Exception:
         return None
 
@@ -366,7 +368,7 @@ def main():
             # over the timed region above
             roof = {"bound": "hbm", "kernel": "k_mega_decode (persistent single-launch decode step)",
                     "achieved": token_roof["achieved"], "peak": peak, "unit": "GB/s", "frac": token_roof["frac"],
-                    "traffic": ncu_traffic("mega"), "bytes_per_launch": btok, "us_per_launch": tok_ms * 1e3,
+                    "traffic": ncu_traffic("mega", f"{args.model}/gs{args.group_size}/tp{world}"), "bytes_per_launch": btok, "us_per_launch": tok_ms * 1e3,
                     "peak_source": peak_src}
         if world == 1:
             m.set_decode_path(0)
@@ -377,7 +379,7 @@ def main():
             g = kernels["gate_up"]
             roof = {"bound": "hbm", "kernel": "gate/up int8 GEMV + SwiGLU (k_gemv<EPI_SWIGLU>)",
                     "achieved": g["GBps"], "peak": peak, "unit": "GB/s", "frac": g["GBps"] / peak,
-                    "traffic": ncu_traffic("gate_up"), "bytes_per_launch": g["bytes"], "us_per_launch": g["us"],
+                    "traffic": ncu_traffic("gate_up", f"{args.model}/gs{args.group_size}/tp{world}"), "bytes_per_launch": g["bytes"], "us_per_launch": g["us"],
                     "peak_source": peak_src}
     except Exception as e:  # noqa: BLE001
         log(f"[bench] kernel roofline failed: {e}")

@@ -608,11 +608,18 @@ static int launch_mega(q3_handle *h, int l0, int l1, bool from_embed, bool run_h
     return 0;
 }
 
-// after a synchronize: did any in-kernel wait time out?
-static int mega_check(q3_handle *h) {
+// did any in-kernel wait time out?  The per-token entry points queue the 4-byte status read on the stream BEFORE their
+// one synchronize (mega_status_async) so that the check costs no extra round trip; the others read it here.
+static int mega_status_async(q3_handle *h) {
+    if (!h->d_status || h->decode_path != 1) return 0;
+    CK(cudaMemcpyAsync(h->h_small + 16, h->d_status, 4, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+static int mega_check(q3_handle *h, bool queued = false) {
     if (!h->d_status || h->decode_path != 1) return 0;
     int code = 0;
-    CK(cudaMemcpy(&code, h->d_status, 4, cudaMemcpyDeviceToHost));
+    if (queued) code = h->h_small[16];
+    else CK(cudaMemcpy(&code, h->d_status, 4, cudaMemcpyDeviceToHost));
     if (code) {
         cudaMemset(h->d_status, 0, 64);
         h->bar_base = 0;
@@ -1126,6 +1133,7 @@ extern "C" int q3_forward(q3_handle *h, int token, int pos, float *logits_host) 
     } else {
         CK(cudaGraphLaunch(h->g_fwd[h->exact], h->stream));
     }
+    if ((rc = mega_status_async(h))) return rc;
     if (logits_host) {
         CK(cudaMemcpyAsync(h->h_logits, h->logits, (size_t)h->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -1133,7 +1141,7 @@ extern "C" int q3_forward(q3_handle *h, int token, int pos, float *logits_host) 
     } else {
         CK(cudaStreamSynchronize(h->stream));
     }
-    return mega_check(h);
+    return mega_check(h, true);
 }
 
 extern "C" int q3_forward_argmax(q3_handle *h, int token, int pos, int *next_token) {
@@ -1148,9 +1156,10 @@ extern "C" int q3_forward_argmax(q3_handle *h, int token, int pos, int *next_tok
         CK(cudaGraphLaunch(h->g_greedy[h->exact], h->stream));
     }
     CK(cudaMemcpyAsync(h->h_small + 8, h->d_tokpos + 2, 4, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = mega_status_async(h))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     *next_token = h->h_small[8];
-    return mega_check(h);
+    return mega_check(h, true);
 }
 
 extern "C" int q3_decode_greedy(q3_handle *h, int first_token, int pos0, int n, int *tokens_out) {

@@ -49,7 +49,7 @@ constexpr long long MEGA_L2_AHEAD = 0;                 // bytes per CTA the L2 p
 
 // tuning switches (compile-time; scripts/ab_variants.py builds and times the alternatives on one box)
 #ifndef MEGA_PREFETCH_W
-#define MEGA_PREFETCH_W 0   // L2-prefetch the next norm / QK-norm / RoPE weights before entering a grid barrier
+#define MEGA_PREFETCH_W 1   // L2-prefetch the next norm / QK-norm / RoPE weights before entering a grid barrier
 #endif
 #ifndef MEGA_PREFETCH_KV
 #define MEGA_PREFETCH_KV 0  // L2-prefetch this CTA's K/V cache slice before the qkv barrier
@@ -566,7 +566,7 @@ __device__ __forceinline__ float4 qk_norm_rope(float4 v, const float *w, const f
 }
 
 #ifndef MEGA_ATTN_CHUNK_
-#define MEGA_ATTN_CHUNK_ 64
+#define MEGA_ATTN_CHUNK_ 32
 #endif
 constexpr int MEGA_ATTN_CHUNK = MEGA_ATTN_CHUNK_; // positions per split before another CTA is recruited
 __device__ __forceinline__ int mega_nsplit(int pos, int n_kv_l, int grid) {

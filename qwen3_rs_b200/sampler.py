@@ -16,7 +16,12 @@ def _total_key(a: np.ndarray) -> np.ndarray:
 
 
 def argmax_last(logits: np.ndarray) -> int:
-    k = _total_key(logits)
+    a = np.ascontiguousarray(logits, np.float32)
+    i = int(np.argmax(a))  # first maximum; the first NaN if there is one
+    m = a[i]
+    if m == m and m != 0.0 and np.count_nonzero(a == m) == 1:
+        return i  # a unique, non-zero, non-NaN maximum: total_cmp and == agree and first == last
+    k = _total_key(a)
     return int(k.size - 1 - np.argmax(k[::-1]))
 
 
