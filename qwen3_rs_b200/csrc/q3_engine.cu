@@ -80,6 +80,9 @@ struct q3_handle {
     float *rope = nullptr; // [seq_len][64][2]
     // activations
     float *x = nullptr, *xb = nullptr, *q = nullptr, *hb = nullptr, *logits = nullptr, *attn_part = nullptr;
+    uint8_t *att_q = nullptr;  // persistent kernel: quantised attention output (+ scales, + per kv head split counters)
+    float *att_s = nullptr;
+    unsigned *att_cnt = nullptr;
     int8_t *xq = nullptr, *hq = nullptr;
     float *xs = nullptr, *hs = nullptr;
     float *kc = nullptr, *vc = nullptr; // [L][seq_len][KV_l]
@@ -573,6 +576,7 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
     int *d_status = h->d_status;
     a.x[0] = h->x; a.x[1] = h->x2;
     a.q = h->q; a.kraw = h->kraw; a.hb = h->hb; a.attn_part = h->attn_part;
+    a.att_q = h->att_q; a.att_s = h->att_s; a.att_cnt = h->att_cnt;
     a.dbg = getenv("Q3_MEGA_DBG") ? atoi(getenv("Q3_MEGA_DBG")) : 0;
     a.bar = h->d_bar; a.status = d_status; a.tokpos = h->d_tokpos; a.history = h->d_history;
     // until q3_tp_connect every "peer" slot points at this rank's own buffers
@@ -626,6 +630,7 @@ static int mega_check(q3_handle *h, bool queued = false) {
         h->xbar_base = 0;
         cudaMemset(h->d_bar, 0, 64);
         cudaMemset(h->d_flags, 0, 64 * 4);
+        if (h->att_cnt) cudaMemset(h->att_cnt, 0, (size_t)h->cfg.n_layers * h->n_kv_l * 4);
         return fail(Q3_ECUDA, "persistent decode kernel: a wait timed out (status %d: 1 grid barrier, 2 stage ring, 3 peer flag)", code);
     }
     return 0;
@@ -953,6 +958,10 @@ static int create_impl(const char *path, int ctx_len, int device, int tp_rank, i
     TRY(dmalloc(h, (void **)&h->hq, (size_t)h->H_l));
     TRY(dmalloc(h, (void **)&h->hs, (size_t)(h->H_l / gs + 1) * 4));
     TRY(dmalloc(h, (void **)&h->attn_part, (size_t)h->n_heads_l * ATTN_MAX_SPLITS * ATTN_PART_STRIDE * 4));
+    TRY(dmalloc(h, (void **)&h->att_q, (size_t)h->AH_l));
+    TRY(dmalloc(h, (void **)&h->att_s, (size_t)(h->AH_l / gs) * 4));
+    TRY(dmalloc(h, (void **)&h->att_cnt, (size_t)h->cfg.n_layers * h->n_kv_l * 4));
+    CKH(cudaMemset(h->att_cnt, 0, (size_t)h->cfg.n_layers * h->n_kv_l * 4));
     TRY(dmalloc(h, (void **)&h->att, (size_t)h->n_heads_l * c.seq_len * 4));
     TRY(prepare_exact_kernels());
     size_t kvn = (size_t)L * c.seq_len * h->KV_l;

@@ -72,6 +72,9 @@ constexpr long long MEGA_L2_AHEAD = 0;                 // bytes per CTA the L2 p
 #ifndef MEGA_RELAXED_POLL
 #define MEGA_RELAXED_POLL 0 // grid barrier: poll with relaxed loads, one acquire fence at the end
 #endif
+#ifndef MEGA_ATT_FINALIZE
+#define MEGA_ATT_FINALIZE 0 // the last attention split of a kv head merges the splits AND quantises; the o_proj prologue only copies
+#endif
 #ifndef MEGA_X_ONCE
 #define MEGA_X_ONCE 0       // load the activation registers once per phase when n_kt == 1
 #endif
@@ -98,6 +101,9 @@ struct MegaArgs {
     float *x[2];                     // residual stream, ping-pong
     float *part[2][MEGA_MAX_TP];     // [o|down][rank]: that rank's landing zone [tp][dim] (peer memory under TP)
     float *q, *kraw, *hb, *attn_part;
+    uint8_t *att_q;                  // MEGA_ATT_FINALIZE: quantised attention output, already in the shared-memory chunk order of PH_O
+    float *att_s;                    // ... and its group scales
+    unsigned *att_cnt;               // [n_layers][n_kv_l] arrivals of the splits of a kv head (returns to 0 within the launch)
     float *logits[MEGA_MAX_TP];      // full-vocab logits buffer of every rank
     unsigned long long *best[MEGA_MAX_TP]; // [tp][grid] argmax candidates of every rank
     unsigned long long *bar;         // grid barrier counter (monotonic, never reset)
@@ -579,7 +585,7 @@ __device__ __forceinline__ int mega_nsplit(int pos, int n_kv_l, int grid) {
 }
 
 // attention phase for one (kv head, split) work item; all 256 consumer threads.
-template <int KVMUL>
+template <int GS, int KVMUL>
 __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int pos, int kvh, int split, int nsplit,
                                                uint8_t *scratch, Prof &pr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -707,6 +713,74 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
             dst[HEAD_DIM + 1] = L;
         }
     }
+#if MEGA_ATT_FINALIZE
+    // The split that arrives LAST at its kv head's counter merges all splits of the group's query heads, normalises and
+    // quantises them (qwen3.rs:152) and stores the int8 bytes in the chunk order the o_proj phase keeps in shared memory:
+    // the o_proj prologue of all 148 CTAs shrinks to a 4 KB copy, at the price of one merge on the (8 x nsplit)-CTA
+    // attention path.  Release: bar.sync + thread 0's fence before its atomic; acquire: fence after it.
+    unsigned *flag = reinterpret_cast<unsigned *>(sm_m); // the position-loop statistics have been consumed above
+    bool last = true;
+    if (nsplit > 1) {
+        csync();
+        if (tid == 0) {
+            __threadfence();
+            unsigned *cnt = a.att_cnt + (size_t)layer * a.n_kv_l + kvh;
+            const unsigned old = atomicAdd(cnt, 1u);
+            const bool is_last = old == (unsigned)nsplit - 1;
+            if (is_last) *cnt = 0; // every split of this (layer, kv head) has arrived; next use is the next launch
+            __threadfence();
+            *flag = is_last ? 1u : 0u;
+        }
+        csync();
+        last = *flag != 0;
+    } else {
+        csync(); // the single split's own partial stores must be visible to the warps re-reading them
+    }
+    if (last && warp < KVMUL) {
+        const int head = kvh * KVMUL + warp;
+        const float *pb = a.attn_part + (size_t)head * MEGA_MAX_SPLITS * ATTN_PART_STRIDE;
+        const float ms = lane < nsplit ? ldcg_f(pb + lane * ATTN_PART_STRIDE + HEAD_DIM) : -INFINITY;
+        const float ls = lane < nsplit ? ldcg_f(pb + lane * ATTN_PART_STRIDE + HEAD_DIM + 1) : 0.0f;
+        const float M = warp_max(ms);
+        const float cs = lane < nsplit ? expf(ms - M) : 0.0f;
+        const float L = warp_sum(ls * cs);
+        float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int s0 = 0; s0 < nsplit; s0 += 4) {
+            float4 pv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                pv[j] = (s0 + j < nsplit) ? ldcg_f4(pb + (s0 + j) * ATTN_PART_STRIDE + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float c = __shfl_sync(0xffffffffu, cs, (s0 + j) & 31);
+                A.x += pv[j].x * c;
+                A.y += pv[j].y * c;
+                A.z += pv[j].z * c;
+                A.w += pv[j].w * c;
+            }
+        }
+        const float inv = __fdiv_rn(1.0f, L);
+        const float4 y = make_float4(__fmul_rn(A.x, inv), __fmul_rn(A.y, inv), __fmul_rn(A.z, inv), __fmul_rn(A.w, inv));
+        uint32_t packed;
+        float qscale;
+        quantize_group4<GS>(y, packed, qscale);
+        const int i4 = head * 32 + lane;
+        xq_store<GS>(a.att_q, i4, packed, a.g[PH_O].KT, a.g[PH_O].G);
+        if ((i4 % (GS / 4)) == 0) a.att_s[i4 / (GS / 4)] = qscale;
+    }
+#endif
+}
+
+// MEGA_ATT_FINALIZE: the o_proj prologue is a copy of the bytes the attention step left in global memory
+template <int GS>
+__device__ __noinline__ void prologue_attn_copy(const MegaArgs &a, uint8_t *sxq, float *sxs) {
+    const int tid = threadIdx.x;
+    const int n16 = a.AH_l >> 4, ng = a.AH_l / GS;
+    for (int i = tid; i < n16; i += MEGA_CTHREADS)
+        reinterpret_cast<int4 *>(sxq)[i] = __ldcg(reinterpret_cast<const int4 *>(a.att_q) + i);
+    for (int g = tid; g < ng; g += MEGA_CTHREADS) sxs[g] = ldcg_f(a.att_s + g);
+    csync();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1035,9 +1109,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
             // QK-norm + RoPE + attention (layers.rs:339-343)
             nsplit = mega_nsplit(pos, a.n_kv_l, gridDim.x);
             if ((int)blockIdx.x < a.n_kv_l * nsplit)
-                attention_item<KVMUL>(a, l, pos, blockIdx.x % a.n_kv_l, blockIdx.x / a.n_kv_l, nsplit, scratch, pr);
+                attention_item<GS, KVMUL>(a, l, pos, blockIdx.x % a.n_kv_l, blockIdx.x / a.n_kv_l, nsplit, scratch, pr);
         } else if (kind == 2) {
-            prologue_attn_out<GS>(a, nsplit, sxq, sxs, a.g[PH_O].KT, a.g[PH_O].G); // quantize(att), qwen3.rs:152
+            if (MEGA_ATT_FINALIZE) prologue_attn_copy<GS>(a, sxq, sxs);
+            else prologue_attn_out<GS>(a, nsplit, sxq, sxs, a.g[PH_O].KT, a.g[PH_O].G); // quantize(att), qwen3.rs:152
             ph = PH_O;
         } else {
             prologue_quant<GS>(a.hb, a.H_l, sxq, sxs, a.g[PH_DN].KT, a.g[PH_DN].G); // quantize(hb), layers.rs:478
