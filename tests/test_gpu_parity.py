@@ -300,6 +300,30 @@ def test_persistent_kernel_matches_graph_path_layerwise(models, name, gs, seed):
         m.set_decode_path(1)
 
 
+def test_persistent_attention_splits_match_graph_path(models):
+    """Attention over a filled cache on both sides of every split boundary of the persistent kernel (one (kv head, split)
+    work item per CTA, 32 positions per split, merged by the o_proj prologue): same layer output as the graph path's
+    split-K kernels up to float round-off."""
+    m = models("small", 64, 3)
+    c = m.get_config()
+    kvd = c.n_kv_heads * c.head_dim
+    rng = np.random.default_rng(5)
+    m.reset()
+    for l in range(c.n_layers):
+        m.kv_write(l, 0, rng.standard_normal((c.seq_len, kvd)).astype(np.float32), rng.standard_normal((c.seq_len, kvd)).astype(np.float32))
+    try:
+        for pos in (31, 32, 33, 63, 64, 65, 130, 299, c.seq_len - 1):
+            x = rng.standard_normal(c.dim).astype(np.float32)
+            m.set_decode_path(0)
+            a = m.forward_layers(x, pos, 1, 2)
+            m.set_decode_path(1)
+            b = m.forward_layers(x, pos, 1, 2)
+            assert np.abs(a - b).max() <= 1e-4 * max(1.0, np.abs(a).max()), pos
+    finally:
+        m.set_decode_path(1)
+        m.reset()
+
+
 def test_kv_cache_rows_match_oracle(models, ckpt):
     name, gs, seed = "tiny-untied", 64, 1
     m, o = models(name, gs, seed), orc.Model(ckpt(name, gs, seed))
