@@ -113,6 +113,7 @@ struct q3_handle {
     bool tp_connected = false;
     std::vector<void *> peer_maps;
     size_t mega_smem = 0;
+    unsigned ll_base = 0;      // MEGA_LL: epoch counter of the (value, epoch) exchanges (same sequence on every TP rank)
     void *mega_fn = nullptr;
     // batched prefill (tcgen05 GEMM) state
     bool pf_ok = false;
@@ -587,7 +588,7 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
     GS_DISPATCH(gs, (h->mega_fn = mega_kernel_for<GS>(h->kv_mul)));
     if (!h->mega_fn) { h->mega_why = "no kernel for this GQA factor"; return 0; }
     const size_t slot = (size_t)MEGA_GW * (MEGA_MAX_KT + 4 * (MEGA_MAX_KT / gs));
-    h->mega_smem = MEGA_NSTAGE * slot + MEGA_SCRATCH + 192 + sizeof(MegaShared) + 64;
+    h->mega_smem = MEGA_NSTAGE * slot + MEGA_SCRATCH + (MEGA_LL ? 1024 + MEGA_MAX_KT * 4 : 192 + sizeof(MegaShared) + 64);
     CK(cudaFuncSetAttribute(h->mega_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mega_smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->mega_fn, MEGA_THREADS, h->mega_smem));
@@ -603,8 +604,11 @@ static int launch_mega(q3_handle *h, int l0, int l1, bool from_embed, bool run_h
     a.gather_logits = gather && h->tp_size > 1;
     a.bar_base = h->bar_base;
     a.xbar_base = h->xbar_base;
-    const int nbar = 5 * (l1 - l0) + (run_head ? 1 : 0);
-    const int nx = h->tp_size > 1 ? 2 * (l1 - l0) + (run_head ? 1 : 0) : 0; // exchange points use the cross-GPU counter
+    // grid barriers per launch; with MEGA_LL the o_proj / down results carry their own flags (no barrier, no cross-GPU barrier)
+    const int nbar = (MEGA_LL ? 3 : 5) * (l1 - l0) + (run_head ? 1 : 0);
+    const int nx = h->tp_size > 1 ? (MEGA_LL ? 0 : 2 * (l1 - l0)) + (run_head ? 1 : 0) : 0; // exchange points use the cross-GPU counter
+    a.ll_base = h->ll_base;
+    h->ll_base += 2u * (unsigned)(l1 - l0);
     void *params[] = {&a};
     CK(cudaLaunchCooperativeKernel(h->mega_fn, dim3(h->num_sms), dim3(MEGA_THREADS), params, h->mega_smem, h->stream));
     h->bar_base += (unsigned long long)(nbar - nx) * h->num_sms;
@@ -943,8 +947,8 @@ static int create_impl(const char *path, int ctx_len, int device, int tp_rank, i
     {   // exchange buffer (see q3_handle::xchg); logits live inside it
         auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
         size_t o = 0;
-        h->off_part[0] = o; o = al(o + (size_t)tp_size * dim * 4);
-        h->off_part[1] = o; o = al(o + (size_t)tp_size * dim * 4);
+        h->off_part[0] = o; o = al(o + (size_t)tp_size * dim * 8); // f32, or (value, epoch) words with MEGA_LL
+        h->off_part[1] = o; o = al(o + (size_t)tp_size * dim * 8);
         h->off_best = o; o = al(o + (size_t)tp_size * h->num_sms * 8);
         h->off_flags = o; o = al(o + 64 * 4);
         h->off_logits = o; o = al(o + (size_t)c.vocab_size * 4);

@@ -75,6 +75,9 @@ constexpr long long MEGA_L2_AHEAD = 0;                 // bytes per CTA the L2 p
 #ifndef MEGA_ATT_FINALIZE
 #define MEGA_ATT_FINALIZE 0 // the last attention split of a kv head merges the splits AND quantises; the o_proj prologue only copies
 #endif
+#ifndef MEGA_LL
+#define MEGA_LL 1           // o_proj / down results travel as (value, epoch) words: no grid / cross-GPU barrier after those phases
+#endif
 #ifndef MEGA_X_ONCE
 #define MEGA_X_ONCE 0       // load the activation registers once per phase when n_kt == 1
 #endif
@@ -113,6 +116,7 @@ struct MegaArgs {
     int *tokpos, *history;
     int *status;                     // != 0: a wait timed out (kernel aborts)
     int layer0, layer1, from_embed, run_head, feedback, gather_logits;
+    unsigned ll_base;                // MEGA_LL: epoch of the last (value, epoch) exchange of the previous launch (host-tracked)
     unsigned long long *prof;        // optional [grid][MEGA_PROF_EVENTS] clock64 stamps (thread 0 of each CTA)
     int dbg;                         // timing experiments only (env Q3_MEGA_DBG; results are garbage): 1 = every bulk copy reads the
                                      // same L2-resident bytes (no HBM traffic), 2 = grid barriers skipped, 4 = prologues skipped
@@ -180,6 +184,16 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(MEGA_CTHREADS) : "memory"); }
 __device__ __forceinline__ float ldcg_f(const float *p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ldcg_f4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+// (value, epoch) words: a 64-bit store is single-copy atomic, so a reader that sees the expected epoch in the upper half
+// holds the value that was written with it -- no fence on the writer, no barrier between writer and reader (the NCCL "LL"
+// idea, here for the row-parallel GEMV results, also across GPUs over NVLink peer stores).
+__device__ __forceinline__ void ll_store(unsigned long long *p, float v, unsigned epoch) {
+    const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
+    asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ void ll_load2(const unsigned long long *p, unsigned long long &x, unsigned long long &y) {
+    asm volatile("ld.relaxed.sys.global.v2.b64 {%0,%1}, [%2];" : "=l"(x), "=l"(y) : "l"(p) : "memory");
+}
 
 // contiguous split of `units` over `nctas`
 __device__ __host__ __forceinline__ void cta_share(int units, int nctas, int c, int &start, int &count) {
@@ -331,14 +345,95 @@ __device__ __forceinline__ float tile_dot(uint32_t tile, const XRegs<GS> &xr, in
 // Also merges the pending partial sums of the previous row-parallel GEMV (o_proj / down_proj:
 // x <- x + sum_r part[r], ResidualConnection layers.rs:249-259; under TP this IS the all-reduce,
 // summed in rank order so every rank computes bit-identical x) and gathers the embedding row.
+constexpr int MEGA_MAXV = (MEGA_MAX_KT + 4 * MEGA_CTHREADS - 1) / (4 * MEGA_CTHREADS); // float4 per thread of a dim <= 4096 vector
+
+// MEGA_LL: v += the tp partial vectors of the row-parallel GEMV that has just run, in rank order, each element taken as soon
+// as its word carries `epoch` (all lanes of a warp retry together; every retry is one L2 round trip).  zone: this rank's
+// landing area [tp][dim] of (value, epoch) words, written by the GEMV epilogues of all ranks.
+__device__ __forceinline__ void ll_merge(const MegaArgs &a, const unsigned long long *zone, unsigned epoch, float4 (&v)[MEGA_MAXV]) {
+    const int tid = threadIdx.x;
+    const int n4 = a.dim >> 2;
+#pragma unroll 1
+    for (int r = 0; r < a.tp_size; r++) {
+        const unsigned long long *src = zone + (size_t)r * a.dim;
+        unsigned long long w[MEGA_MAXV][4];
+        unsigned spins = 0;
+        while (true) {
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < MEGA_MAXV; k++) {
+                const int i4 = tid + k * MEGA_CTHREADS;
+                if (i4 < n4) {
+                    ll_load2(src + (size_t)i4 * 4, w[k][0], w[k][1]);
+                    ll_load2(src + (size_t)i4 * 4 + 2, w[k][2], w[k][3]);
+                    ok = ok && (unsigned)(w[k][0] >> 32) == epoch && (unsigned)(w[k][1] >> 32) == epoch &&
+                         (unsigned)(w[k][2] >> 32) == epoch && (unsigned)(w[k][3] >> 32) == epoch;
+                }
+            }
+            if (__all_sync(0xffffffffu, ok)) break;
+            if ((++spins & 255u) == 0) {
+                if (*(volatile int *)a.status) break;
+                if (spins > (1u << 22)) {
+                    atomicExch(a.status, 6);
+                    break;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < MEGA_MAXV; k++) {
+            if (tid + k * MEGA_CTHREADS < n4) {
+                v[k].x = __fadd_rn(v[k].x, __uint_as_float((unsigned)w[k][0]));
+                v[k].y = __fadd_rn(v[k].y, __uint_as_float((unsigned)w[k][1]));
+                v[k].z = __fadd_rn(v[k].z, __uint_as_float((unsigned)w[k][2]));
+                v[k].w = __fadd_rn(v[k].w, __uint_as_float((unsigned)w[k][3]));
+            }
+        }
+    }
+}
+
+// MEGA_LL adds: sx = this CTA's copy of the residual stream in shared memory (a thread always owns the same elements),
+// dense_in = take the stream from a.x[0] (teacher-forced entry), llzone/epoch = pending partial sums to merge (or null).
 template <int GS>
 __device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, bool from_embed, const float *const *parts,
-                                              int &cur, uint8_t *sxq, float *sxs, float *sred, bool write_normed, int KT, int G, Prof &pr) {
+                                              int &cur, uint8_t *sxq, float *sxs, float *sred, bool write_normed, int KT, int G, Prof &pr,
+                                              float *sx = nullptr, bool dense_in = false, const unsigned long long *llzone = nullptr,
+                                              unsigned epoch = 0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n4 = a.dim >> 2;
-    constexpr int MAXV = (MEGA_MAX_KT + 4 * MEGA_CTHREADS - 1) / (4 * MEGA_CTHREADS); // dim <= 4096 on this path
+    constexpr int MAXV = MEGA_MAXV;
     float4 v[MAXV];
     float ss = 0.0f;
+#if MEGA_LL
+#pragma unroll
+    for (int k = 0; k < MAXV; k++) {
+        const int i4 = tid + k * MEGA_CTHREADS;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i4 < n4) {
+            if (from_embed) {
+                size_t base = (size_t)a.tokpos[0] * a.dim + (size_t)i4 * 4;
+                char4 e = *reinterpret_cast<const char4 *>(a.embed_q + base);
+                float sc = a.embed_s[base / GS];
+                v[k] = make_float4((float)e.x * sc, (float)e.y * sc, (float)e.z * sc, (float)e.w * sc);
+            } else if (dense_in) {
+                v[k] = ldcg_f4(a.x[0] + (size_t)i4 * 4);
+            } else {
+                v[k] = reinterpret_cast<const float4 *>(sx)[i4];
+            }
+        }
+    }
+    if (llzone) ll_merge(a, llzone, epoch, v);
+#pragma unroll
+    for (int k = 0; k < MAXV; k++) {
+        const int i4 = tid + k * MEGA_CTHREADS;
+        if (i4 < n4) {
+            reinterpret_cast<float4 *>(sx)[i4] = v[k];
+            ss += __fmul_rn(v[k].x, v[k].x);
+            ss += __fmul_rn(v[k].y, v[k].y);
+            ss += __fmul_rn(v[k].z, v[k].z);
+            ss += __fmul_rn(v[k].w, v[k].w);
+        }
+    }
+#else
     const float *xin = a.x[cur];
     float *xout = a.x[cur ^ 1];
     const bool merge = parts != nullptr;
@@ -373,6 +468,7 @@ __device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, bo
         }
     }
     if (merge && !from_embed) cur ^= 1;
+#endif
     prof_mark(pr, 32); // x (+ partial sums) arrived
     float4 wv[MAXV]; // norm weights: issue the loads before the reduction so their latency overlaps it
 #pragma unroll
@@ -405,7 +501,7 @@ __device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, bo
             if (i4 < n4) {
                 xq_store<GS>(sxq, i4, packed, KT, G);
                 if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
-                if (write_normed && blockIdx.x == 0) reinterpret_cast<float4 *>(a.x[cur])[i4] = y;
+                if (write_normed && blockIdx.x == 0) reinterpret_cast<float4 *>(a.x[MEGA_LL ? 0 : cur])[i4] = y;
             }
         }
     }
@@ -888,6 +984,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
     uint64_t *full = reinterpret_cast<uint64_t *>(scratch + MEGA_SCRATCH); // [MEGA_GROUPS][MEGA_NSTAGE]
     uint64_t *empty = full + MEGA_GROUPS * MEGA_NSTAGE;                    // [MEGA_NSTAGE]
     MegaShared &sh = *reinterpret_cast<MegaShared *>(scratch + MEGA_SCRATCH + 192);
+    static_assert(192 + sizeof(MegaShared) <= 1024, "MegaShared outgrew its slot");
+    float *sx = reinterpret_cast<float *>(scratch + MEGA_SCRATCH + 1024); // MEGA_LL: residual stream, MEGA_MAX_KT floats
     volatile unsigned *issued = reinterpret_cast<volatile unsigned *>(scratch + MEGA_SCRATCH + 128); // [MEGA_NSTAGE] uses issued per slot
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -1083,7 +1181,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
     // Single GPU: the o_proj / down epilogue adds the residual itself (x_new[r] = x[r] + row result, the
     // same single f32 add as ResidualConnection, layers.rs:249-259) so the next prologue reads one vector
     // instead of x and the partial sums.  Under TP the partial sums of all ranks are merged in the prologue.
-    const bool fused_res = MEGA_FUSED_RES && a.tp_size == 1;
+    const bool fused_res = MEGA_FUSED_RES && !MEGA_LL && a.tp_size == 1;
 
     for (int step = 0; step < n_steps; step++) {
         const bool head = step >= n_layer_steps;
@@ -1099,12 +1197,20 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
             const float *w = kind == 0 ? a.rms_att + (size_t)l * a.dim : kind == 3 ? a.rms_ffn + (size_t)l * a.dim : a.rms_final;
             const bool emb = kind == 0 && l == L0 && a.from_embed;
             const float *const *parts = nullptr;
-            if (kind == 3 || (kind == 0 ? l > L0 : L1 > L0)) { // a row-parallel GEMV (o_proj / down) has just run
-                if (fused_res) cur ^= 1;                       // single GPU: its epilogue already wrote x + result
+            const bool pending = kind == 3 || (kind == 0 ? l > L0 : L1 > L0); // a row-parallel GEMV (o_proj / down) has just run
+            ph = kind == 0 ? PH_QKV : kind == 3 ? PH_GU : PH_HEAD;
+#if MEGA_LL
+            // epoch of the exchange being consumed: o_proj of this layer (kind 3) or down of the previous one
+            const unsigned ep_in = a.ll_base + 1 + 2 * (unsigned)((kind == 3 ? l : (kind == 0 ? l - 1 : L1 - 1)) - L0) + (kind == 3 ? 0 : 1);
+            prologue_norm<GS>(a, w, emb, parts, cur, sxq, sxs, sred, kind == 5, a.g[ph].KT, a.g[ph].G, pr, sx, !pending && !emb,
+                              pending ? reinterpret_cast<const unsigned long long *>(sh.part[kind == 3 ? 0 : 1][a.tp_rank]) : nullptr, ep_in);
+#else
+            if (pending) {
+                if (fused_res) cur ^= 1; // single GPU: its epilogue already wrote x + result
                 else parts = (const float *const *)sh.part[kind == 3 ? 0 : 1];
             }
-            ph = kind == 0 ? PH_QKV : kind == 3 ? PH_GU : PH_HEAD;
             prologue_norm<GS>(a, w, emb, parts, cur, sxq, sxs, sred, kind == 5, a.g[ph].KT, a.g[ph].G, pr);
+#endif
         } else if (kind == 1) {
             // QK-norm + RoPE + attention (layers.rs:339-343)
             nsplit = mega_nsplit(pos, a.n_kv_l, gridDim.x);
@@ -1204,7 +1310,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                                 else if (r < a.AH_l + a.KV_l) a.kraw[r - a.AH_l] = v;
                                 else vrow[r - a.AH_l - a.KV_l] = v;
                             } else if (kind == 2 || kind == 4) {
-                                if (fused_res) {
+                                if (MEGA_LL) { // (value, epoch) word into every rank's landing zone (peer stores under TP)
+                                    const unsigned ep_out = a.ll_base + 1 + 2 * (unsigned)(l - L0) + (kind == 2 ? 0 : 1);
+                                    float *const *dst = sh.part[kind == 2 ? 0 : 1];
+#pragma unroll 1
+                                    for (int p = 0; p < a.tp_size; p++)
+                                        ll_store(reinterpret_cast<unsigned long long *>(dst[p]) + (size_t)a.tp_rank * a.dim + r, v, ep_out);
+                                } else if (fused_res) {
                                     a.x[cur ^ 1][r] = __fadd_rn(j == 0 ? xres0 : xres1, v);
                                 } else { // row-parallel partial sums -> every rank's landing zone
                                     float *const *dst = sh.part[kind == 2 ? 0 : 1];
@@ -1266,7 +1378,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                 }
             }
         }
-        grid_barrier(a, bs, cross, pr);
+        if (MEGA_LL && (kind == 2 || kind == 4)) csync(); // results carry their own flags; only this CTA's warps must be done with sxq
+        else grid_barrier(a, bs, cross, pr);
         prof_mark(pr, 3 + 3 * kind);
     }
 
@@ -1297,7 +1410,22 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
         }
     } else {
         // teacher-forced layer range: materialise x = x + pending partial sums into x[0]
-        if (fused_res) {
+        if (MEGA_LL) {
+            if (blockIdx.x == 0 && L1 > L0) {
+                float4 v[MEGA_MAXV];
+#pragma unroll
+                for (int k = 0; k < MEGA_MAXV; k++) {
+                    const int i4 = tid + k * MEGA_CTHREADS;
+                    v[k] = (i4 < (a.dim >> 2)) ? reinterpret_cast<const float4 *>(sx)[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                ll_merge(a, reinterpret_cast<const unsigned long long *>(sh.part[1][a.tp_rank]), a.ll_base + 2 * (unsigned)(L1 - L0), v);
+#pragma unroll
+                for (int k = 0; k < MEGA_MAXV; k++) {
+                    const int i4 = tid + k * MEGA_CTHREADS;
+                    if (i4 < (a.dim >> 2)) reinterpret_cast<float4 *>(a.x[0])[i4] = v[k];
+                }
+            }
+        } else if (fused_res) {
             if (L1 > L0) cur ^= 1; // the last down epilogue wrote the merged stream
             if (blockIdx.x == 0 && cur != 0)
                 for (int i = tid; i < a.dim; i += MEGA_CTHREADS) a.x[0][i] = ldcg_f(a.x[cur] + i);
