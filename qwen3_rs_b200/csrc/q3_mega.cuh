@@ -187,6 +187,14 @@ __device__ __forceinline__ float4 ldcg_f4(const float *p) { return __ldcg(reinte
 // (value, epoch) words: a 64-bit store is single-copy atomic, so a reader that sees the expected epoch in the upper half
 // holds the value that was written with it -- no fence on the writer, no barrier between writer and reader (the NCCL "LL"
 // idea, here for the row-parallel GEMV results, also across GPUs over NVLink peer stores).
+// Why nothing else is needed:
+//  * the words are the ONLY data that crosses CTAs on these two edges (the residual stream lives in each CTA's shared
+//    memory); every other cross-CTA buffer (q / k / V rows, attention partials, hb, logits) is still written before and
+//    read after one of the remaining grid barriers;
+//  * epochs are unique per (launch, layer, edge) (host-tracked base, same sequence on every TP rank), zones start zeroed
+//    and epoch 0 is never used, so stale words of an earlier use never match;
+//  * a zone is rewritten one layer later; a writer can only get there after a grid barrier that every CTA (under TP: after
+//    a flagged exchange that every CTA of every rank) reaches only once it has finished reading the previous contents.
 __device__ __forceinline__ void ll_store(unsigned long long *p, float v, unsigned epoch) {
     const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
     asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
