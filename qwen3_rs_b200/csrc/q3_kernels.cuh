@@ -131,9 +131,6 @@ __device__ __forceinline__ int quant_fast(float v, float scale, float inv) {
     if (!(fabsf(fabsf(t - n) - 0.5f) >= 2e-4f)) return quant_one(v, scale); // also taken when t is inf / NaN (denormal or zero scale)
     return __float2int_rn(n);
 }
-#ifndef Q3_LEAN_QUANT
-#define Q3_LEAN_QUANT 0 // (no measurable gain: the prologues are not issue-bound) one shared exact-path branch per float4 instead of one per element
-#endif
 template <int GS>
 __device__ __forceinline__ void quantize_group4(const float4 &y, uint32_t &packed, float &scale) {
     constexpr int LANES = GS / 4;
@@ -144,22 +141,7 @@ __device__ __forceinline__ void quantize_group4(const float4 &y, uint32_t &packe
     for (int o = LANES / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     scale = __fdiv_rn(m, 127.0f);
     const float inv = __frcp_rn(scale);
-#if Q3_LEAN_QUANT
-    const float t0 = __fmul_rn(y.x, inv), t1 = __fmul_rn(y.y, inv), t2 = __fmul_rn(y.z, inv), t3 = __fmul_rn(y.w, inv);
-    const float n0 = rintf(t0), n1 = rintf(t1), n2 = rintf(t2), n3 = rintf(t3);
-    // comparisons, not fminf: an inf / NaN quotient (zero or denormal scale) must fail the test
-    const bool safe = (fabsf(fabsf(t0 - n0) - 0.5f) >= 2e-4f) & (fabsf(fabsf(t1 - n1) - 0.5f) >= 2e-4f) &
-                      (fabsf(fabsf(t2 - n2) - 0.5f) >= 2e-4f) & (fabsf(fabsf(t3 - n3) - 0.5f) >= 2e-4f);
-    if (safe) {
-        const unsigned lo = __byte_perm(__float2int_rn(n0), __float2int_rn(n1), 0x0040);
-        const unsigned hi = __byte_perm(__float2int_rn(n2), __float2int_rn(n3), 0x0040);
-        packed = __byte_perm(lo, hi, 0x5410);
-    } else {
-        packed = pack4(quant_one(y.x, scale), quant_one(y.y, scale), quant_one(y.z, scale), quant_one(y.w, scale));
-    }
-#else
     packed = pack4(quant_fast(y.x, scale, inv), quant_fast(y.y, scale, inv), quant_fast(y.z, scale, inv), quant_fast(y.w, scale, inv));
-#endif
 }
 
 // ------------------------------------------------------------------------------------------

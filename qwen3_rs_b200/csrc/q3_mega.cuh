@@ -1,13 +1,16 @@
 // q3_mega.cuh -- persistent single-launch decode step ("megakernel") for sm_100a.
 //
 // One cooperative launch per token: 148 CTAs (one per SM) walk the whole forward pass
-// (qwen3.rs:62-79, 131-176) phase by phase, separated by grid barriers.  Inside each CTA one
-// PRODUCER warp streams the CTA's share of the int8 weights HBM -> shared memory with
-// cp.async.bulk (TMA, 1-D) into a ring of mbarrier-guarded stages, and runs AHEAD of the
+// (qwen3.rs:62-79, 131-176) phase by phase.  Inside each CTA two PRODUCER threads (one per
+// consumer group) stream the CTA's share of the int8 weights HBM -> shared memory with
+// cp.async.bulk (TMA, 1-D) into a 4-stage ring of mbarrier-guarded stages, and run AHEAD of the
 // consumers across phase and layer boundaries (weights do not depend on activations), so HBM
-// stays busy while the 8 CONSUMER warps sit in a grid barrier or rebuild the quantised
-// activation vector.  Consumers keep their slice of the activation vector in registers and do
-// the int8 dot products with dp4a straight out of shared memory.
+// stays busy while the 16 CONSUMER warps (two groups owning alternate stages) wait on a
+// dependency or rebuild the quantised activation vector.  Consumers keep their slice of the
+// activation vector in registers and do the int8 dot products with dp4a out of shared memory.
+// Dependencies per layer: three grid barriers (after QKV, attention, gate/up) and two flagged
+// exchanges (o_proj / down rows travel as (value, epoch) words, see ll_store; under tensor
+// parallelism the same words are pushed into every peer GPU's memory over NVLink).
 //
 // HBM "stream" layout (built once at load by k_build_stream): for every GEMV phase, rows are
 // split contiguously over CTAs; a CTA's rows are stored in the exact order its consumers eat
@@ -30,12 +33,10 @@ constexpr int MEGA_BATCH = 4 * MEGA_GW;             // rows per batch of a row p
 constexpr int MEGA_GROUPS = 2;                      // consumer groups; stages alternate between them
 constexpr int MEGA_NCW = MEGA_GW * MEGA_GROUPS;     // 16 consumer warps
 constexpr int MEGA_CTHREADS = MEGA_NCW * 32;        // 512 consumer threads
-#ifndef MEGA_SETMAXNREG
-#define MEGA_SETMAXNREG 0   // producers sit in their own warpgroup and hand registers to the consumers (setmaxnreg)
-#endif
-// + one producer warp per consumer group; with setmaxnreg the producers fill a whole warpgroup (4 warps, 2 of them idle)
-constexpr int MEGA_THREADS = MEGA_CTHREADS + (MEGA_SETMAXNREG ? 128 : 32 * MEGA_GROUPS);
-constexpr int MEGA_REG_PRODUCER = 24, MEGA_REG_CONSUMER = 120; // per SM sub-partition: 32 * (24 + 4 * 120) <= 16384
+// + one producer warp per consumer group.  (A producer warpgroup that hands its registers to the consumers with
+// setmaxnreg was tried: ptxas cannot allocate this kernel's consumer path in 112-120 registers without spilling and
+// refuses -- see DESIGN.md.)
+constexpr int MEGA_THREADS = MEGA_CTHREADS + 32 * MEGA_GROUPS;
 #ifndef MEGA_NSTAGE_
 #define MEGA_NSTAGE_ 4
 #endif
@@ -44,8 +45,6 @@ constexpr int MEGA_MAX_KT = 4096;
 constexpr int MEGA_SCRATCH = 40960;                 // xq/xs or attention buffers
 constexpr int MEGA_MAX_TP = 8;
 constexpr int MEGA_MAX_SPLITS = ATTN_MAX_SPLITS;
-constexpr long long MEGA_L2_AHEAD = 0;                 // bytes per CTA the L2 prefetch cursor runs ahead of the ring (0 = off:
-                                                    // measured SLOWER on B200 -- the extra L2 fill traffic delays the consumers' activation loads)
 
 // tuning switches (compile-time; scripts/ab_variants.py builds and times the alternatives on one box)
 #ifndef MEGA_PREFETCH_W
@@ -1026,11 +1025,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
 
     const int L0 = a.layer0, L1 = a.layer1;
 
-#if MEGA_SETMAXNREG
-    if (warp >= MEGA_NCW) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MEGA_REG_PRODUCER));
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MEGA_REG_CONSUMER));
-#endif
-    if (warp >= MEGA_NCW + MEGA_GROUPS) return; // idle warps of the producer warpgroup
     if (warp >= MEGA_NCW) {
         // =============================== PRODUCERS ===============================
         // One producer thread per consumer group: the serial wait -> expect_tx -> bulk-copy loop of a single
@@ -1044,49 +1038,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
         Prof pr; // producer 0 logs every stage it issues (tag 64 + slot) into a second row per CTA
         pr.row = (a.prof && pw == 0) ? a.prof + (size_t)(gridDim.x + blockIdx.x) * MEGA_PROF_EVENTS : nullptr;
         pr.ev = 0;
-        // L2 prefetch cursor.  The shared-memory ring alone (5 x 34 KB per SM) cannot keep enough
-        // bytes in flight to saturate HBM at its loaded latency, and it stalls whenever the consumers
-        // sit in a barrier or a prologue.  So a second cursor walks the same byte stream
-        // MEGA_L2_AHEAD bytes in front of the ring's fill pointer -- across phase and layer
-        // boundaries, weights being static -- and pulls it into L2 with cp.async.bulk.prefetch.L2;
-        // the ring then fills from L2.
-        int pf_l = L0, pf_ph = PH_QKV; // segment the cursor is in (PH_HEAD: pf_l unused)
-        const uint8_t *pf_ptr = nullptr;
-        long long pf_left = 0;
-        long long pf_ahead = 0; // bytes the cursor is in front of the ring's fill pointer
-        bool pf_done = false;
-        auto pf_open = [&]() {
-            PhaseGeom pg = phase_geom(a, sh, pf_ph, pf_ph == PH_HEAD ? 0 : pf_l);
-            pf_ptr = pg.seg;
-            pf_left = sh.seg_len[pf_ph];
-        };
-        auto pf_next_segment = [&]() {
-            if (pf_ph == PH_HEAD) { pf_done = true; return; }
-            if (pf_ph == PH_DN) {
-                pf_l++;
-                if (pf_l < L1) pf_ph = PH_QKV;
-                else if (a.run_head) pf_ph = PH_HEAD;
-                else { pf_done = true; return; }
-            } else {
-                pf_ph++;
-            }
-            pf_open();
-        };
-        auto pf_advance = [&](long long bytes) {
-            while (bytes > 0 && !pf_done) {
-                if (pf_left == 0) { pf_next_segment(); continue; }
-                long long chunk = bytes < pf_left ? bytes : pf_left;
-                if (chunk > 65536) chunk = 65536;
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf_ptr), "r"((unsigned)chunk) : "memory");
-                pf_ptr += chunk;
-                pf_left -= chunk;
-                bytes -= chunk;
-                pf_ahead += chunk;
-            }
-        };
-        if (L1 > L0) pf_open();
-        else if (a.run_head) { pf_ph = PH_HEAD; pf_open(); }
-        else pf_done = true;
         auto push = [&](const uint8_t *src, int nr, int tile_bytes, int owner) {
             if (owner != pw) { // the other producer's stage
                 it++;
@@ -1105,17 +1056,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                     if (clock64() - t0 > 4000000000LL) { atomicExch(a.status, 4); break; }
                 }
             }
-            if (MEGA_L2_AHEAD > 0) {
-                // the cursor must at least cover what is about to be copied; beyond that it only advances
-                // while the ring is full (consumers in a barrier / prologue), i.e. exactly when HBM would idle
-                if (pf_ahead < (long long)bytes) pf_advance(bytes - pf_ahead);
-                const uint32_t par = ((it / MEGA_NSTAGE) & 1) ^ 1;
-                while (!mbar_try_wait(&empty[slot], par)) {
-                    if (pf_ahead < MEGA_L2_AHEAD && !pf_done) pf_advance(16384);
-                    else { mbar_wait(&empty[slot], par, a.status); break; }
-                }
-                pf_ahead -= bytes;
-            } else
             mbar_wait(&empty[slot], ((it / MEGA_NSTAGE) & 1) ^ 1, a.status);
             uint64_t *fb = &full[owner * MEGA_NSTAGE + slot];
             mbar_expect_tx(fb, bytes);
