@@ -1,0 +1,287 @@
+// qwen3_transformer.hpp -- C++17 host-side mirror of the reference's interface for the quantized forward
+// path, over the C ABI of libqwen3cuda (include/qwen3_cuda.h).  Header-only; link with -lqwen3cuda.
+//
+// The reference is Rust (toolchain absent from the build image), so the host layer a reference user
+// programs against is restated here with the same names, argument meaning and error behaviour:
+//
+//   reference (qwen3-inference/src)                         here
+//   ------------------------------------------------------  -----------------------------------------------
+//   models/mod.rs:13-18   trait Transformer                  qwen3::Transformer::forward / get_config
+//   models/mod.rs:40-74   TransformerBuilder                 qwen3::TransformerBuilder(path).with_ctx_length(..).build()
+//   configuration.rs:18-30 ModelConfig                       qwen3::ModelConfig
+//   sampler.rs            Sampler (xorshift64*, top-p)       qwen3::Sampler
+//   layers.rs:495-506     softmax                            qwen3::softmax
+//   generation.rs:9-48    generate                           qwen3::generate (token ids; tokenizer out of scope)
+//   generation.rs:153-162 generate_next_token                qwen3::generate_next_token
+//
+// Extensions of the drop-in: forward_argmax, decode_greedy, prefill.
+//
+// Errors: construction failures throw qwen3::Error (the reference returns anyhow::Error with the same
+// message text); forward() with an out-of-range token / pos throws (the reference panics on the slice
+// index).  There is no CPU fallback: without a CUDA device build() throws with code Q3_ECUDA.
+//
+// Bit-fidelity of Sampler/softmax with the reference needs IEEE semantics from the compiler building THIS
+// header: no -ffast-math, no FMA contraction of `a*b+c` (gcc: -ffp-contract=off), as Rust never contracts.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "qwen3_cuda.h"
+
+namespace qwen3 {
+
+class Error : public std::runtime_error {
+public:
+    Error(int code, const std::string &what) : std::runtime_error(what), code_(code) {}
+    int code() const { return code_; } // a Q3_E* value
+private:
+    int code_;
+};
+
+namespace detail {
+inline void check(int rc) {
+    if (rc != 0) {
+        const char *m = q3_last_error();
+        throw Error(rc, m ? m : "qwen3cuda error");
+    }
+}
+// f32::total_cmp ordering key (sampler.rs:58, :87)
+inline int32_t total_key(float f) {
+    int32_t b;
+    std::memcpy(&b, &f, 4);
+    return b ^ (int32_t)(((uint32_t)(b >> 31)) >> 1);
+}
+} // namespace detail
+
+// configuration.rs:18-30
+struct ModelConfig {
+    int dim = 0, hidden_dim = 0, n_layers = 0, n_heads = 0, n_kv_heads = 0, head_dim = 0, seq_len = 0, vocab_size = 0;
+    int group_size = 0;
+    bool shared_classifier = false;
+    int architecture_id = 0;
+};
+
+// The `Transformers::Qwen3` variant (models/mod.rs:20-37) resident on one GPU.  Move-only; owns the handle.
+class Transformer {
+public:
+    Transformer(const Transformer &) = delete;
+    Transformer &operator=(const Transformer &) = delete;
+    Transformer(Transformer &&o) noexcept : h_(o.h_), cfg_(o.cfg_), logits_(std::move(o.logits_)) { o.h_ = nullptr; }
+    Transformer &operator=(Transformer &&o) noexcept {
+        if (this != &o) {
+            close();
+            h_ = o.h_;
+            cfg_ = o.cfg_;
+            logits_ = std::move(o.logits_);
+            o.h_ = nullptr;
+        }
+        return *this;
+    }
+    ~Transformer() { close(); }
+
+    // Transformer::forward (models/mod.rs:15): logits of the next token, valid until the next call.
+    const std::vector<float> &forward(size_t token, size_t pos) {
+        detail::check(q3_forward(h_, (int)token, (int)pos, logits_.data()));
+        return logits_;
+    }
+    const ModelConfig &get_config() const { return cfg_; }
+
+    // ---- extensions ----
+    size_t forward_argmax(size_t token, size_t pos) { // greedy token chosen on the device (sampler.rs:57-59 tie rule)
+        int next = 0;
+        detail::check(q3_forward_argmax(h_, (int)token, (int)pos, &next));
+        return (size_t)next;
+    }
+    std::vector<int> decode_greedy(size_t first_token, size_t pos0, size_t n) { // whole greedy loop on the GPU
+        std::vector<int> out(n ? n : 1);
+        detail::check(q3_decode_greedy(h_, (int)first_token, (int)pos0, (int)n, out.data()));
+        out.resize(n);
+        return out;
+    }
+    // n prompt tokens at once (tensor-core GEMMs); cache and logits as after n sequential forwards
+    const std::vector<float> &prefill(const std::vector<int> &tokens, size_t pos0) {
+        detail::check(q3_prefill(h_, tokens.data(), (int)tokens.size(), (int)pos0, logits_.data()));
+        return logits_;
+    }
+    void reset() { detail::check(q3_reset(h_)); } // zero the KV cache
+    q3_handle *handle() { return h_; }
+
+private:
+    friend class TransformerBuilder;
+    Transformer(q3_handle *h) : h_(h) {
+        const q3_config *c = q3_get_config(h);
+        cfg_.dim = c->dim;
+        cfg_.hidden_dim = c->hidden_dim;
+        cfg_.n_layers = c->n_layers;
+        cfg_.n_heads = c->n_heads;
+        cfg_.n_kv_heads = c->n_kv_heads;
+        cfg_.head_dim = c->head_dim;
+        cfg_.seq_len = c->seq_len;
+        cfg_.vocab_size = c->vocab_size;
+        cfg_.group_size = c->group_size;
+        cfg_.shared_classifier = c->shared_classifier != 0;
+        cfg_.architecture_id = c->architecture_id;
+        logits_.resize((size_t)cfg_.vocab_size);
+    }
+    void close() {
+        if (h_) q3_destroy(h_);
+        h_ = nullptr;
+    }
+    q3_handle *h_ = nullptr;
+    ModelConfig cfg_;
+    std::vector<float> logits_;
+};
+
+// models/mod.rs:40-74
+class TransformerBuilder {
+public:
+    explicit TransformerBuilder(std::string checkpoint_path) : path_(std::move(checkpoint_path)) {}
+    TransformerBuilder &with_ctx_length(std::optional<int> ctx_length) { // None = the checkpoint's seq_len
+        ctx_ = ctx_length;
+        return *this;
+    }
+    TransformerBuilder &with_device(int device) { // addition: which GPU
+        device_ = device;
+        return *this;
+    }
+    Transformer build() const {
+        q3_handle *h = nullptr;
+        detail::check(q3_create(path_.c_str(), ctx_.value_or(0), device_, &h));
+        return Transformer(h);
+    }
+
+private:
+    std::string path_;
+    std::optional<int> ctx_;
+    int device_ = 0;
+};
+
+// layers.rs:495-506: subtract the maximum, exp, left-fold sum, multiply by 1/sum
+inline void softmax(float *x, size_t n) {
+    float mx = -INFINITY; // fold(NEG_INFINITY, f32::max): NaN-ignoring maximum
+    for (size_t i = 0; i < n; i++) mx = std::fmax(mx, x[i]);
+    float sum = 0.0f;
+    for (size_t i = 0; i < n; i++) {
+        x[i] = std::exp(x[i] - mx);
+        sum += x[i];
+    }
+    const float inv = 1.0f / sum;
+    for (size_t i = 0; i < n; i++) x[i] *= inv;
+}
+
+// sampler.rs
+class Sampler {
+public:
+    float temperature, topp;
+    uint64_t rng_state;
+
+    Sampler(size_t vocab_size, float temperature_, float topp_, uint64_t rng_seed)
+        : temperature(temperature_), topp(std::min(std::max(topp_, 0.0f), 1.0f)), rng_state(rng_seed), probindex_(vocab_size) {
+        if (vocab_size == 0) throw std::invalid_argument("Vocab size must be positive");
+        if (!(temperature_ >= 0.0f)) throw std::invalid_argument("Temperature must be non-negative");
+        if (!(topp_ >= 0.0f && topp_ <= 1.0f)) throw std::invalid_argument("Top-p must be between 0.0 and 1.0");
+    }
+
+    uint32_t random_u32() { // :44-49 xorshift64*
+        rng_state ^= rng_state >> 12;
+        rng_state ^= rng_state << 25;
+        rng_state ^= rng_state >> 27;
+        return (uint32_t)((rng_state * 0x2545F4914F6CDD1DULL) >> 32);
+    }
+    float random_f32() { return (float)(random_u32() >> 8) / 16777216.0f; } // :52-54
+
+    static size_t sample_argmax(const float *logits, size_t n) { // :57-59: max_by(total_cmp) keeps the LAST maximum
+        size_t best = 0;
+        for (size_t i = 1; i < n; i++)
+            if (detail::total_key(logits[i]) >= detail::total_key(logits[best])) best = i;
+        return best;
+    }
+    static size_t sample_mult(const float *p, size_t n, float coin) { // :62-71
+        float cdf = 0.0f;
+        for (size_t i = 0; i < n; i++) {
+            cdf += p[i];
+            if (coin < cdf) return i;
+        }
+        return n ? n - 1 : 0;
+    }
+    size_t sample_topp(const float *p, size_t n, float coin) { // :74-110
+        const float cutoff = (1.0f - topp) / (float)std::max<size_t>(n ? n - 1 : 0, 1);
+        size_t n0 = 0;
+        for (size_t i = 0; i < n; i++)
+            if (p[i] >= cutoff) probindex_[n0++] = {p[i], i};
+        // the reference's sort_unstable_by leaves the order of equal probabilities unspecified; stable here
+        std::stable_sort(probindex_.begin(), probindex_.begin() + (std::ptrdiff_t)n0,
+                         [](const ProbIndex &a, const ProbIndex &b) { return detail::total_key(b.prob) < detail::total_key(a.prob); });
+        float cumulative = 0.0f;
+        size_t last = n0 ? n0 - 1 : 0;
+        for (size_t i = 0; i < n0; i++) {
+            cumulative += probindex_[i].prob;
+            if (cumulative > topp) {
+                last = i;
+                break;
+            }
+        }
+        const float r = coin * cumulative;
+        float cdf = 0.0f;
+        for (size_t i = 0; i <= last && i < n0; i++) {
+            cdf += probindex_[i].prob;
+            if (r < cdf) return probindex_[i].index;
+        }
+        return n0 ? probindex_[last].index : 0;
+    }
+    // :116-136 (modifies `logits` in place, as the reference does)
+    size_t sample(float *logits, size_t n) {
+        if (temperature == 0.0f) return sample_argmax(logits, n);
+        for (size_t i = 0; i < n; i++) logits[i] /= temperature;
+        softmax(logits, n);
+        const float coin = random_f32();
+        if (topp <= 0.0f || topp >= 1.0f) return sample_mult(logits, n, coin);
+        return sample_topp(logits, n, coin);
+    }
+    size_t sample(std::vector<float> &logits) { return sample(logits.data(), logits.size()); }
+
+private:
+    struct ProbIndex {
+        float prob;
+        size_t index;
+    };
+    std::vector<ProbIndex> probindex_;
+};
+
+// generation.rs:153-162
+inline size_t generate_next_token(Transformer &t, Sampler &s, size_t token, size_t pos) {
+    std::vector<float> logits = t.forward(token, pos); // logits.to_vec()
+    return s.sample(logits);
+}
+
+// generation.rs:9-48 on token ids.  Prompt tokens except the last are never forwarded (:26-28); stops at
+// bos/eos (not emitted), at seq_len, or after max_new tokens (addition; 0 = no cap).
+inline std::vector<size_t> generate(Transformer &t, Sampler &s, const std::vector<size_t> &prompt_tokens, size_t max_new = 0,
+                                    long bos_token_id = -1, long eos_token_id = -1) {
+    if (prompt_tokens.empty()) throw std::invalid_argument("Please provide a prompt");
+    const size_t seq_len = (size_t)t.get_config().seq_len;
+    size_t pos = 0, token = prompt_tokens[0];
+    std::vector<size_t> out;
+    while (pos < seq_len && (max_new == 0 || out.size() < max_new)) {
+        size_t next;
+        if (pos + 1 < prompt_tokens.size()) {
+            next = prompt_tokens[pos + 1];
+        } else {
+            next = generate_next_token(t, s, token, pos);
+            if ((long)next == bos_token_id || (long)next == eos_token_id) break;
+            out.push_back(next);
+        }
+        token = next;
+        pos++;
+    }
+    return out;
+}
+
+} // namespace qwen3

@@ -1,0 +1,61 @@
+// Test driver for include/qwen3_transformer.hpp (the C++ host mirror of the reference interface).
+//   host_check sample <vocab> <temperature> <topp> <seed> <n> <logits.f32>   -> n sampled ids, then the RNG state
+//   host_check errors <missing.bin> <valid.bin>                               -> error codes of the two constructions
+//   host_check generate <ckpt.bin> <max_new> <tok> [tok ...]                  -> greedy generate() + decode_greedy() ids (needs a GPU)
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "qwen3_transformer.hpp"
+
+int main(int argc, char **argv) {
+    if (argc < 2) return 2;
+    const std::string mode = argv[1];
+    if (mode == "sample" && argc == 8) {
+        const size_t V = std::strtoul(argv[2], nullptr, 10);
+        qwen3::Sampler s(V, std::strtof(argv[3], nullptr), std::strtof(argv[4], nullptr), std::strtoull(argv[5], nullptr, 10));
+        const size_t n = std::strtoul(argv[6], nullptr, 10);
+        FILE *f = std::fopen(argv[7], "rb");
+        if (!f) return 3;
+        std::vector<float> logits(V);
+        for (size_t i = 0; i < n; i++) {
+            if (std::fread(logits.data(), 4, V, f) != V) return 4;
+            std::printf("%zu\n", s.sample(logits));
+        }
+        std::fclose(f);
+        std::printf("%llu\n", (unsigned long long)s.rng_state);
+        return 0;
+    }
+    if (mode == "errors" && argc == 4) {
+        for (int i = 2; i < 4; i++) {
+            try {
+                qwen3::Transformer t = qwen3::TransformerBuilder(argv[i]).with_ctx_length(std::nullopt).build();
+                std::printf("0 ok vocab=%d\n", t.get_config().vocab_size);
+            } catch (const qwen3::Error &e) {
+                std::printf("%d %s\n", e.code(), e.what());
+            }
+        }
+        return 0;
+    }
+    if (mode == "generate" && argc >= 5) {
+        const size_t max_new = std::strtoul(argv[3], nullptr, 10);
+        std::vector<size_t> prompt;
+        for (int i = 4; i < argc; i++) prompt.push_back(std::strtoul(argv[i], nullptr, 10));
+        qwen3::Transformer t = qwen3::TransformerBuilder(argv[2]).with_ctx_length(64).build();
+        qwen3::Sampler s((size_t)t.get_config().vocab_size, 0.0f, 0.9f, 0);
+        for (size_t tok : qwen3::generate(t, s, prompt, max_new)) std::printf("%zu ", tok);
+        std::printf("\n");
+        t.reset();
+        for (int tok : t.decode_greedy(prompt.back(), prompt.size() - 1, max_new)) std::printf("%d ", tok);
+        std::printf("\n");
+        try {
+            t.forward((size_t)t.get_config().vocab_size, 0); // out of range: the reference panics
+            std::printf("no error\n");
+        } catch (const qwen3::Error &e) {
+            std::printf("%d\n", e.code());
+        }
+        return 0;
+    }
+    return 2;
+}
