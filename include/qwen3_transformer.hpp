@@ -13,6 +13,8 @@
 //   layers.rs:495-506     softmax                            qwen3::softmax
 //   generation.rs:9-48    generate                           qwen3::generate (token ids; tokenizer out of scope)
 //   generation.rs:153-162 generate_next_token                qwen3::generate_next_token
+//   tokenizer.rs          Tokenizer (byte-level BPE)         qwen3::Tokenizer (same results; vocabulary lookups hashed)
+//   generation.rs:188-195 render_prompt                      qwen3::render_prompt
 //
 // Extensions of the drop-in: forward_argmax, decode_greedy, prefill.
 //
@@ -27,10 +29,14 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <optional>
+#include <sstream>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "qwen3_cuda.h"
@@ -282,6 +288,156 @@ inline std::vector<size_t> generate(Transformer &t, Sampler &s, const std::vecto
         pos++;
     }
     return out;
+}
+
+// tokenizer.rs: byte-level BPE tokenizer read from `<checkpoint>.tokenizer` (+ the prompt templates next to it).
+// Same token ids as the reference; its O(vocab) scans per lookup (`Iterator::position`, :145-151, :213-224) are
+// replaced by a hash map that keeps the FIRST index of every byte string, which is what `position` returns.
+class Tokenizer {
+public:
+    std::vector<std::string> vocab; // raw bytes, not necessarily valid UTF-8
+    std::vector<float> merge_scores;
+    size_t vocab_size = 0;
+    uint32_t max_token_length = 0, bos_token_id = 0, eos_token_id = 0;
+    std::string prompt_template, system_prompt_template;
+
+    // Tokenizer::new (:40-100).  A file that ends early yields empty tokens with score 0, as in the reference.
+    Tokenizer(const std::string &checkpoint_path, size_t vocab_size_, bool enable_thinking) : vocab_size(vocab_size_) {
+        const std::string path = checkpoint_path + ".tokenizer";
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw std::runtime_error("cannot open " + path);
+        if (!read_u32(f, max_token_length) || !read_u32(f, bos_token_id) || !read_u32(f, eos_token_id))
+            throw std::runtime_error("short tokenizer header in " + path);
+        vocab.reserve(vocab_size);
+        merge_scores.reserve(vocab_size);
+        for (size_t i = 0; i < vocab_size; i++) {
+            float score;
+            if (!f.read(reinterpret_cast<char *>(&score), 4)) {
+                vocab.emplace_back();
+                merge_scores.push_back(0.0f);
+                continue;
+            }
+            merge_scores.push_back(score);
+            uint32_t len;
+            if (!read_u32(f, len)) {
+                vocab.emplace_back();
+                continue;
+            }
+            std::string bytes(len, '\0');
+            if (len && !f.read(bytes.data(), len)) bytes.clear();
+            vocab.push_back(std::move(bytes));
+        }
+        for (size_t i = 0; i < vocab.size(); i++) index_.emplace(vocab[i], i); // emplace keeps the first index
+        prompt_template = load_prompt_template(checkpoint_path, false, enable_thinking);
+        system_prompt_template = load_prompt_template(checkpoint_path, true, enable_thinking);
+    }
+
+    // :122-140: the token's bytes (the reference hands back the same bytes even when they are not valid UTF-8)
+    std::string decode(size_t token) const { return token < vocab.size() ? vocab[token] : std::string(); }
+
+    // :166-238
+    std::vector<size_t> encode(const std::string &text) const {
+        std::vector<std::string> chars = split_chars(text); // text.chars()
+        std::vector<size_t> tokens;
+        size_t i = 0;
+        while (i < chars.size()) {
+            bool found_special = false;
+            if (chars[i] == "<") { // special tokens: "<...>" of at most max_token_length characters
+                const size_t limit = std::min(chars.size(), i + (size_t)max_token_length);
+                size_t end = 0;
+                bool has_end = false;
+                for (size_t j = i + 1; j < limit; j++) {
+                    if (chars[j] == ">") {
+                        end = j;
+                        has_end = true;
+                        break;
+                    }
+                }
+                if (has_end) {
+                    std::string special;
+                    for (size_t j = i; j <= end; j++) special += chars[j];
+                    auto it = index_.find(special);
+                    if (it != index_.end()) {
+                        tokens.push_back(it->second);
+                        i = end + 1;
+                        found_special = true;
+                    }
+                }
+            }
+            if (!found_special) {
+                auto it = index_.find(chars[i]);
+                if (it != index_.end()) tokens.push_back(it->second);
+                else std::fprintf(stderr, "Warning: unknown character '%s' in input, skipping.\n", chars[i].c_str());
+                i++;
+            }
+        }
+        // merge the adjacent pair whose concatenation has the highest score until none is in the vocabulary;
+        // strict `>`: among equal scores the leftmost pair wins
+        while (true) {
+            float best_score = -1e10f;
+            size_t best_id = 0, best_idx = 0;
+            bool found = false;
+            for (size_t k = 0; k + 1 < tokens.size(); k++) {
+                auto it = index_.find(vocab[tokens[k]] + vocab[tokens[k + 1]]);
+                if (it != index_.end() && merge_scores[it->second] > best_score) {
+                    best_score = merge_scores[it->second];
+                    best_id = it->second;
+                    best_idx = k;
+                    found = true;
+                }
+            }
+            if (!found) break;
+            tokens[best_idx] = best_id;
+            tokens.erase(tokens.begin() + (std::ptrdiff_t)best_idx + 1);
+        }
+        return tokens;
+    }
+
+private:
+    static bool read_u32(std::ifstream &f, uint32_t &v) { return (bool)f.read(reinterpret_cast<char *>(&v), 4); } // little endian hosts
+    // :103-119
+    static std::string load_prompt_template(const std::string &checkpoint_path, bool with_system, bool enable_thinking) {
+        const char *suffix = with_system ? (enable_thinking ? ".template.with-system-and-thinking" : ".template.with-system")
+                                         : (enable_thinking ? ".template.with-thinking" : ".template");
+        std::ifstream f(checkpoint_path + suffix, std::ios::binary);
+        if (!f) {
+            std::fprintf(stderr, "Warning: Could not load prompt template %s%s\n", checkpoint_path.c_str(), suffix);
+            return std::string();
+        }
+        std::ostringstream ss;
+        ss << f.rdbuf();
+        return ss.str();
+    }
+    // Unicode scalar values of a UTF-8 string, each kept as its UTF-8 bytes (a stray byte counts as one character)
+    static std::vector<std::string> split_chars(const std::string &s) {
+        std::vector<std::string> out;
+        for (size_t i = 0; i < s.size();) {
+            const unsigned char c = (unsigned char)s[i];
+            size_t n = c < 0x80 ? 1 : (c >> 5) == 0x6 ? 2 : (c >> 4) == 0xE ? 3 : (c >> 3) == 0x1E ? 4 : 1;
+            if (i + n > s.size()) n = 1;
+            for (size_t k = 1; k < n; k++)
+                if (((unsigned char)s[i + k] >> 6) != 0x2) {
+                    n = 1;
+                    break;
+                }
+            out.emplace_back(s, i, n);
+            i += n;
+        }
+        return out;
+    }
+    std::unordered_map<std::string, size_t> index_;
+};
+
+// generation.rs:188-195.  `str::replace` substitutes EVERY "%s" - in the system template both placeholders receive
+// "{system}\n{user}" - which is what the reference does and therefore what this does.
+inline std::string render_prompt(size_t pos, const std::optional<std::string> &system_prompt, const std::string &user_prompt,
+                                 const Tokenizer &tokenizer) {
+    auto replace_all = [](std::string tmpl, const std::string &with) {
+        for (size_t at = tmpl.find("%s"); at != std::string::npos; at = tmpl.find("%s", at + with.size())) tmpl.replace(at, 2, with);
+        return tmpl;
+    };
+    if (pos == 0 && system_prompt) return replace_all(tokenizer.system_prompt_template, *system_prompt + "\n" + user_prompt);
+    return replace_all(tokenizer.prompt_template, user_prompt);
 }
 
 } // namespace qwen3

@@ -2,6 +2,8 @@
 //   host_check sample <vocab> <temperature> <topp> <seed> <n> <logits.f32>   -> n sampled ids, then the RNG state
 //   host_check errors <missing.bin> <valid.bin>                               -> error codes of the two constructions
 //   host_check generate <ckpt.bin> <max_new> <tok> [tok ...]                  -> greedy generate() + decode_greedy() ids (needs a GPU)
+//   host_check tokenize <ckpt path> <vocab> <thinking> <texts file>           -> per line of the file: its token ids; then a summary line
+//   host_check render <ckpt path> <vocab> <thinking> <pos> <system|-> <user>  -> the rendered prompt
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -55,6 +57,39 @@ int main(int argc, char **argv) {
         } catch (const qwen3::Error &e) {
             std::printf("%d\n", e.code());
         }
+        return 0;
+    }
+    if (mode == "tokenize" && argc == 6) {
+        qwen3::Tokenizer tok(argv[2], std::strtoul(argv[3], nullptr, 10), std::atoi(argv[4]) != 0);
+        FILE *f = std::fopen(argv[5], "rb");
+        if (!f) return 3;
+        std::string all;
+        char buf[4096];
+        size_t n;
+        while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) all.append(buf, n);
+        std::fclose(f);
+        size_t start = 0;
+        while (start <= all.size()) { // one text per line (texts contain no newline)
+            size_t nl = all.find('\n', start);
+            if (nl == std::string::npos) nl = all.size();
+            std::string line = all.substr(start, nl - start);
+            std::string back;
+            for (size_t t : tok.encode(line)) {
+                std::printf("%zu ", t);
+                back += tok.decode(t);
+            }
+            std::printf("| %d\n", back == line ? 1 : 0);
+            if (nl == all.size()) break;
+            start = nl + 1;
+        }
+        std::printf("meta %u %u %u %zu\n", tok.max_token_length, tok.bos_token_id, tok.eos_token_id, tok.vocab.size());
+        return 0;
+    }
+    if (mode == "render" && argc == 8) {
+        qwen3::Tokenizer tok(argv[2], std::strtoul(argv[3], nullptr, 10), std::atoi(argv[4]) != 0);
+        std::optional<std::string> sys;
+        if (std::string(argv[6]) != "-") sys = argv[6];
+        std::fputs(qwen3::render_prompt(std::strtoul(argv[5], nullptr, 10), sys, argv[7], tok).c_str(), stdout);
         return 0;
     }
     return 2;

@@ -75,3 +75,89 @@ def test_cpp_generate_matches_the_oracle(host_check, ckpt):
     assert [int(x) for x in out[0].split()] == want      # generate() through Transformer::forward + host argmax
     assert [int(x) for x in out[1].split()] == want      # the device-resident loop
     assert out[2].strip() == "-1"                         # Q3_EINVAL for an out-of-range token
+
+
+# ---- tokenizer.rs / render_prompt --------------------------------------------------------------
+from oracle import tokenizer_ref as tr  # noqa: E402
+
+
+def _toy_tokenizer(tmp_path, thinking_templates=True):
+    # ids:     0     1     2     3     4      5       6        7              8      9      10       11
+    vocab = [b"a", b"b", b"c", b" ", b"ab", b"bc", b"abc", b"<|im_start|>", b"<", b">", b"\xc3\xa9", b"ab"]
+    score = [0.0, 0.0, 0.0, 0.0, 5.0, 7.0, 9.0, 0.0, 0.0, 0.0, 0.0, 99.0]   # id 11 duplicates "ab": never found (first position wins)
+    base = str(tmp_path / "toy.bin")
+    tr.write_tokenizer_file(base, vocab, score, max_token_length=12, bos=7, eos=3)
+    open(base + ".template", "w").write("<|im_start|>user\n%s<|im_end|>\n")
+    open(base + ".template.with-system", "w").write("S:%s|U:%s|")
+    if thinking_templates:
+        open(base + ".template.with-thinking", "w").write("T:%s")
+    return base, len(vocab)
+
+
+def test_tokenizer_known_answers(host_check, tmp_path):
+    base, V = _toy_tokenizer(tmp_path)
+    cases = {
+        "abc": [6],                   # round 1: "bc" (7.0) outranks "ab" (5.0) -> [a, bc]; round 2: a + bc = "abc" (9.0) -> [abc]
+        "ab": [4],                    # first vocabulary position of "ab" is id 4, not the duplicate 11
+        "abab": [4, 4],               # equal scores: the leftmost pair merges first
+        "<|im_start|>ab": [7, 4],     # special token found by the "<...>" scan
+        "<ab>": [8, 4, 9],            # "<ab>" is not in the vocabulary: falls back to characters
+        "a<b": [0, 8, 1],             # no closing ">"
+        "<aaaaaaaaaaaa>": [8] + [0] * 12 + [9],  # ">" is beyond max_token_length (12) characters: not even looked up
+        "aéz b": [0, 10, 3, 1],  # two-byte character found as one token; unknown "z" skipped
+        "": [],
+    }
+    ref = tr.Tokenizer(base, V, False)
+    for text, want in cases.items():
+        assert ref.encode(text) == want, text  # the literal restatement agrees with the hand-computed answers
+    texts = tmp_path / "texts.txt"
+    texts.write_bytes("\n".join(cases).encode("utf-8"))
+    out = _run(host_check, "tokenize", base, V, 0, texts)
+    for line, (text, want) in zip(out, cases.items()):
+        ids, ok = line.split("|")
+        assert [int(x) for x in ids.split()] == want, text
+        assert ok.strip() == ("0" if "z" in text else "1")  # decode(encode(text)) == text unless a character was dropped
+    assert out[len(cases)] == "meta 12 7 3 %d" % V
+
+
+def test_tokenizer_matches_the_literal_restatement_on_random_vocabularies(host_check, tmp_path):
+    rng = np.random.default_rng(11)
+    alphabet = [c.encode("utf-8") for c in "abcdefgh é中<>|"]
+    vocab = list(alphabet)
+    while len(vocab) < 120:  # grow a BPE-like vocabulary by concatenating existing tokens
+        a, b = rng.integers(0, len(vocab), 2)
+        t = vocab[a] + vocab[b]
+        if len(t) <= 10:
+            vocab.append(t)
+    vocab += [b"<|x|>", b"<y>"]
+    score = [0.0] * len(alphabet) + [float(x) for x in rng.integers(1, 40, len(vocab) - len(alphabet))]  # many ties
+    base = str(tmp_path / "rnd.bin")
+    tr.write_tokenizer_file(base, vocab, score, max_token_length=8, bos=0, eos=1)
+    ref = tr.Tokenizer(base, len(vocab), True)
+    chars = list("abcdefgh é中<>|") + ["<|x|>", "<y>", "q"]
+    lines = ["".join(rng.choice(chars, rng.integers(0, 40))) for _ in range(200)]
+    texts = tmp_path / "texts.txt"
+    texts.write_bytes("\n".join(lines).encode("utf-8"))
+    out = _run(host_check, "tokenize", base, len(vocab), 1, texts)
+    for line, text in zip(out, lines):
+        assert [int(x) for x in line.split("|")[0].split()] == ref.encode(text), text
+
+
+def test_tokenizer_short_file_and_templates(host_check, tmp_path):
+    base, V = _toy_tokenizer(tmp_path, thinking_templates=False)
+    data = open(base + ".tokenizer", "rb").read()
+    open(base + ".tokenizer", "wb").write(data[:12 + 3 * 9 + 6])  # cut inside token 3
+    ref = tr.Tokenizer(base, V, False)
+    assert ref.vocab[:3] == [b"a", b"b", b"c"] and all(v == b"" for v in ref.vocab[3:]) and len(ref.vocab) == V
+    texts = tmp_path / "t.txt"
+    texts.write_bytes(b"abc cab")
+    out = _run(host_check, "tokenize", base, V, 0, texts)
+    assert [int(x) for x in out[0].split("|")[0].split()] == ref.encode("abc cab") == [0, 1, 2, 2, 0, 1]
+    # render_prompt: every "%s" receives the same text (str::replace), system template only at pos 0
+    for pos, sys_p, user in ((0, "be brief", "hi"), (5, "be brief", "hi"), (0, None, "x%sy")):
+        got = "\n".join(_run(host_check, "render", base, V, 0, pos, sys_p if sys_p is not None else "-", user))
+        assert got == tr.render_prompt(pos, sys_p, user, ref)
+    assert tr.render_prompt(0, "be brief", "hi", ref) == "S:be brief\nhi|U:be brief\nhi|"
+    # missing template files give empty templates (tokenizer.rs:111-117)
+    assert tr.Tokenizer(base, V, True).prompt_template == ""
+    assert "\n".join(_run(host_check, "render", base, V, 1, 3, "-", "hello")) == ""
