@@ -13,6 +13,7 @@
 //   layers.rs:495-506     softmax                            qwen3::softmax
 //   generation.rs:9-48    generate                           qwen3::generate (token ids; tokenizer out of scope)
 //   generation.rs:153-162 generate_next_token                qwen3::generate_next_token
+//   generation.rs:50-151  chat (user / assistant turns)      qwen3::chat, user_turn, user_turn_prefill (one q3_prefill per turn)
 //   tokenizer.rs          Tokenizer (byte-level BPE)         qwen3::Tokenizer (same results; vocabulary lookups hashed)
 //   generation.rs:188-195 render_prompt                      qwen3::render_prompt
 //
@@ -261,16 +262,21 @@ private:
     std::vector<ProbIndex> probindex_;
 };
 
+// The loops below are generic over the transformer type, like the reference's `T: Transformer` (generation.rs:9,50):
+// anything with forward(token, pos) -> logits, get_config().seq_len and (for the prefill turn) prefill(tokens, pos0).
+
 // generation.rs:153-162
-inline size_t generate_next_token(Transformer &t, Sampler &s, size_t token, size_t pos) {
+template <class T>
+size_t generate_next_token(T &t, Sampler &s, size_t token, size_t pos) {
     std::vector<float> logits = t.forward(token, pos); // logits.to_vec()
     return s.sample(logits);
 }
 
 // generation.rs:9-48 on token ids.  Prompt tokens except the last are never forwarded (:26-28); stops at
 // bos/eos (not emitted), at seq_len, or after max_new tokens (addition; 0 = no cap).
-inline std::vector<size_t> generate(Transformer &t, Sampler &s, const std::vector<size_t> &prompt_tokens, size_t max_new = 0,
-                                    long bos_token_id = -1, long eos_token_id = -1) {
+template <class T>
+std::vector<size_t> generate(T &t, Sampler &s, const std::vector<size_t> &prompt_tokens, size_t max_new = 0, long bos_token_id = -1,
+                             long eos_token_id = -1) {
     if (prompt_tokens.empty()) throw std::invalid_argument("Please provide a prompt");
     const size_t seq_len = (size_t)t.get_config().seq_len;
     size_t pos = 0, token = prompt_tokens[0];
@@ -288,6 +294,87 @@ inline std::vector<size_t> generate(Transformer &t, Sampler &s, const std::vecto
         pos++;
     }
     return out;
+}
+
+// generation.rs:236-257 (metrics omitted)
+struct GenerationState {
+    size_t pos = 0, token = 0;
+    void reset(size_t initial_token) {
+        pos = 0;
+        token = initial_token;
+    }
+    void advance(size_t next_token) {
+        token = next_token;
+        pos++;
+    }
+};
+
+// handle_user_turn's token loop (generation.rs:116-122): one forward AND one sample per prompt token; only the last
+// sample is used, the others merely advance the sampler's RNG.
+template <class T>
+size_t user_turn(T &t, Sampler &s, GenerationState &state, const std::vector<size_t> &prompt_tokens) {
+    const size_t seq_len = (size_t)t.get_config().seq_len;
+    size_t next_token = 0;
+    for (size_t token : prompt_tokens) {
+        if (state.pos >= seq_len) break;
+        next_token = generate_next_token(t, s, token, state.pos);
+        state.advance(token);
+    }
+    return next_token;
+}
+
+// The drop-in for user_turn: the whole turn in ONE prefill call, one sample from the last token's logits, and the RNG
+// advanced by the draws the discarded samples would have made (Sampler::sample draws exactly one random_f32 per call
+// when temperature > 0, none for argmax) - a seeded run continues with the same stream.
+template <class T>
+size_t user_turn_prefill(T &t, Sampler &s, GenerationState &state, const std::vector<size_t> &prompt_tokens) {
+    const size_t seq_len = (size_t)t.get_config().seq_len;
+    const size_t n = state.pos >= seq_len ? 0 : std::min(prompt_tokens.size(), seq_len - state.pos);
+    if (n == 0) return 0;
+    std::vector<int> ids(prompt_tokens.begin(), prompt_tokens.begin() + (std::ptrdiff_t)n);
+    std::vector<float> logits = t.prefill(ids, state.pos);
+    if (s.temperature != 0.0f)
+        for (size_t i = 1; i < n; i++) s.random_u32();
+    const size_t next_token = s.sample(logits);
+    state.pos += n;
+    state.token = prompt_tokens[n - 1];
+    return next_token;
+}
+
+// chat() (generation.rs:50-93, 128-151) over already rendered + encoded user turns; returns the assistant's tokens per turn.
+// A full context window resets the position and hands the turn back to the user (:65-69).  max_new_per_turn is an
+// addition (0 = none: the reference generates until bos/eos or the window is full).
+template <class T>
+std::vector<std::vector<size_t>> chat(T &t, Sampler &s, const std::vector<std::vector<size_t>> &turns, long bos_token_id = -1,
+                                      long eos_token_id = -1, bool use_prefill = true, size_t max_new_per_turn = 0) {
+    const size_t seq_len = (size_t)t.get_config().seq_len;
+    GenerationState state;
+    std::vector<std::vector<size_t>> replies;
+    size_t turn = 0, next_token = 0;
+    bool is_user = true;
+    while (true) {
+        if (state.pos >= seq_len) {
+            state.reset(0);
+            is_user = true;
+        }
+        if (is_user) {
+            if (turn >= turns.size() || turns[turn].empty()) break;
+            next_token = use_prefill ? user_turn_prefill(t, s, state, turns[turn]) : user_turn(t, s, state, turns[turn]);
+            turn++;
+            replies.emplace_back();
+            is_user = false;
+        } else {
+            if ((long)next_token == bos_token_id || (long)next_token == eos_token_id ||
+                (max_new_per_turn != 0 && replies.back().size() >= max_new_per_turn)) {
+                is_user = true;
+                continue;
+            }
+            replies.back().push_back(next_token);
+            next_token = generate_next_token(t, s, next_token, state.pos);
+            state.advance(next_token);
+        }
+    }
+    return replies;
 }
 
 // tokenizer.rs: byte-level BPE tokenizer read from `<checkpoint>.tokenizer` (+ the prompt templates next to it).

@@ -2,6 +2,7 @@
 //   host_check sample <vocab> <temperature> <topp> <seed> <n> <logits.f32>   -> n sampled ids, then the RNG state
 //   host_check errors <missing.bin> <valid.bin>                               -> error codes of the two constructions
 //   host_check generate <ckpt.bin> <max_new> <tok> [tok ...]                  -> greedy generate() + decode_greedy() ids (needs a GPU)
+//   host_check chat <use_prefill> <temperature> <topp> <seed> <max_new>        -> replies of a 3-turn chat on a fake transformer, RNG state, #forwards
 //   host_check tokenize <ckpt path> <vocab> <thinking> <texts file>           -> per line of the file: its token ids; then a summary line
 //   host_check render <ckpt path> <vocab> <thinking> <pos> <system|-> <user>  -> the rendered prompt
 #include <cstdio>
@@ -10,6 +11,29 @@
 #include <vector>
 
 #include "qwen3_transformer.hpp"
+
+// deterministic stand-in for the transformer (host-logic checks only): logits are an integer hash of (i, token, pos)
+struct FakeTransformer {
+    struct Cfg {
+        int seq_len, vocab_size;
+    } cfg{40, 64};
+    std::vector<float> logits = std::vector<float>(64);
+    size_t forwards = 0, prefills = 0;
+    const Cfg &get_config() const { return cfg; }
+    const std::vector<float> &forward(size_t token, size_t pos) {
+        forwards++;
+        for (uint32_t i = 0; i < 64; i++)
+            logits[i] = (float)(((i * 2654435761u + (uint32_t)token * 40503u + (uint32_t)pos * 69069u) >> 8) & 1023u) / 64.0f;
+        return logits;
+    }
+    const std::vector<float> &prefill(const std::vector<int> &tokens, size_t pos0) { // q3_prefill's contract
+        prefills++;
+        const size_t before = forwards;
+        for (size_t i = 0; i < tokens.size(); i++) forward((size_t)tokens[i], pos0 + i);
+        forwards = before;
+        return logits;
+    }
+};
 
 int main(int argc, char **argv) {
     if (argc < 2) return 2;
@@ -57,6 +81,17 @@ int main(int argc, char **argv) {
         } catch (const qwen3::Error &e) {
             std::printf("%d\n", e.code());
         }
+        return 0;
+    }
+    if (mode == "chat" && argc == 7) {
+        FakeTransformer t;
+        qwen3::Sampler s(64, std::strtof(argv[3], nullptr), std::strtof(argv[4], nullptr), std::strtoull(argv[5], nullptr, 10));
+        const std::vector<std::vector<size_t>> turns = {{5, 9, 20, 31}, {7, 7, 30}, {11}};
+        for (const auto &reply : qwen3::chat(t, s, turns, -1, -1, std::atoi(argv[2]) != 0, std::strtoul(argv[6], nullptr, 10))) {
+            for (size_t tok : reply) std::printf("%zu ", tok);
+            std::printf("\n");
+        }
+        std::printf("rng %llu forwards %zu prefills %zu\n", (unsigned long long)s.rng_state, t.forwards, t.prefills);
         return 0;
     }
     if (mode == "tokenize" && argc == 6) {

@@ -161,3 +161,42 @@ def test_tokenizer_short_file_and_templates(host_check, tmp_path):
     # missing template files give empty templates (tokenizer.rs:111-117)
     assert tr.Tokenizer(base, V, True).prompt_template == ""
     assert "\n".join(_run(host_check, "render", base, V, 1, 3, "-", "hello")) == ""
+
+
+# ---- chat loop with one prefill per user turn, C++ mirror ----------------------------------------
+class _Fake:
+    """Python twin of host_check's FakeTransformer (same integer-hash logits)."""
+
+    class _Cfg:
+        seq_len, vocab_size = 40, 64
+
+    def __init__(self):
+        self.forwards = 0
+
+    def get_config(self):
+        return self._Cfg
+
+    def forward(self, token, pos):
+        self.forwards += 1
+        i = np.arange(64, dtype=np.uint64)
+        h = (i * 2654435761 + token * 40503 + pos * 69069) & 0xFFFFFFFF
+        return (((h >> 8) & 1023).astype(np.float32) / np.float32(64.0)).astype(np.float32)
+
+    def prefill(self, tokens, pos0):
+        for k, t in enumerate(tokens):
+            lg = self.forward(t, pos0 + k)
+        return lg
+
+
+@pytest.mark.parametrize("temperature,topp", [(0.0, 0.9), (0.8, 0.9), (1.0, 1.0)])
+def test_cpp_chat_one_prefill_per_turn(host_check, temperature, topp):
+    seq = _run(host_check, "chat", 0, temperature, topp, 42, 5)
+    pre = _run(host_check, "chat", 1, temperature, topp, 42, 5)
+    assert seq[:3] == pre[:3]                                   # same replies
+    assert seq[3].split()[1] == pre[3].split()[1]               # same RNG state afterwards
+    assert seq[3].split()[3:] == ["23", "prefills", "0"] and pre[3].split()[3:] == ["15", "prefills", "3"]
+    if temperature == 0.0:  # argmax path is exact across languages: the Python mirror must give the same tokens
+        from qwen3_rs_b200 import generation
+        from qwen3_rs_b200.sampler import Sampler
+        want = generation.chat(_Fake(), Sampler(64, 0.0, topp, 42), [[5, 9, 20, 31], [7, 7, 30], [11]], max_new_per_turn=5)
+        assert [[int(x) for x in l.split()] for l in pre[:3]] == want
