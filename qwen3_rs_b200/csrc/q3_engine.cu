@@ -635,7 +635,7 @@ static int mega_check(q3_handle *h, bool queued = false) {
         cudaMemset(h->d_bar, 0, 64);
         cudaMemset(h->d_flags, 0, 64 * 4);
         if (h->att_cnt) cudaMemset(h->att_cnt, 0, (size_t)h->cfg.n_layers * h->n_kv_l * 4);
-        return fail(Q3_ECUDA, "persistent decode kernel: a wait timed out (status %d: 1 grid barrier, 2 stage ring, 3 peer flag)", code);
+        return fail(Q3_ECUDA, "persistent decode kernel: a wait timed out (status %d: 1 grid barrier, 2 stage ring, 3 cross-GPU barrier, 4 producer order, 6 flagged exchange)", code);
     }
     return 0;
 }
