@@ -24,6 +24,26 @@ def test_header_declares_the_reference_trait_surface():
         assert must in syms
 
 
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: the header must compile as C99 (no C++ types in the signatures) and link from C."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc")
+    if cc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "qwen3_cuda.h"\n#include <stdio.h>\n'
+                   'int main(void) { q3_handle *h = 0; int rc = q3_create("/nonexistent.bin", 0, 0, &h);\n'
+                   '  printf("%d %s\\n", rc, q3_version()); return rc == Q3_EIO ? 0 : 1; }\n')
+    lib = T._build.build()
+    exe = tmp_path / "abi"
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", str(src), "-I", os.path.join(ROOT, "include"),
+                           "-L", os.path.dirname(lib), "-lqwen3cuda", "-Wl,-rpath," + os.path.dirname(lib), "-o", str(exe)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.split()[0] == "-2"
+
+
 def test_library_exports_every_declared_symbol():
     lib = C.CDLL(T._build.build())
     for name in declared_symbols():
