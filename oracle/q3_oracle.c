@@ -11,8 +11,10 @@
  *     PARITY UNPINNED by the reference -- qwen3-inference ships zero tests and
  *     no golden vectors for it, and the Rust toolchain is absent here so the
  *     reference itself cannot be run.  This restatement is cross-checked against
- *     an independent numpy restatement (oracle/np_forward.py) and hand-computed
- *     known answers (tests/test_oracle_*.py).
+ *     an independent numpy restatement (oracle/np_forward.py), hand-computed
+ *     known answers (tests/test_oracle_*.py) and, for the architecture as a whole,
+ *     Hugging Face's fp32 Qwen3 on the same weights (tests/test_oracle_vs_hf.py:
+ *     agreement to the int8 quantisation noise, ~3 %; one wrong convention: 40-50 %).
  *   - exporter quantizer (quantize_q80, round_half_to_even,
  *     find_optimal_group_size, header constants): PINNED against the reference's
  *     own known-answer tests, qwen3-export/tests/unit/model_exporter_test.rs.
