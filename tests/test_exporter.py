@@ -146,3 +146,34 @@ def test_golden_checkpoints_regenerate_bit_identically(ckpt, golden_meta):
         path = ckpt(meta["shape"], meta["group_size"], meta["seed"])
         assert os.path.getsize(path) == meta["bytes"]
         assert hashlib.sha256(open(path, "rb").read()).hexdigest() == meta["sha256"], key
+
+
+# ---- config loader: the reference's own tests (qwen3-export/tests/unit/config_loader_test.rs) -----------------
+_HF_CFG = {"architectures": ["Qwen3ForCausalLM"], "hidden_size": 256, "intermediate_size": 1024, "num_hidden_layers": 4,
+           "num_attention_heads": 8, "num_key_value_heads": 8, "vocab_size": 1000, "max_position_embeddings": 512,
+           "rms_norm_eps": 1e-6, "head_dim": 32, "bos_token_id": 1, "eos_token_id": 2}
+
+
+def test_load_hf_config_valid_and_defaults(tmp_path):  # config_loader_test.rs:31-51, :90-118
+    import json
+    p = tmp_path / "config.json"
+    p.write_text(json.dumps(_HF_CFG))
+    c = export.ExportConfig.from_hf_json(str(p))
+    assert (c.dim, c.hidden_dim, c.n_layers, c.n_heads, c.n_kv_heads) == (256, 1024, 4, 8, 8)
+    assert (c.vocab_size, c.max_seq_len, c.head_dim, c.bos_token_id, c.eos_token_id) == (1000, 512, 32, 1, 2)
+    assert abs(c.norm_eps - 1e-6) < 1e-9
+    d = {k: v for k, v in _HF_CFG.items() if k not in ("head_dim", "bos_token_id", "eos_token_id")}
+    p.write_text(json.dumps(d))
+    c = export.ExportConfig.from_hf_json(str(p))
+    assert (c.bos_token_id, c.eos_token_id, c.head_dim) == (0, 0, 256 // 8)
+
+
+def test_load_hf_config_errors(tmp_path):  # :54-87 (message text is serde's in the reference; the failure is what matters)
+    import json
+    p = tmp_path / "config.json"
+    p.write_text("invalid json")
+    with pytest.raises(ValueError):
+        export.ExportConfig.from_hf_json(str(p))
+    p.write_text(json.dumps({"intermediate_size": 1024, "num_hidden_layers": 4}))
+    with pytest.raises((ValueError, KeyError)):
+        export.ExportConfig.from_hf_json(str(p))
