@@ -414,7 +414,7 @@ def main():
     out = {
         "metric": "decode_tokens_per_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "scaling": "strong", "vs_baseline": None,
         "dtype": "int8 weights x int8 activations, int32 group dots, f32 accumulate", "data": "synthetic",
         "config": workload_config(args, world, "cuda"),
         "wall_ms_per_step": wall_ms / args.steps,
