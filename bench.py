@@ -402,7 +402,7 @@ def main():
             log(f"[bench] prefill measurement failed: {e}")
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         try:
             v, cores, dt = cpu_decode_tok_s(path, args.ctx, args.cpu_sample_tokens)
             cpu = {"value": v, "unit": "tok/s", "cores": cores, "kind": "port",
