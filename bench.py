@@ -224,7 +224,7 @@ def run_reference(args, rank: int, world: int):
 def workload_config(args, n_gpus: int, where: str) -> dict:
     return {
         "workload": f"{args.model} Q8_0 group_size {args.group_size}, batch-1 greedy decode, {args.tokens_per_step} tokens/step, ctx {args.ctx}",
-        "model_shape": args.model, "group_size": args.group_size, "ctx": args.ctx, "tokens_per_step": args.tokens_per_step,
+        "checkpoint": args.model, "group_size": args.group_size, "ctx": args.ctx, "tokens_per_step": args.tokens_per_step,
         "parallelism": ("tp%d" % n_gpus) if n_gpus > 1 else "single",
         "l2": "weights streamed per token (>= 0.6 GB) exceed the 126 MB L2; no explicit flush",
         "weights": "random-init, seeded, exported by qwen3_rs_b200.export (reference .bin format)",
