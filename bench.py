@@ -212,7 +212,7 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": "decode_tokens_per_s", "value": val, "unit": "tok/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "int8 weights x int8 activations, int32 group dots, f32 accumulate",
-        "data": "synthetic", "config": workload_config(args, 1, "cpu"),
+        "data": "synthetic", "config": workload_config(args), "parallelism": "host threads", "where": "cpu",
         "cpu_baseline": {"value": val, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -221,14 +221,13 @@ def run_reference(args, rank: int, world: int):
     emit(out)
 
 
-def workload_config(args, n_gpus: int, where: str) -> dict:
+def workload_config(args) -> dict:
+    """The workload only -- identical for both arms and every N (how it is run goes into top-level keys)."""
     return {
         "workload": f"{args.model} Q8_0 group_size {args.group_size}, batch-1 greedy decode, {args.tokens_per_step} tokens/step, ctx {args.ctx}",
         "checkpoint": args.model, "group_size": args.group_size, "ctx": args.ctx, "tokens_per_step": args.tokens_per_step,
-        "parallelism": ("tp%d" % n_gpus) if n_gpus > 1 else "single",
         "l2": "weights streamed per token (>= 0.6 GB) exceed the 126 MB L2; no explicit flush",
         "weights": "random-init, seeded, exported by qwen3_rs_b200.export (reference .bin format)",
-        "where": where,
     }
 
 
@@ -416,7 +415,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None,
         "dtype": "int8 weights x int8 activations, int32 group dots, f32 accumulate", "data": "synthetic",
-        "config": workload_config(args, world, "cuda"),
+        "config": workload_config(args), "parallelism": ("tp%d" % world) if world > 1 else "single", "where": "cuda",
         "wall_ms_per_step": wall_ms / args.steps,
         "e2e": {"value": e2e_val, "unit": "tok/s", "h2d_bytes_per_step": 16 * tps, "d2h_bytes_per_step": vocab * 4 * tps,
                 "tokens_timed": e2e_tokens, "path": "Transformer.forward -> host logits -> host argmax (sampler.rs)"},
