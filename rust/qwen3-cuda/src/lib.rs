@@ -21,6 +21,11 @@ extern "C" {
     fn q3_get_config(h: *const Q3Handle) -> *const Q3Config;
     fn q3_forward(h: *mut Q3Handle, token: c_int, pos: c_int, logits_host: *mut c_float) -> c_int;
     fn q3_last_error() -> *const c_char;
+    // extensions of the drop-in (no counterpart in the reference's trait)
+    fn q3_forward_argmax(h: *mut Q3Handle, token: c_int, pos: c_int, next_token: *mut c_int) -> c_int;
+    fn q3_decode_greedy(h: *mut Q3Handle, first_token: c_int, pos0: c_int, n: c_int, tokens_out: *mut c_int) -> c_int;
+    fn q3_prefill(h: *mut Q3Handle, tokens: *const c_int, n: c_int, pos0: c_int, last_logits_host: *mut c_float) -> c_int;
+    fn q3_reset(h: *mut Q3Handle) -> c_int;
 }
 
 fn last_error() -> String {
@@ -52,6 +57,44 @@ impl CudaTransformer {
         };
         let logits = vec![0.0; config.vocab_size];
         Ok(Self { handle, config, logits })
+    }
+
+    /// Greedy token chosen on the device, same tie rule as `Sampler::sample_argmax` (sampler.rs:57-59).
+    pub fn forward_argmax(&mut self, token: usize, pos: usize) -> usize {
+        let mut next: c_int = 0;
+        let rc = unsafe { q3_forward_argmax(self.handle, token as c_int, pos as c_int, &mut next) };
+        if rc != 0 {
+            panic!("{}", last_error());
+        }
+        next as usize
+    }
+
+    /// `n` greedy tokens with the loop resident on the GPU (what `generate` does at temperature 0).
+    pub fn decode_greedy(&mut self, first_token: usize, pos0: usize, n: usize) -> Vec<usize> {
+        let mut out = vec![0 as c_int; n.max(1)];
+        let rc = unsafe { q3_decode_greedy(self.handle, first_token as c_int, pos0 as c_int, n as c_int, out.as_mut_ptr()) };
+        if rc != 0 {
+            panic!("{}", last_error());
+        }
+        out.truncate(n);
+        out.into_iter().map(|t| t as usize).collect()
+    }
+
+    /// A whole prompt in one call (tensor-core GEMMs); cache and logits as after `tokens.len()` sequential forwards.
+    /// For `handle_user_turn` (generation.rs:116-122): call this once, advance the sampler's RNG by
+    /// `tokens.len() - 1` draws when temperature > 0, then sample once.
+    pub fn prefill(&mut self, tokens: &[usize], pos0: usize) -> &[f32] {
+        let ids: Vec<c_int> = tokens.iter().map(|&t| t as c_int).collect();
+        let rc = unsafe { q3_prefill(self.handle, ids.as_ptr(), ids.len() as c_int, pos0 as c_int, self.logits.as_mut_ptr()) };
+        if rc != 0 {
+            panic!("{}", last_error());
+        }
+        &self.logits
+    }
+
+    /// Zero the KV cache (a fresh `TransformerBlockBuffers`, qwen3.rs:439-440).
+    pub fn reset(&mut self) {
+        unsafe { q3_reset(self.handle) };
     }
 }
 
