@@ -12,7 +12,13 @@ the repo's exporter (no checkpoints offline), i.e. BASELINE.json configs[3] at o
             q3_bench_decode, cross-checked by a host clock around barrier+synchronize), token
             feedback on the device, weights/KV resident in HBM.
   e2e     : the same tokens/s through the reference-facing call -- Transformer.forward(token, pos)
-            -> host logits (vocab x f32 D2H every token) -> host argmax (sampler.rs semantics).
+            -> host logits (vocab x f32 D2H every token) -> host argmax (sampler.rs semantics),
+            over the SAME positions as `value` (the cache below them is refilled untimed).
+  parity  : (N=1) the GPU against the CPU oracle on the bench checkpoint itself, teacher-forced along
+            the oracle's greedy tokens: max |dlogit| and token agreement in exact (reference-order) mode
+            and in the fast mode that `value` times, plus exact mode's own tokens/s.
+  long_context / prefill_4b: BASELINE.json configs 5 and 3 (32K-token KV cache decode; Qwen3-4B
+            2048-token batched prefill + 256 decode tokens), N=1 only, skipped with --no-extras.
   roofline: the dominant kernel.  On the default path the whole decode step is ONE launch of the
             persistent kernel k_mega_decode, so algorithmic bytes per launch = bytes per token
             (weights + scales + f32 KV rows read) and the duration is the CUDA-event time per launch
@@ -58,18 +64,6 @@ def emit(obj) -> None:
 # ---------------------------------------------------------------------------------------------
 # checkpoint (synthetic, exported by the repo's exporter)
 # ---------------------------------------------------------------------------------------------
-def _quantize_q80_torch(t, gs):
-    """export.quantize_q80 evaluated with torch on the GPU (IEEE div + round-half-even, bit-identical
-    on finite inputs); used only to make multi-GB bench checkpoints quickly."""
-    import torch
-
-    g = t.reshape(-1, gs)
-    gmax = g.abs().amax(dim=1)
-    scale = torch.where(gmax > 0, gmax / 127.0, torch.ones_like(gmax))
-    q = torch.round(g / scale[:, None]).clamp_(-127, 127).to(torch.int8)
-    return q.reshape(-1).cpu().numpy(), scale.cpu().numpy(), 0.0
-
-
 def bench_checkpoint(model: str, gs: int, seed: int = 0) -> str:
     from qwen3_rs_b200 import synth
 
@@ -90,7 +84,9 @@ def bench_checkpoint(model: str, gs: int, seed: int = 0) -> str:
         cuda = False
     tmp = path + f".tmp{os.getpid()}"
     if cuda:
-        synth.export_synthetic(shape, tmp, gs, seed=seed, device="cuda", quantizer=_quantize_q80_torch)
+        # weights generated on the GPU and quantised by the library's own exporter kernel (k_quantize_q80, SURVEY 8f-3;
+        # bit-identical to export.quantize_q80: tests/test_gpu_parity.py::test_device_quantizer_makes_identical_checkpoints)
+        synth.export_synthetic(shape, tmp, gs, seed=seed, device="cuda", quantizer=synth.quantize_q80_device)
     else:
         synth.export_synthetic(shape, tmp, gs, seed=seed)
     os.replace(tmp, path)
@@ -169,19 +165,26 @@ def ncu_traffic(kind: str, workload: str = ""):
 # reference arm / cpu baseline (the oracle; the only place bench.py executes oracle/)
 # ---------------------------------------------------------------------------------------------
 def cpu_decode_tok_s(path: str, ctx: int, n_tokens: int, threads: int = 0):
+    """-> tok/s, threads, seconds, input tokens [n+1], logits [n+1][vocab] of the oracle's greedy run from token 1."""
     from oracle import binding as orc
 
     orc.set_threads(threads or os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host core
     cores = orc.max_threads()
     m = orc.Model(path, ctx)
     tok = 1
-    tok = orc.argmax(m.forward(tok, 0))  # untimed first touch (page-in of the mmap)
+    seq, logits = [tok], []
+    lg = m.forward(tok, 0)  # untimed first touch (page-in of the mmap)
+    logits.append(lg)
+    tok = orc.argmax(lg)
     t0 = time.perf_counter()
     for pos in range(1, 1 + n_tokens):
-        tok = orc.argmax(m.forward(tok, pos))
+        seq.append(tok)
+        lg = m.forward(tok, pos)
+        logits.append(lg)
+        tok = orc.argmax(lg)
     dt = time.perf_counter() - t0
     m.close()
-    return n_tokens / dt, cores, dt
+    return n_tokens / dt, cores, dt, seq, np.stack(logits)
 
 
 def run_reference(args, rank: int, world: int):
@@ -195,22 +198,29 @@ def run_reference(args, rank: int, world: int):
     orc.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host core
     cores = orc.max_threads()
     m = orc.Model(path, args.ctx)
-    tok, pos = 1, 0
-    for _ in range(args.warmup):
-        for _ in range(1):
-            tok = orc.argmax(m.forward(tok, pos))
-            pos += 1
+    # Same positions as the CUDA arm's timed region: step i starts at (warmup + i) * tokens_per_step; of each step's
+    # tokens_per_step tokens the first `tps` are run (the CPU decodes ~5 tok/s: a full 64-token step takes ~13 s).  The
+    # cache below the sampled positions holds whatever the sampled tokens wrote, zeros elsewhere -- the arithmetic per
+    # token (all weights once + attention over pos+1 rows) does not depend on the values.
+    tok = 1
+    for w in range(args.warmup):
+        tok = orc.argmax(m.forward(tok, w * args.tokens_per_step))
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for i in range(args.steps):
+        pos = (args.warmup + i) * args.tokens_per_step
         for _ in range(tps):
             tok = orc.argmax(m.forward(tok, pos))
             pos += 1
     dt = time.perf_counter() - t0
     val = args.steps * tps / dt
-    sample = f"{args.steps} steps x {tps} greedy tokens of {args.model} gs{args.group_size} (bounded sample of the {args.tokens_per_step}-token step), {cores} OpenMP threads"
+    sample = (f"{args.steps} steps x the first {tps} of each step's {args.tokens_per_step} greedy tokens of {args.model} gs{args.group_size}, at the CUDA "
+              f"arm's positions ({args.warmup * args.tokens_per_step}..); {cores} OpenMP threads")
     out = {
         "impl": "reference", "metric": "decode_tokens_per_s", "value": val, "unit": "tok/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup,
+        # time of one full tokens_per_step-token step at the measured rate (tokens_run_per_step were actually run and timed)
+        "ms_per_step": dt / args.steps * 1e3 * (args.tokens_per_step / tps), "tokens_run_per_step": tps,
+        "ms_per_sampled_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "int8 weights x int8 activations, int32 group dots, f32 accumulate",
         "data": "synthetic", "config": workload_config(args), "parallelism": "host threads", "where": "cpu",
         "cpu_baseline": {"value": val, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample},
@@ -232,6 +242,85 @@ def workload_config(args) -> dict:
 
 
 # ---------------------------------------------------------------------------------------------
+# parity on the bench checkpoint; BASELINE.json configs 5 and 3 (N=1 extras)
+# ---------------------------------------------------------------------------------------------
+def parity_block(m, oseq, ologits, args) -> dict:
+    """GPU vs the CPU oracle on the timed checkpoint, teacher-forced along the oracle's greedy tokens (so nothing but the
+    forward arithmetic is compared): exact mode (reference-order reductions; expected bit-identical) and the fast mode
+    that `value` times.  north_star: logits max-abs <= 1e-2, greedy tokens identical."""
+    from qwen3_rs_b200.sampler import argmax_last
+
+    n = len(oseq)
+    want = [int(np.argmax(ologits[p])) for p in range(n)]
+    out = {"checkpoint": f"{args.model} gs{args.group_size}", "positions": n, "reference": "oracle/q3_oracle.c (C restatement of the reference forward)",
+           "tolerance": {"logits_max_abs": 1e-2, "tokens": "identical"}}
+    for mode in ("exact", "fast"):
+        m.set_exact(mode == "exact")
+        m.reset()
+        errs, same = [], 0
+        t0 = time.perf_counter()
+        outs = [m.forward(oseq[p], p) for p in range(n)]
+        dt = time.perf_counter() - t0
+        for p in range(n):
+            errs.append(float(np.abs(outs[p] - ologits[p]).max()))
+            same += int(argmax_last(outs[p]) == argmax_last(ologits[p]))
+        out[mode] = {"max_abs_dlogit": max(errs), "max_abs_dlogit_per_position": errs, "tokens_identical": same == n, "tokens_agree": f"{same}/{n}",
+                     "tok_s": n / dt, "within_tolerance": max(errs) <= 1e-2 and same == n}
+    m.set_exact(False)
+    out["logit_scale"] = float(np.abs(ologits).max())
+    out["note"] = ("fast mode = identical int32 group dots and per-group terms, parallel f32 reduction trees; a last-ulp difference can flip one int8 "
+                   "activation, which later layers amplify on random-init weights (DESIGN.md section 2) -- exact mode is the bit-level proof")
+    return out
+
+
+def long_context_line(path, args, shape, peak, device) -> dict:
+    """BASELINE.json config 5: batch-1 decode against a 32 768-token f32 KV cache (split-K GQA attention)."""
+    from qwen3_rs_b200 import transformer as T
+
+    npos, steps = 32768, 24
+    m = T.TransformerBuilder.new(path).with_ctx_length(npos + steps + 8).with_device(device).build()
+    try:
+        c = m.get_config()
+        kvd = c.n_kv_heads * c.head_dim
+        rng = np.random.default_rng(5)
+        blk = rng.standard_normal((4096, kvd)).astype(np.float32)
+        for l in range(c.n_layers):  # synthetic N(0,1) K / V rows (SURVEY 8d), tiled
+            for p0 in range(0, npos, 4096):
+                m.kv_write(l, p0, blk, blk)
+        m.bench_decode(1, npos, 4)
+        ms = min(m.bench_decode(1, npos + 4, steps - 4) for _ in range(2)) / (steps - 4)
+        btok = shape.bytes_per_token(args.group_size, npos + steps // 2)
+        return {"workload": f"{args.model} gs{args.group_size} decode at positions {npos + 4}..{npos + steps} (32K-token f32 KV cache, synthetic N(0,1) rows)",
+                "value": 1e3 / ms, "unit": "tok/s", "us_per_token": ms * 1e3, "bytes_per_token": btok, "achieved_GBps": btok / ms / 1e6,
+                "frac_of_measured_peak": btok / ms / 1e6 / peak, "frac_of_8TBps": btok / ms / 1e6 / 8000.0}
+    finally:
+        m.close()
+
+
+def prefill_4b_line(args, device) -> dict:
+    """BASELINE.json config 3: Qwen3-4B gs64, 2048-token batched prefill (tcgen05 int8 GEMM) + 256 decode tokens."""
+    from qwen3_rs_b200 import synth, transformer as T
+
+    shape = synth.SHAPES["qwen3-4b"]
+    path = bench_checkpoint("qwen3-4b", 64)
+    m = T.TransformerBuilder.new(path).with_ctx_length(2048 + 256 + 8).with_device(device).build()
+    try:
+        Tn = 2048
+        toks = np.random.default_rng(0).integers(0, shape.vocab_size, Tn).tolist()
+        pms = m.bench_prefill(toks, 0)
+        ah, kvd = shape.n_heads * shape.head_dim, shape.n_kv_heads * shape.head_dim
+        ops = 2.0 * Tn * shape.n_layers * (2 * shape.dim * ah + 2 * shape.dim * kvd + 3 * shape.dim * shape.hidden_dim)
+        m.bench_decode(1, Tn, 8)
+        dms = m.bench_decode(1, Tn, 256) / 256
+        btok = shape.bytes_per_token(64, Tn + 128)
+        return {"workload": "qwen3-4b gs64: 2048-token prefill + 256 decode tokens", "prefill_tok_s": Tn / pms * 1e3, "prefill_ms": pms,
+                "gemm_int8_TOPS": ops / pms / 1e9, "frac_of_int8_peak_4500_TOPS_spec": ops / pms / 1e9 / 4500.0,
+                "decode_tok_s": 1e3 / dms, "decode_frac_of_8TBps": btok / dms / 1e6 / 8000.0}
+    finally:
+        m.close()
+
+
+# ---------------------------------------------------------------------------------------------
 # main arm
 # ---------------------------------------------------------------------------------------------
 def main():
@@ -244,7 +333,8 @@ def main():
     ap.add_argument("--group-size", type=int, default=64)
     ap.add_argument("--ctx", type=int, default=2048)
     ap.add_argument("--tokens-per-step", type=int, default=64)
-    ap.add_argument("--ref-tokens-per-step", type=int, default=2)
+    ap.add_argument("--ref-tokens-per-step", type=int, default=4)
+    ap.add_argument("--no-extras", action="store_true", help="skip the parity block, the 32K-context line and the 4B prefill line")
     ap.add_argument("--cpu-sample-tokens", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prefill", action="store_true")
@@ -324,12 +414,13 @@ def main():
     value = n_tok / (dev_ms / 1e3)
 
     # ---- end to end through the reference-facing call: forward -> host logits -> host argmax ----
+    # same positions as `value`: the cache below pos_start is refilled untimed, then every one of the n_tok
+    # positions is decoded through Transformer.forward
     m.reset()
-    tok, p = tok0, 0
-    for _ in range(8):
-        tok = argmax_last(m.forward(tok, p))
-        p += 1
-    e2e_tokens = min(n_tok, 256)
+    for p0 in range(0, pos_start, tps):
+        m.bench_decode(tok0, p0, min(tps, pos_start - p0))
+    tok, p = tok0, pos_start
+    e2e_tokens = n_tok
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_tokens):
@@ -348,6 +439,7 @@ def main():
             dist.destroy_process_group()
         return
 
+    vocab = m.get_config().vocab_size
     # ---- roofline ----
     peak, peak_src = measured_peak_gbs()
     mean_pos = pos_start + (n_tok - 1) / 2.0
@@ -367,13 +459,15 @@ def main():
             # over the timed region above
             roof = {"bound": "hbm", "kernel": "k_mega_decode (persistent single-launch decode step)",
                     "achieved": token_roof["achieved"], "peak": peak, "unit": "GB/s", "frac": token_roof["frac"],
-                    "traffic": ncu_traffic("mega", f"{args.model}/gs{args.group_size}/tp{world}"), "bytes_per_launch": btok, "us_per_launch": tok_ms * 1e3,
-                    "peak_source": peak_src}
+                    "traffic": ncu_traffic("mega", f"{args.model}/gs{args.group_size}/tp{world}"), "traffic_source": ncu_traffic("source", f"{args.model}/gs{args.group_size}/tp{world}"),
+                    "bytes_per_launch": btok, "us_per_launch": tok_ms * 1e3, "peak_source": peak_src}
         if world == 1:
             m.set_decode_path(0)
         for kind in (("gate_up", "down", "qkv", "o_proj", "lm_head") if world == 1 else ()):
             ms, nbytes, n = m.bench_kernel(kind, 0, reps=3 if kind != "lm_head" else 1)
             kernels[kind] = {"us": ms * 1e3, "GBps": nbytes / ms / 1e6, "bytes": nbytes}
+        if world == 1 and persistent:
+            m.set_decode_path(1)  # back on the path that was timed (parity block below)
         if not persistent:
             g = kernels["gate_up"]
             roof = {"bound": "hbm", "kernel": "gate/up int8 GEMV + SwiGLU (k_gemv<EPI_SWIGLU>)",
@@ -400,16 +494,30 @@ def main():
         except Exception as e:  # noqa: BLE001
             log(f"[bench] prefill measurement failed: {e}")
 
-    cpu = None
+    cpu, parity = None, None
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         try:
-            v, cores, dt = cpu_decode_tok_s(path, args.ctx, args.cpu_sample_tokens)
+            v, cores, dt, oseq, ologits = cpu_decode_tok_s(path, args.ctx, args.cpu_sample_tokens)
             cpu = {"value": v, "unit": "tok/s", "cores": cores, "kind": "port",
                    "sample": f"{args.cpu_sample_tokens} greedy tokens of the same {args.model} gs{args.group_size} .bin after 1 untimed token ({dt:.1f}s), all host threads"}
+            if not args.no_extras:
+                parity = parity_block(m, oseq, ologits, args)
         except Exception as e:  # noqa: BLE001
-            log(f"[bench] cpu baseline failed: {e}")
+            log(f"[bench] cpu baseline / parity failed: {e}")
 
-    vocab = m.get_config().vocab_size
+    long_ctx = prefill_4b = None
+    if world == 1 and not args.no_extras:
+        m.close()
+        m = None
+        try:
+            long_ctx = long_context_line(path, args, shape, peak, local_rank)
+        except Exception as e:  # noqa: BLE001
+            log(f"[bench] long-context line failed: {e}")
+        try:
+            prefill_4b = prefill_4b_line(args, local_rank)
+        except Exception as e:  # noqa: BLE001
+            log(f"[bench] 4B prefill line failed: {e}")
+
     out = {
         "metric": "decode_tokens_per_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -418,14 +526,16 @@ def main():
         "config": workload_config(args), "parallelism": ("tp%d" % world) if world > 1 else "single", "where": "cuda",
         "wall_ms_per_step": wall_ms / args.steps,
         "e2e": {"value": e2e_val, "unit": "tok/s", "h2d_bytes_per_step": 16 * tps, "d2h_bytes_per_step": vocab * 4 * tps,
-                "tokens_timed": e2e_tokens, "path": "Transformer.forward -> host logits -> host argmax (sampler.rs)"},
+                "tokens_timed": e2e_tokens, "positions": [pos_start, pos_start + n_tok], "path": "Transformer.forward -> host logits -> host argmax (sampler.rs)"},
         "gpu_launches": launches_per_token * n_tok,
         "launches_per_token": launches_per_token,
         "clocks": clk, "roofline": roof, "token_roofline": token_roof, "graph_path_kernels": kernels, "cpu_baseline": cpu,
         "decode_path": "persistent" if persistent else "graph", "prefill": prefill,
+        "parity": parity, "exact_mode_tok_s": (parity or {}).get("exact", {}).get("tok_s"), "long_context": long_ctx, "prefill_4b": prefill_4b,
     }
     emit(out)
-    m.close()
+    if m is not None:
+        m.close()
     if world > 1:
         dist.destroy_process_group()
 

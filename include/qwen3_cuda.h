@@ -91,6 +91,21 @@ int q3_forward_argmax(q3_handle *h, int token, int pos, int *next_token);
  * (first_token, pos0). */
 int q3_decode_greedy(q3_handle *h, int first_token, int pos0, int n, int *tokens_out);
 
+/* Extension (second half): the reference's Sampler (sampler.rs) on the device.
+ * q3_sampler_set = Sampler::new(vocab, temperature, topp, rng_seed) (:30-41; the same argument checks, Q3_EINVAL instead
+ * of the asserts).  q3_forward_sample = forward + Sampler::sample (:116-136): temperature 0 -> argmax; otherwise
+ * temperature, softmax, xorshift64* coin, multinomial or top-p -- the same RNG stream and the same decisions as the
+ * reference (order-sensitive sums are left folds, exp is glibc's; equal-probability candidates are taken in index
+ * order, which the reference's unstable sort leaves unspecified).  Only the token crosses PCIe.
+ * q3_decode_sample: n sampled steps entirely on the device.  q3_sampler_skip advances the RNG by n draws (the reference's
+ * chat loop samples and discards once per prompt token, generation.rs:116-122; no-op when greedy).  q3_sampler_state
+ * reads the RNG state back (Sampler::rng_state).  Under tensor parallelism every rank must be given the same seed. */
+int q3_sampler_set(q3_handle *h, float temperature, float topp, unsigned long long rng_seed);
+int q3_sampler_state(q3_handle *h, unsigned long long *rng_state_out);
+int q3_sampler_skip(q3_handle *h, int n_draws);
+int q3_forward_sample(q3_handle *h, int token, int pos, int *next_token);
+int q3_decode_sample(q3_handle *h, int first_token, int pos0, int n, int *tokens_out);
+
 /* Extension: batched prefill of n tokens at positions pos0..pos0+n-1.  Leaves
  * the KV cache as n sequential forwards would (within float tolerance) and returns the logits
  * of the last token (NULL to skip). */
@@ -107,7 +122,8 @@ int q3_reset(q3_handle *h);
 const float *q3_logits_device(const q3_handle *h);
 
 /* Copy KV cache rows [pos0, pos0+n) of one layer to the host, layout [n][n_kv_heads*head_dim]
- * (the reference's cache layout, layers.rs:329-331), or overwrite them from the host. */
+ * (the reference's cache layout, layers.rs:329-331), or overwrite them from the host.  A tensor-parallel handle holds
+ * only its own kv heads: rows are [n][(n_kv_heads / tp_size) * head_dim], heads tp_rank * n_kv_heads / tp_size ... */
 int q3_kv_read(q3_handle *h, int layer, int pos0, int n, float *k_host, float *v_host);
 int q3_kv_write(q3_handle *h, int layer, int pos0, int n, const float *k_host, const float *v_host);
 
@@ -127,6 +143,10 @@ int q3_set_decode_path(q3_handle *h, int path);
  * fast mode, which differs in summation order only -- logits are bit-identical to the
  * reference's.  Same kernels otherwise; slower (serial sums).  Used to demonstrate exact parity. */
 int q3_set_exact(q3_handle *h, int on);
+/* One reduction at a time (attribution of where the fast mode's int8 flips come from): bit 0 RMSNorm sum of squares,
+ * bit 1 GEMV group fold, bit 2 QK-norm sum of squares, bit 3 attention (score dots, softmax with glibc expf, value mix),
+ * bit 4 glibc expf in SwiGLU.  mask 31 == q3_set_exact(h, 1), mask 0 == fast mode. */
+int q3_set_exact_mask(q3_handle *h, int mask);
 
 /* Timing helper for benchmarks: runs `steps` decode steps at positions pos0.. (greedy token
  * feedback on the device) with inputs already resident, timed with CUDA events on the launch
@@ -139,10 +159,18 @@ int q3_bench_decode(q3_handle *h, int first_token, int pos0, int steps, float *m
  * number of launches, algorithmic bytes per launch (weights + scales, or K/V rows read). */
 int q3_bench_kernel(q3_handle *h, int kind, int pos, int reps, float *ms_out, int *launches_out,
                     double *bytes_per_launch_out);
-/* Developer aid: one decode step of the persistent kernel with per-CTA clock64 stamps at every
- * phase boundary (14 per layer: prologue / GEMV / barrier of the 5 phases; attention has no
- * prologue).  out: [num_SMs][1024] u64 SM cycles. */
-int q3_debug_profile(q3_handle *h, int token, int pos, unsigned long long *out, int *n_events_out);
+/* Developer aid: one decode step of the persistent kernel with per-CTA tagged clock64 stamps (prof_mark in
+ * csrc/q3_mega.cuh).  out: [n_rows][n_events] u64 words of (clock64 << 8 | tag); n_rows = 3 * q3_num_sms(h) (consumer
+ * thread 0, producer 0, first lane of consumer group 1 of every CTA), the last word of a row is its event count.
+ * out_words is the capacity of `out` in 64-bit words: too small -> Q3_EINVAL, nothing is written.  out == NULL with
+ * out_words == 0 only returns the two sizes.  token / pos are validated like q3_forward. */
+int q3_debug_profile(q3_handle *h, int token, int pos, unsigned long long *out, size_t out_words, int *n_rows_out,
+                     int *n_events_out);
+/* Number of SMs (= CTAs of the persistent kernel) of the handle's device. */
+int q3_num_sms(const q3_handle *h);
+/* Test hook: set the number of flagged exchanges issued so far (the persistent kernel's epochs are this counter
+ * mod 2^32 - 1, plus 1), e.g. just below the wrap.  Every tensor-parallel rank must be given the same value. */
+int q3_debug_set_epoch(q3_handle *h, unsigned long long exchanges_issued);
 /* Number of kernel launches one decode step issues on the current path. */
 int q3_launches_per_step(const q3_handle *h);
 
@@ -164,10 +192,17 @@ int q3_op_expf(int device, const float *x, int n, float *out);
  * GEMV in exact mode (same per-group terms, groups added in order). */
 int q3_op_gemm_q8(int device, const int8_t *xq, const float *xs, const int8_t *wq, const float *ws,
                   int T, int N, int K, int gs, float *out);
+/* sampler.rs:116-136 Sampler::sample with temperature > 0 on host-supplied logits (n f32): one draw on the device;
+ * *rng_state is Sampler::rng_state before the call and after it. */
+int q3_op_sample(int device, const float *logits, int n, float temperature, float topp, unsigned long long *rng_state,
+                 int *token_out);
 /* layers.rs:109-119 RMSNorm::forward */
 int q3_op_rmsnorm(int device, const float *x, const float *w, int n, float *out);
 /* qwen3-export model_exporter.rs:104-161 quantize_q80 on the device. */
 int q3_op_quantize_q80(int device, const float *w, size_t n, int gs, int8_t *q_out, float *s_out);
+/* The same kernel on DEVICE buffers (w_dev: n f32, q_dev: n int8, s_dev: n/gs f32, all on `device`): how the synthetic
+ * multi-GB bench / test checkpoints are quantised. */
+int q3_op_quantize_q80_dev(int device, const float *w_dev, size_t n, int gs, int8_t *q_dev, float *s_dev);
 
 const char *q3_last_error(void);
 const char *q3_version(void);

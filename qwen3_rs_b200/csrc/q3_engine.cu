@@ -8,6 +8,7 @@
 #include "q3_kernels.cuh"
 #include "q3_mega.cuh"
 #include "q3_prefill.cuh"
+#include "q3_sampler.cuh"
 #include <cudaTypedefs.h>
 
 #include <cuda_runtime.h>
@@ -80,9 +81,7 @@ struct q3_handle {
     float *rope = nullptr; // [seq_len][64][2]
     // activations
     float *x = nullptr, *xb = nullptr, *q = nullptr, *hb = nullptr, *logits = nullptr, *attn_part = nullptr;
-    uint8_t *att_q = nullptr;  // persistent kernel: quantised attention output (+ scales, + per kv head split counters)
-    float *att_s = nullptr;
-    unsigned *att_cnt = nullptr;
+    unsigned *att_cnt = nullptr; // persistent kernel: per (layer, kv head) arrival counters of the attention splits
     int8_t *xq = nullptr, *hq = nullptr;
     float *xs = nullptr, *hs = nullptr;
     float *kc = nullptr, *vc = nullptr; // [L][seq_len][KV_l]
@@ -92,8 +91,11 @@ struct q3_handle {
     float *h_logits = nullptr; // pinned
     int *h_small = nullptr;    // pinned scratch
     cudaStream_t stream = nullptr;
-    cudaGraphExec_t g_fwd[2] = {nullptr, nullptr}, g_greedy[2] = {nullptr, nullptr}; // [exact]
-    int exact = 0;          // 1: reference-order reductions + glibc expf (bit-level parity mode)
+    cudaGraphExec_t g_fwd[32] = {}, g_greedy[32] = {}; // [exact mask]
+    // Reference-order mask (bit-level parity mode; q3_set_exact = all bits, q3_set_exact_mask = per reduction, for the
+    // attribution of int8 flips): 1 RMSNorm sum of squares, 2 GEMV group fold, 4 QK-norm sum of squares,
+    // 8 attention (score dots, softmax with glibc expf, value mix), 16 glibc expf in SwiGLU
+    int exact = 0;
     float *att = nullptr;   // exact mode scratch [n_heads_l][seq_len] (the reference's `att`)
     int decode_path = 0;    // 0 = multi-kernel CUDA graph, 1 = persistent megakernel
     int launches_per_step = 0, graph_launches_per_step = 0;
@@ -103,7 +105,9 @@ struct q3_handle {
     MegaArgs margs{};
     unsigned long long bar_base = 0, xbar_base = 0;
     int *d_status = nullptr;  // device abort flag raised by a timed-out wait inside the kernel
-    float *x2 = nullptr, *kraw = nullptr, *part_buf[2] = {nullptr, nullptr};
+    unsigned long long *part_buf[2] = {nullptr, nullptr};            // TP landing zones [tp][dim] (inside xchg: peers write them)
+    unsigned long long *zq = nullptr, *za = nullptr, *zh = nullptr, *zr[2] = {nullptr, nullptr}; // local (payload, epoch) zones
+    bool poisoned = false;    // a wait timed out under tensor parallelism: the ranks' epoch / barrier sequences may have diverged
     unsigned long long *d_best = nullptr, *d_bar = nullptr;
     unsigned int *d_flags = nullptr;
     // everything a TP peer writes into lives in ONE allocation (one CUDA IPC handle per rank):
@@ -113,7 +117,7 @@ struct q3_handle {
     bool tp_connected = false;
     std::vector<void *> peer_maps;
     size_t mega_smem = 0;
-    unsigned ll_base = 0;      // MEGA_LL: epoch counter of the (value, epoch) exchanges (same sequence on every TP rank)
+    unsigned long long ll_count = 0; // flagged exchanges issued so far (same sequence on every TP rank); epochs derive from it
     void *mega_fn = nullptr;
     // batched prefill (tcgen05 GEMM) state
     bool pf_ok = false;
@@ -122,6 +126,10 @@ struct q3_handle {
     float *pf_x = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_hb = nullptr, *pf_xsT = nullptr, *pf_hsT = nullptr;
     int8_t *pf_xq = nullptr, *pf_hq = nullptr;
     int *pf_tokens = nullptr;
+    // device sampler (sampler.rs on the device, q3_sampler.cuh)
+    float samp_temperature = 0.0f, samp_topp = 0.9f;
+    unsigned long long *d_rng = nullptr, *d_keys = nullptr;
+    float *d_probs = nullptr;
     size_t dev_bytes = 0;
     std::vector<void *> allocs;
 };
@@ -322,11 +330,14 @@ static void launch_gemv_t(const q3_handle *h, GemvArgs a, cudaStream_t s) {
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     size_t smem = (size_t)a.K + (size_t)(a.K / GS) * 4;
-    if (h->exact) {
+    const bool expref = EPI == EPI_SWIGLU && (h->exact & 16);
+    if (h->exact & 2) {
         smem += (size_t)16 * (a.K / GS) * 4; // [8 warps][2 rows][ng] terms
-        k_gemv<GS, EPI, true><<<grid, 256, smem, s>>>(a);
+        if (expref) k_gemv<GS, EPI, true, true><<<grid, 256, smem, s>>>(a);
+        else k_gemv<GS, EPI, true, false><<<grid, 256, smem, s>>>(a);
     } else {
-        k_gemv<GS, EPI, false><<<grid, 256, smem, s>>>(a);
+        if (expref) k_gemv<GS, EPI, false, true><<<grid, 256, smem, s>>>(a);
+        else k_gemv<GS, EPI, false, false><<<grid, 256, smem, s>>>(a);
     }
 }
 template <int EPI>
@@ -335,7 +346,7 @@ static void launch_gemv(const q3_handle *h, const GemvArgs &a, cudaStream_t s) {
 }
 
 static int launch_norm_quant(const q3_handle *h, const NormQuantArgs &a, cudaStream_t s) {
-    if (h->exact) {
+    if (h->exact & 1) {
         GS_DISPATCH(h->cfg.group_size, (k_rmsnorm_quant<GS, true><<<1, 1024, (size_t)a.n * 4, s>>>(a)));
     } else {
         GS_DISPATCH(h->cfg.group_size, (k_rmsnorm_quant<GS, false><<<1, 1024, 0, s>>>(a)));
@@ -364,14 +375,14 @@ static int launch_layer(q3_handle *h, int l, bool first_from_embed, cudaStream_t
     launch_gemv<EPI_QKV>(h, g, s); n++;
     // QK-norm + RoPE (layers.rs:339-340)
     int nh = h->n_heads_l + h->n_kv_l;
-    if (h->exact)
+    if (h->exact & 4)
         k_qknorm_rope<true><<<(nh + 3) / 4, 128, 0, s>>>(h->q, kc_l, W.q_ln, W.k_ln, h->rope, d_pos, h->n_heads_l, h->n_kv_l, h->KV_l);
     else
         k_qknorm_rope<false><<<(nh + 3) / 4, 128, 0, s>>>(h->q, kc_l, W.q_ln, W.k_ln, h->rope, d_pos, h->n_heads_l, h->n_kv_l, h->KV_l);
     n++;
     // attention (layers.rs:343) + quantize (qwen3.rs:152)
     dim3 ag(h->n_kv_l, ATTN_MAX_SPLITS);
-    if (h->exact) {
+    if (h->exact & 8) {
         k_attn_ordered<<<h->n_heads_l, 128, 0, s>>>(h->q, kc_l, vc_l, h->att, h->xb, d_pos, h->KV_l, h->kv_mul, c.seq_len);
         int n4 = h->AH_l / 4, grid = (n4 + 255) / 256;
         GS_DISPATCH(gs, (k_quantize<GS><<<grid, 256, 0, s>>>(h->xb, h->AH_l, h->xq, h->xs)));
@@ -466,14 +477,16 @@ static int prepare_exact_kernels() {
     if ((rc = allow_smem(k_rmsnorm_quant<64, true>, 65536))) return rc;
     if ((rc = allow_smem(k_rmsnorm_quant<128, true>, 65536))) return rc;
 #define ALLOW_GEMV(GS)                                                      \
-    if ((rc = allow_smem(k_gemv<GS, EPI_STORE, true>, 131072))) return rc;  \
-    if ((rc = allow_smem(k_gemv<GS, EPI_QKV, true>, 131072))) return rc;    \
-    if ((rc = allow_smem(k_gemv<GS, EPI_RESID, true>, 131072))) return rc;  \
-    if ((rc = allow_smem(k_gemv<GS, EPI_SWIGLU, true>, 131072))) return rc; \
-    if ((rc = allow_smem(k_gemv<GS, EPI_STORE, false>, 98304))) return rc;  \
-    if ((rc = allow_smem(k_gemv<GS, EPI_QKV, false>, 98304))) return rc;    \
-    if ((rc = allow_smem(k_gemv<GS, EPI_RESID, false>, 98304))) return rc;  \
-    if ((rc = allow_smem(k_gemv<GS, EPI_SWIGLU, false>, 98304))) return rc;
+    if ((rc = allow_smem(k_gemv<GS, EPI_STORE, true, false>, 131072))) return rc;  \
+    if ((rc = allow_smem(k_gemv<GS, EPI_QKV, true, false>, 131072))) return rc;    \
+    if ((rc = allow_smem(k_gemv<GS, EPI_RESID, true, false>, 131072))) return rc;  \
+    if ((rc = allow_smem(k_gemv<GS, EPI_SWIGLU, true, false>, 131072))) return rc; \
+    if ((rc = allow_smem(k_gemv<GS, EPI_SWIGLU, true, true>, 131072))) return rc;  \
+    if ((rc = allow_smem(k_gemv<GS, EPI_STORE, false, false>, 98304))) return rc;  \
+    if ((rc = allow_smem(k_gemv<GS, EPI_QKV, false, false>, 98304))) return rc;    \
+    if ((rc = allow_smem(k_gemv<GS, EPI_RESID, false, false>, 98304))) return rc;  \
+    if ((rc = allow_smem(k_gemv<GS, EPI_SWIGLU, false, false>, 98304))) return rc; \
+    if ((rc = allow_smem(k_gemv<GS, EPI_SWIGLU, false, true>, 98304))) return rc;
     ALLOW_GEMV(32)
     ALLOW_GEMV(64)
     ALLOW_GEMV(128)
@@ -533,6 +546,8 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
     if (!pick_n_kt(h->AH_l, gs) || !pick_n_kt(h->H_l, gs)) { h->mega_why = "no K tiling for o_proj/down"; return 0; }
     if (h->AH_l > 16384 || h->H_l > 16384 || dim > 16384) { h->mega_why = "activation vector > 16384"; return 0; }
     if (c.vocab_size % h->tp_size) { h->mega_why = "vocab not divisible by tp"; return 0; }
+    // zone-reuse safety of the flagged exchanges (q3_mega.cuh): every CTA must own a qkv row and a gate/up unit
+    if (h->layers[0].qkv.rows < h->num_sms || h->H_l < h->num_sms) { h->mega_why = "fewer qkv rows / FFN units than SMs"; return 0; }
     MegaArgs &a = h->margs;
     a = MegaArgs{};
     a.dim = dim; a.n_layers = L; a.n_heads_l = h->n_heads_l; a.n_kv_l = h->n_kv_l; a.AH_l = h->AH_l; a.KV_l = h->KV_l;
@@ -565,9 +580,19 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
     if ((rc = upload_f32(h, &p, k_ln_all, (size_t)L * HEAD_DIM))) return rc; a.k_ln = p;
     a.rms_final = h->rms_final;
     a.embed_q = h->embed.q; a.embed_s = h->embed.s; a.rope = h->rope; a.kc = h->kc; a.vc = h->vc;
-    if ((rc = dmalloc(h, (void **)&h->x2, (size_t)dim * 4))) return rc;
-    if ((rc = dmalloc(h, (void **)&h->kraw, (size_t)h->KV_l * 4))) return rc;
-    for (int i = 0; i < 2; i++) h->part_buf[i] = (float *)(h->xchg + h->off_part[i]);
+    for (int i = 0; i < 2; i++) h->part_buf[i] = (unsigned long long *)(h->xchg + h->off_part[i]);
+    {   // local zones, zero = "never written" (epoch 0 is not a valid epoch)
+        struct { unsigned long long **p; size_t words; } zones[] = {
+            {&h->zq, (size_t)h->AH_l + 2 * (size_t)h->KV_l},
+            {&h->za, (size_t)h->AH_l / 4 + (size_t)h->AH_l / gs},
+            {&h->zh, (size_t)h->H_l},
+            {&h->zr[0], (size_t)dim},
+            {&h->zr[1], (size_t)dim}};
+        for (auto &z : zones) {
+            if ((rc = dmalloc(h, (void **)z.p, (z.words + 2) * 8))) return rc;
+            CK(cudaMemset(*z.p, 0, (z.words + 2) * 8));
+        }
+    }
     h->d_best = (unsigned long long *)(h->xchg + h->off_best);
     h->d_flags = (unsigned int *)(h->xchg + h->off_flags);
     if ((rc = dmalloc(h, (void **)&h->d_bar, 64))) return rc;
@@ -575,9 +600,9 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
     if ((rc = dmalloc(h, (void **)&h->d_status, 64))) return rc;
     CK(cudaMemset(h->d_status, 0, 64));
     int *d_status = h->d_status;
-    a.x[0] = h->x; a.x[1] = h->x2;
-    a.q = h->q; a.kraw = h->kraw; a.hb = h->hb; a.attn_part = h->attn_part;
-    a.att_q = h->att_q; a.att_s = h->att_s; a.att_cnt = h->att_cnt;
+    a.x = h->x;
+    a.zq = h->zq; a.za = h->za; a.zh = h->zh; a.zr[0] = h->zr[0]; a.zr[1] = h->zr[1];
+    a.attn_part = h->attn_part; a.att_cnt = h->att_cnt;
     a.dbg = getenv("Q3_MEGA_DBG") ? atoi(getenv("Q3_MEGA_DBG")) : 0;
     a.bar = h->d_bar; a.status = d_status; a.tokpos = h->d_tokpos; a.history = h->d_history;
     // until q3_tp_connect every "peer" slot points at this rank's own buffers
@@ -588,7 +613,7 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
     GS_DISPATCH(gs, (h->mega_fn = mega_kernel_for<GS>(h->kv_mul)));
     if (!h->mega_fn) { h->mega_why = "no kernel for this GQA factor"; return 0; }
     const size_t slot = (size_t)MEGA_GW * (MEGA_MAX_KT + 4 * (MEGA_MAX_KT / gs));
-    h->mega_smem = MEGA_NSTAGE * slot + MEGA_SCRATCH + (MEGA_LL ? 1024 + MEGA_MAX_KT * 4 : 192 + sizeof(MegaShared) + 64);
+    h->mega_smem = MEGA_NSTAGE * slot + MEGA_SCRATCH + 1024 + MEGA_MAX_KT * 4;
     CK(cudaFuncSetAttribute(h->mega_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mega_smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->mega_fn, MEGA_THREADS, h->mega_smem));
@@ -604,11 +629,12 @@ static int launch_mega(q3_handle *h, int l0, int l1, bool from_embed, bool run_h
     a.gather_logits = gather && h->tp_size > 1;
     a.bar_base = h->bar_base;
     a.xbar_base = h->xbar_base;
-    // grid barriers per launch; with MEGA_LL the o_proj / down results carry their own flags (no barrier, no cross-GPU barrier)
-    const int nbar = (MEGA_LL ? 3 : 5) * (l1 - l0) + (run_head ? 1 : 0);
-    const int nx = h->tp_size > 1 ? (MEGA_LL ? 0 : 2 * (l1 - l0)) + (run_head ? 1 : 0) : 0; // exchange points use the cross-GPU counter
-    a.ll_base = h->ll_base;
-    h->ll_base += 2u * (unsigned)(l1 - l0);
+    if (h->poisoned) return fail(Q3_ECOMM, "tensor-parallel handle is unusable after a timed-out wait (ranks may have diverged): destroy and re-create every rank");
+    // the only grid barrier of a launch is the one before the argmax (cross-GPU under TP); every per-layer edge is a flagged exchange
+    const int nbar = run_head ? 1 : 0;
+    const int nx = h->tp_size > 1 ? nbar : 0;
+    a.ll_base = (unsigned)(h->ll_count % 0xFFFFFFFFull); // epochs = (count mod 2^32 - 1) + 1: never 0, wrap-around is harmless
+    h->ll_count += (unsigned long long)MEGA_EDGES * (unsigned)(l1 - l0 + 1); // one epoch per step; + the head step's slot
     void *params[] = {&a};
     CK(cudaLaunchCooperativeKernel(h->mega_fn, dim3(h->num_sms), dim3(MEGA_THREADS), params, h->mega_smem, h->stream));
     h->bar_base += (unsigned long long)(nbar - nx) * h->num_sms;
@@ -616,6 +642,7 @@ static int launch_mega(q3_handle *h, int l0, int l1, bool from_embed, bool run_h
     return 0;
 }
 
+static int check_tok_pos(const q3_handle *h, int token, int pos);
 // did any in-kernel wait time out?  The per-token entry points queue the 4-byte status read on the stream BEFORE their
 // one synchronize (mega_status_async) so that the check costs no extra round trip; the others read it here.
 static int mega_status_async(q3_handle *h) {
@@ -629,19 +656,34 @@ static int mega_check(q3_handle *h, bool queued = false) {
     if (queued) code = h->h_small[16];
     else CK(cudaMemcpy(&code, h->d_status, 4, cudaMemcpyDeviceToHost));
     if (code) {
+        // Single GPU: all protocol state is local, reset it and the handle stays usable.  Tensor parallel: peers write into this
+        // rank's flags and keep their own counters, so a rank-local reset would pair stale counters -- fail-stop instead.
         cudaMemset(h->d_status, 0, 64);
-        h->bar_base = 0;
-        h->xbar_base = 0;
-        cudaMemset(h->d_bar, 0, 64);
-        cudaMemset(h->d_flags, 0, 64 * 4);
-        if (h->att_cnt) cudaMemset(h->att_cnt, 0, (size_t)h->cfg.n_layers * h->n_kv_l * 4);
-        return fail(Q3_ECUDA, "persistent decode kernel: a wait timed out (status %d: 1 grid barrier, 2 stage ring, 3 cross-GPU barrier, 4 producer order, 6 flagged exchange)", code);
+        if (h->tp_size > 1) {
+            h->poisoned = true;
+        } else {
+            h->bar_base = 0;
+            h->xbar_base = 0;
+            cudaMemset(h->d_bar, 0, 64);
+            cudaMemset(h->d_flags, 0, 64 * 4);
+            if (h->att_cnt) cudaMemset(h->att_cnt, 0, (size_t)h->cfg.n_layers * h->n_kv_l * 4);
+        }
+        return fail(Q3_ECUDA, "persistent decode kernel: a wait timed out (status %d: 1 grid barrier, 2 stage ring, 3 cross-GPU barrier, 4 producer order, "
+                              "6-10 flagged exchange: 6 o/down rows, 7 attention output, 8 SwiGLU outputs, 9 qkv rows, 10 TP partials)%s", code,
+                    h->tp_size > 1 ? "; tensor-parallel handle poisoned" : "");
     }
     return 0;
 }
-extern "C" int q3_debug_profile(q3_handle *h, int token, int pos, unsigned long long *out, int *n_events_out) {
-    if (!h || !out) return fail(Q3_EINVAL, "null argument");
+extern "C" int q3_debug_profile(q3_handle *h, int token, int pos, unsigned long long *out, size_t out_words, int *n_rows_out,
+                                int *n_events_out) {
+    if (!h) return fail(Q3_EINVAL, "null argument");
+    if (n_rows_out) *n_rows_out = 3 * h->num_sms;
+    if (n_events_out) *n_events_out = MEGA_PROF_EVENTS;
+    if (!out) return out_words == 0 ? Q3_OK : fail(Q3_EINVAL, "null argument"); // size query
     if (!h->mega_ok) return fail(Q3_EUNSUPPORTED, "persistent decode kernel unavailable: %s", h->mega_why.c_str());
+    if (out_words < (size_t)3 * h->num_sms * MEGA_PROF_EVENTS)
+        return fail(Q3_EINVAL, "profile buffer too small: %zu words, need %zu", out_words, (size_t)3 * h->num_sms * MEGA_PROF_EVENTS);
+    if (int rc0 = check_tok_pos(h, token, pos)) return rc0;
     CK(cudaSetDevice(h->device));
     h->h_small[0] = token; h->h_small[1] = pos; h->h_small[2] = 0; h->h_small[3] = 0;
     CK(cudaMemcpyAsync(h->d_tokpos, h->h_small, 16, cudaMemcpyHostToDevice, h->stream));
@@ -658,8 +700,15 @@ extern "C" int q3_debug_profile(q3_handle *h, int token, int pos, unsigned long 
         if (e != cudaSuccess) rc = fail(Q3_ECUDA, "profile run failed: %s", cudaGetErrorString(e));
     }
     cudaFree(d);
-    if (n_events_out) *n_events_out = MEGA_PROF_EVENTS;
+    if (!rc) rc = mega_check(h);
     return rc;
+}
+extern "C" int q3_num_sms(const q3_handle *h) { return h ? h->num_sms : 0; }
+// test hook: move the flagged-exchange epoch counter (e.g. next to the 2^32 - 1 wrap); all TP ranks must use the same value
+extern "C" int q3_debug_set_epoch(q3_handle *h, unsigned long long exchanges_issued) {
+    if (!h) return fail(Q3_EINVAL, "null handle");
+    h->ll_count = exchanges_issued;
+    return Q3_OK;
 }
 
 static inline bool use_mega(const q3_handle *h) { return h->decode_path == 1 && h->mega_ok && !h->exact; }
@@ -754,25 +803,37 @@ static int prefill_init(q3_handle *h) {
     return 0;
 }
 
+static void prefill_release(q3_handle *h) {
+    void **ps[] = {(void **)&h->pf_x, (void **)&h->pf_q, (void **)&h->pf_att, (void **)&h->pf_hb, (void **)&h->pf_xsT, (void **)&h->pf_hsT,
+                   (void **)&h->pf_xq, (void **)&h->pf_hq, (void **)&h->pf_tokens};
+    for (void **p : ps) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    h->pf_cap = 0;
+}
 static int prefill_reserve(q3_handle *h, int T) {
     const int Tpad = (T + 127) / 128 * 128;
     if (Tpad <= h->pf_cap) return 0;
     const q3_config &c = h->cfg;
     const int gs = c.group_size, dim = c.dim, AH = h->AH_l, H = h->H_l;
     const int maxd = AH > dim ? AH : dim;
-    for (void *p : {(void *)h->pf_x, (void *)h->pf_q, (void *)h->pf_att, (void *)h->pf_hb, (void *)h->pf_xsT, (void *)h->pf_hsT,
-                    (void *)h->pf_xq, (void *)h->pf_hq, (void *)h->pf_tokens})
-        if (p) cudaFree(p);
-    h->pf_cap = 0;
-    CK(cudaMalloc((void **)&h->pf_x, (size_t)Tpad * dim * 4));
-    CK(cudaMalloc((void **)&h->pf_q, (size_t)Tpad * AH * 4));
-    CK(cudaMalloc((void **)&h->pf_att, (size_t)Tpad * AH * 4));
-    CK(cudaMalloc((void **)&h->pf_hb, (size_t)Tpad * H * 4));
-    CK(cudaMalloc((void **)&h->pf_xsT, (size_t)(maxd / gs) * Tpad * 4));
-    CK(cudaMalloc((void **)&h->pf_hsT, (size_t)(H / gs) * Tpad * 4));
-    CK(cudaMalloc((void **)&h->pf_xq, (size_t)Tpad * maxd));
-    CK(cudaMalloc((void **)&h->pf_hq, (size_t)Tpad * H));
-    CK(cudaMalloc((void **)&h->pf_tokens, (size_t)Tpad * 4));
+    prefill_release(h);
+    struct { void **p; size_t bytes; } want[] = {
+        {(void **)&h->pf_x, (size_t)Tpad * dim * 4},          {(void **)&h->pf_q, (size_t)Tpad * AH * 4},
+        {(void **)&h->pf_att, (size_t)Tpad * AH * 4},         {(void **)&h->pf_hb, (size_t)Tpad * H * 4},
+        {(void **)&h->pf_xsT, (size_t)(maxd / gs) * Tpad * 4}, {(void **)&h->pf_hsT, (size_t)(H / gs) * Tpad * 4},
+        {(void **)&h->pf_xq, (size_t)Tpad * maxd},            {(void **)&h->pf_hq, (size_t)Tpad * H},
+        {(void **)&h->pf_tokens, (size_t)Tpad * 4}};
+    for (auto &w : want) {
+        cudaError_t e = cudaMalloc(w.p, w.bytes);
+        if (e != cudaSuccess) { // leave no dangling pointer behind: a later prefill / destroy must not free twice
+            *w.p = nullptr;
+            prefill_release(h);
+            cudaGetLastError();
+            return fail(Q3_ECUDA, "prefill buffers for %d tokens: %s", T, cudaGetErrorString(e));
+        }
+    }
     CK(cudaMemset(h->pf_xq, 0, (size_t)Tpad * maxd));
     CK(cudaMemset(h->pf_hq, 0, (size_t)Tpad * H));
     CK(cudaMemset(h->pf_xsT, 0, (size_t)(maxd / gs) * Tpad * 4));
@@ -962,8 +1023,6 @@ static int create_impl(const char *path, int ctx_len, int device, int tp_rank, i
     TRY(dmalloc(h, (void **)&h->hq, (size_t)h->H_l));
     TRY(dmalloc(h, (void **)&h->hs, (size_t)(h->H_l / gs + 1) * 4));
     TRY(dmalloc(h, (void **)&h->attn_part, (size_t)h->n_heads_l * ATTN_MAX_SPLITS * ATTN_PART_STRIDE * 4));
-    TRY(dmalloc(h, (void **)&h->att_q, (size_t)h->AH_l));
-    TRY(dmalloc(h, (void **)&h->att_s, (size_t)(h->AH_l / gs) * 4));
     TRY(dmalloc(h, (void **)&h->att_cnt, (size_t)h->cfg.n_layers * h->n_kv_l * 4));
     CKH(cudaMemset(h->att_cnt, 0, (size_t)h->cfg.n_layers * h->n_kv_l * 4));
     TRY(dmalloc(h, (void **)&h->att, (size_t)h->n_heads_l * c.seq_len * 4));
@@ -1064,8 +1123,8 @@ extern "C" int q3_tp_connect(q3_handle *h, const void *blobs) {
             h->peer_maps.push_back(p);
             base = (uint8_t *)p;
         }
-        a.part[0][r] = (float *)(base + h->off_part[0]);
-        a.part[1][r] = (float *)(base + h->off_part[1]);
+        a.part[0][r] = (unsigned long long *)(base + h->off_part[0]);
+        a.part[1][r] = (unsigned long long *)(base + h->off_part[1]);
         a.best[r] = (unsigned long long *)(base + h->off_best);
         a.xbar[r] = (unsigned long long *)(base + h->off_flags);
         a.logits[r] = (float *)(base + h->off_logits);
@@ -1078,13 +1137,11 @@ extern "C" void q3_destroy(q3_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (int e = 0; e < 2; e++) {
+    for (int e = 0; e < 32; e++) {
         if (h->g_fwd[e]) cudaGraphExecDestroy(h->g_fwd[e]);
         if (h->g_greedy[e]) cudaGraphExecDestroy(h->g_greedy[e]);
     }
-    for (void *p : {(void *)h->pf_x, (void *)h->pf_q, (void *)h->pf_att, (void *)h->pf_hb, (void *)h->pf_xsT, (void *)h->pf_hsT,
-                    (void *)h->pf_xq, (void *)h->pf_hq, (void *)h->pf_tokens})
-        if (p) cudaFree(p);
+    prefill_release(h);
     for (void *p : h->peer_maps) cudaIpcCloseMemHandle(p);
     for (void *p : h->allocs) cudaFree(p);
     if (h->h_logits) cudaFreeHost(h->h_logits);
@@ -1107,15 +1164,17 @@ extern "C" int q3_set_decode_path(q3_handle *h, int path) {
     return Q3_OK;
 }
 
-extern "C" int q3_set_exact(q3_handle *h, int on) {
+extern "C" int q3_set_exact_mask(q3_handle *h, int mask) {
     if (!h) return fail(Q3_EINVAL, "null handle");
+    if (mask < 0 || mask > 31) return fail(Q3_EINVAL, "exact mask %d outside 0..31", mask);
     CK(cudaSetDevice(h->device));
-    if (on && h->tp_size > 1) return fail(Q3_EUNSUPPORTED, "exact mode is single-GPU");
-    h->exact = on ? 1 : 0;
-    if (h->exact && h->cfg.dim > 16384) return fail(Q3_EUNSUPPORTED, "exact mode needs dim <= 16384");
+    if (mask && h->tp_size > 1) return fail(Q3_EUNSUPPORTED, "exact mode is single-GPU");
+    if (mask && h->cfg.dim > 16384) return fail(Q3_EUNSUPPORTED, "exact mode needs dim <= 16384");
+    h->exact = mask;
     if (!h->g_fwd[h->exact]) return build_graphs(h);
     return Q3_OK;
 }
+extern "C" int q3_set_exact(q3_handle *h, int on) { return q3_set_exact_mask(h, on ? 31 : 0); }
 
 static int check_tok_pos(const q3_handle *h, int token, int pos) {
     if (!h) return fail(Q3_EINVAL, "null handle");
@@ -1192,6 +1251,101 @@ extern "C" int q3_decode_greedy(q3_handle *h, int first_token, int pos0, int n, 
     if (tokens_out && n > 0) {
         CK(cudaMemcpyAsync(tokens_out, h->d_history, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
     }
+    CK(cudaStreamSynchronize(h->stream));
+    return mega_check(h);
+}
+
+// ------------------------------------------------------------------------------------------
+// device sampler: Sampler::new / sample (sampler.rs:30-41, 116-136)
+// ------------------------------------------------------------------------------------------
+static size_t next_pow2(size_t n) {
+    size_t p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+extern "C" int q3_sampler_set(q3_handle *h, float temperature, float topp, unsigned long long rng_seed) {
+    if (!h) return fail(Q3_EINVAL, "null handle");
+    if (!(temperature >= 0.0f)) return fail(Q3_EINVAL, "Temperature must be non-negative");
+    if (!(topp >= 0.0f && topp <= 1.0f)) return fail(Q3_EINVAL, "Top-p must be between 0.0 and 1.0");
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if (!h->d_rng) {
+        if ((rc = dmalloc(h, (void **)&h->d_rng, 64))) return rc;
+        if ((rc = dmalloc(h, (void **)&h->d_probs, (size_t)h->cfg.vocab_size * 4))) return rc;
+        if ((rc = dmalloc(h, (void **)&h->d_keys, next_pow2((size_t)h->cfg.vocab_size) * 8))) return rc;
+    }
+    h->samp_temperature = temperature;
+    h->samp_topp = topp;
+    CK(cudaMemcpyAsync(h->d_rng, &rng_seed, 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return Q3_OK;
+}
+extern "C" int q3_sampler_state(q3_handle *h, unsigned long long *rng_state_out) {
+    if (!h || !rng_state_out) return fail(Q3_EINVAL, "null argument");
+    if (!h->d_rng) return fail(Q3_EINVAL, "q3_sampler_set has not been called");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(rng_state_out, h->d_rng, 8, cudaMemcpyDeviceToHost));
+    return Q3_OK;
+}
+extern "C" int q3_sampler_skip(q3_handle *h, int n_draws) {
+    if (!h || n_draws < 0) return fail(Q3_EINVAL, "bad argument");
+    if (!h->d_rng) return fail(Q3_EINVAL, "q3_sampler_set has not been called");
+    CK(cudaSetDevice(h->device));
+    if (h->samp_temperature != 0.0f && n_draws > 0) k_rng_skip<<<1, 1, 0, h->stream>>>(h->d_rng, n_draws); // greedy draws no coin (:117-119)
+    CK(cudaGetLastError());
+    return Q3_OK;
+}
+// one decode step + sample on the device; feedback: the sampled token / next position stay on the device for the next step
+static int launch_sampled_step(q3_handle *h, bool feedback) {
+    int rc;
+    const bool greedy = h->samp_temperature == 0.0f;
+    if (use_mega(h)) {
+        if ((rc = launch_mega(h, 0, h->cfg.n_layers, true, true, greedy && feedback, !greedy))) return rc;
+    } else if (greedy) {
+        if (feedback) CK(cudaGraphLaunch(h->g_greedy[h->exact], h->stream));
+        else {
+            CK(cudaGraphLaunch(h->g_fwd[h->exact], h->stream));
+            launch_argmax(h, false, h->stream);
+        }
+    } else {
+        CK(cudaGraphLaunch(h->g_fwd[h->exact], h->stream));
+    }
+    if (!greedy) {
+        SampleArgs a{};
+        a.logits = h->logits; a.n = h->cfg.vocab_size; a.temperature = h->samp_temperature; a.topp = h->samp_topp;
+        a.rng_state = h->d_rng; a.p = h->d_probs; a.keys = h->d_keys; a.token_out = h->d_tokpos + 2;
+        if (feedback) { a.token_feedback = h->d_tokpos; a.pos_advance = h->d_tokpos + 1; a.history = h->d_history; a.history_idx = h->d_tokpos + 3; }
+        k_sample<<<1, SAMPLE_THREADS, 0, h->stream>>>(a);
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+extern "C" int q3_forward_sample(q3_handle *h, int token, int pos, int *next_token) {
+    int rc = check_tok_pos(h, token, pos);
+    if (rc) return rc;
+    if (!next_token) return fail(Q3_EINVAL, "null next_token");
+    if (!h->d_rng) return fail(Q3_EINVAL, "q3_sampler_set has not been called");
+    CK(cudaSetDevice(h->device));
+    if ((rc = set_tok_pos(h, token, pos))) return rc;
+    if ((rc = launch_sampled_step(h, false))) return rc;
+    CK(cudaMemcpyAsync(h->h_small + 8, h->d_tokpos + 2, 4, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = mega_status_async(h))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    *next_token = h->h_small[8];
+    return mega_check(h, true);
+}
+extern "C" int q3_decode_sample(q3_handle *h, int first_token, int pos0, int n, int *tokens_out) {
+    int rc = check_tok_pos(h, first_token, pos0);
+    if (rc) return rc;
+    if (n < 0 || pos0 + n > h->cfg.seq_len) return fail(Q3_EINVAL, "pos0 + n = %d exceeds seq_len %d", pos0 + n, h->cfg.seq_len);
+    if (n > h->history_cap) return fail(Q3_EINVAL, "n too large");
+    if (!h->d_rng) return fail(Q3_EINVAL, "q3_sampler_set has not been called");
+    CK(cudaSetDevice(h->device));
+    if ((rc = set_tok_pos(h, first_token, pos0))) return rc;
+    for (int i = 0; i < n; i++)
+        if ((rc = launch_sampled_step(h, true))) return rc;
+    if (tokens_out && n > 0) CK(cudaMemcpyAsync(tokens_out, h->d_history, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return mega_check(h);
 }
@@ -1493,7 +1647,7 @@ extern "C" int q3_op_matmul(int device, const int8_t *xq, const float *xs, const
     cudaGetDeviceProperties(&prop, device);
     fake.num_sms = prop.multiProcessorCount;
     fake.cfg.group_size = gs;
-    fake.exact = exact ? 1 : 0;
+    fake.exact = exact ? 31 : 0;
     if ((rc = prepare_exact_kernels())) return rc;
     launch_gemv<EPI_STORE>(&fake, a, 0);
     CK(cudaGetLastError());
@@ -1533,6 +1687,29 @@ extern "C" int q3_op_gemm_q8(int device, const int8_t *xq, const float *xs, cons
     return Q3_OK;
 }
 
+// Sampler::sample on host-supplied logits (operator-level parity entry): one draw, RNG state in / out
+extern "C" int q3_op_sample(int device, const float *logits, int n, float temperature, float topp, unsigned long long *rng_state,
+                            int *token_out) {
+    CK(cudaSetDevice(device));
+    if (!logits || !rng_state || !token_out || n <= 0) return fail(Q3_EINVAL, "bad argument");
+    if (!(temperature > 0.0f)) return fail(Q3_EINVAL, "temperature must be positive (0 = greedy: use the argmax path)");
+    DevBuf dl, dp, dk, dr, dt;
+    int rc;
+    if ((rc = dl.alloc((size_t)n * 4)) || (rc = dp.alloc((size_t)n * 4)) || (rc = dk.alloc(next_pow2((size_t)n) * 8)) || (rc = dr.alloc(8)) ||
+        (rc = dt.alloc(4)))
+        return rc;
+    CK(cudaMemcpy(dl.p, logits, (size_t)n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dr.p, rng_state, 8, cudaMemcpyHostToDevice));
+    SampleArgs a{};
+    a.logits = dl.as<float>(); a.n = n; a.temperature = temperature; a.topp = topp < 0.f ? 0.f : (topp > 1.f ? 1.f : topp);
+    a.rng_state = dr.as<unsigned long long>(); a.p = dp.as<float>(); a.keys = dk.as<unsigned long long>(); a.token_out = dt.as<int>();
+    k_sample<<<1, SAMPLE_THREADS>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(rng_state, dr.p, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(token_out, dt.p, 4, cudaMemcpyDeviceToHost));
+    return Q3_OK;
+}
+
 extern "C" int q3_op_rmsnorm(int device, const float *x, const float *w, int n, float *out) {
     CK(cudaSetDevice(device));
     if (n <= 0) return fail(Q3_EINVAL, "n must be positive");
@@ -1544,6 +1721,21 @@ extern "C" int q3_op_rmsnorm(int device, const float *x, const float *w, int n, 
     k_rmsnorm<<<1, 1024>>>(dx.as<float>(), dw.as<float>(), dout.as<float>(), n);
     CK(cudaGetLastError());
     CK(cudaMemcpy(out, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return Q3_OK;
+}
+
+// same kernel on buffers that already live on the device (bench / fixture generation of multi-GB checkpoints)
+extern "C" int q3_op_quantize_q80_dev(int device, const float *w_dev, size_t n, int gs, int8_t *q_dev, float *s_dev) {
+    int rc = op_prologue(device, gs);
+    if (rc) return rc;
+    if (n % gs) return fail(Q3_EINVAL, "Weight length is not a multiple of group_size");
+    if (n == 0) return Q3_OK;
+    if (!w_dev || !q_dev || !s_dev) return fail(Q3_EINVAL, "null argument");
+    size_t blocks = (n / 4 + 255) / 256;
+    int grid = (int)(blocks > 148 * 16 ? 148 * 16 : blocks);
+    GS_DISPATCH(gs, (k_quantize_q80<GS><<<grid, 256>>>(w_dev, n, q_dev, s_dev)));
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
     return Q3_OK;
 }
 

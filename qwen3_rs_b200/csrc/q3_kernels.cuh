@@ -305,8 +305,8 @@ struct GemvArgs {
 
 // ORDERED: the per-group f32 terms are parked in shared memory and folded left to right by one
 // lane per row (tensor.rs:41-61 `.map(..).sum()`), making the row result bit-identical to the
-// reference; exp() in the SwiGLU epilogue uses the glibc restatement.
-template <int GS, int EPI, bool ORDERED = false>
+// reference; EXPREF: exp() in the SwiGLU epilogue uses the glibc restatement.
+template <int GS, int EPI, bool ORDERED = false, bool EXPREF = ORDERED>
 __global__ void __launch_bounds__(256) k_gemv(GemvArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     int4 *sx = reinterpret_cast<int4 *>(smem);
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(256) k_gemv(GemvArgs a) {
                 a.out[r0 + 1] = __fadd_rn(a.out[r0 + 1], acc1);
             } else if (EPI == EPI_SWIGLU) { // layers.rs:472-475: g * (1/(1+exp(-g))) * up
                 float g = acc0;
-                float sw = __fmul_rn(g, __fdiv_rn(1.0f, __fadd_rn(1.0f, exp_sel<ORDERED>(-g))));
+                float sw = __fmul_rn(g, __fdiv_rn(1.0f, __fadd_rn(1.0f, exp_sel<EXPREF>(-g))));
                 a.out[p] = __fmul_rn(sw, acc1);
             } else { // EPI_QKV, layers.rs:334-336: K and V go straight into the cache row of `pos`
                 const int pos = *a.pos;

@@ -8,9 +8,16 @@
 // stays busy while the 16 CONSUMER warps (two groups owning alternate stages) wait on a
 // dependency or rebuild the quantised activation vector.  Consumers keep their slice of the
 // activation vector in registers and do the int8 dot products with dp4a out of shared memory.
-// Dependencies per layer: three grid barriers (after QKV, attention, gate/up) and two flagged
-// exchanges (o_proj / down rows travel as (value, epoch) words, see ll_store; under tensor
-// parallelism the same words are pushed into every peer GPU's memory over NVLink).
+//
+// Dependencies: there is NO grid barrier inside a layer.  Every datum that crosses CTAs travels as a
+// 64-bit (payload, epoch) word (see ll_store) that its consumer polls:
+//   qkv rows          -> zone Q, polled by the (kv head, split) attention CTAs (only the rows of their kv group)
+//   attention output  -> merged, normalised and QUANTISED once by the last-arriving split of a kv head, published
+//                        as packed int8 + scales in zone A (already in the o_proj shared-memory order)
+//   o_proj / down     -> zone O / D (under tensor parallelism: partial rows pushed into every peer GPU over NVLink,
+//                        reduced once by the CTA that owns the row, republished locally)
+//   SwiGLU outputs    -> zone H, quantised by every CTA for down_proj
+// The only grid barrier left is the one before the greedy argmax (one per token).
 //
 // HBM "stream" layout (built once at load by k_build_stream): for every GEMV phase, rows are
 // split contiguously over CTAs; a CTA's rows are stored in the exact order its consumers eat
@@ -45,40 +52,26 @@ constexpr int MEGA_MAX_KT = 4096;
 constexpr int MEGA_SCRATCH = 40960;                 // xq/xs or attention buffers
 constexpr int MEGA_MAX_TP = 8;
 constexpr int MEGA_MAX_SPLITS = ATTN_MAX_SPLITS;
+constexpr int MEGA_EDGES = 6;                       // epochs per layer: one per step kind (0 qkv .. 4 down), one spare; the head step uses the next layer's 0
 
 // tuning switches (compile-time; scripts/ab_variants.py builds and times the alternatives on one box)
 #ifndef MEGA_PREFETCH_W
-#define MEGA_PREFETCH_W 1   // L2-prefetch the next norm / QK-norm / RoPE weights before entering a grid barrier
-#endif
-#ifndef MEGA_PREFETCH_KV
-#define MEGA_PREFETCH_KV 0  // L2-prefetch this CTA's K/V cache slice before the qkv barrier
+#define MEGA_PREFETCH_W 1   // L2-prefetch the next norm / QK-norm / RoPE weights at the end of the preceding step
 #endif
 #ifndef MEGA_ATTN_NP
 #define MEGA_ATTN_NP 2      // positions per warp iteration in the attention loop
 #endif
-#ifndef MEGA_FUSED_RES
-#define MEGA_FUSED_RES 1    // single GPU: o_proj / down epilogue adds the residual
-#endif
-#ifndef MEGA_QUANT_U
-#define MEGA_QUANT_U 1      // float4 loads in flight per thread in prologue_quant
-#endif
-#ifndef MEGA_AO_UNROLL
-#define MEGA_AO_UNROLL 1    // unroll factor of the attention-output quantiser loop (nsplit == 1 path)
-#endif
 #ifndef MEGA_PSLEEP
 #define MEGA_PSLEEP 0       // ns the producers sleep per iteration while waiting for their turn on a slot
 #endif
-#ifndef MEGA_RELAXED_POLL
-#define MEGA_RELAXED_POLL 0 // grid barrier: poll with relaxed loads, one acquire fence at the end
-#endif
-#ifndef MEGA_ATT_FINALIZE
-#define MEGA_ATT_FINALIZE 0 // the last attention split of a kv head merges the splits AND quantises; the o_proj prologue only copies
-#endif
-#ifndef MEGA_LL
-#define MEGA_LL 1           // o_proj / down results travel as (value, epoch) words: no grid / cross-GPU barrier after those phases
-#endif
 #ifndef MEGA_X_ONCE
-#define MEGA_X_ONCE 0       // load the activation registers once per phase when n_kt == 1
+#define MEGA_X_ONCE 0       // load the activation registers once per phase when n_kt == 1 (measured: -9 %, register pressure)
+#endif
+#ifndef MEGA_POLL_SLEEP
+#define MEGA_POLL_SLEEP 0   // ns between two polls of a word that has not arrived yet (measured: 0 best, 64: -1.4 %, 200: -1.9 %)
+#endif
+#ifndef MEGA_EARLY_W
+#define MEGA_EARLY_W 1      // issue the norm-weight loads BEFORE polling for the activation (one loaded round trip instead of two)
 #endif
 
 enum { PH_QKV = 0, PH_O = 1, PH_GU = 2, PH_DN = 3, PH_HEAD = 4 };
@@ -100,11 +93,14 @@ struct MegaArgs {
     const float *embed_s;
     const float *rope;
     float *kc, *vc;
-    float *x[2];                     // residual stream, ping-pong
-    float *part[2][MEGA_MAX_TP];     // [o|down][rank]: that rank's landing zone [tp][dim] (peer memory under TP)
-    float *q, *kraw, *hb, *attn_part;
-    uint8_t *att_q;                  // MEGA_ATT_FINALIZE: quantised attention output, already in the shared-memory chunk order of PH_O
-    float *att_s;                    // ... and its group scales
+    float *x;                        // residual stream in / out of a teacher-forced layer range; normed x after the head prologue
+    // (payload, epoch) zones, all zero-initialised; see ll_store
+    unsigned long long *zq;          // [AH_l + 2 KV_l]        q | k | v rows of the current layer (raw GEMV results)
+    unsigned long long *za;          // [AH_l/4 + AH_l/GS]     quantised attention output (4 int8 per word, PH_O smem order) | group scales
+    unsigned long long *zh;          // [H_l]                  SwiGLU outputs
+    unsigned long long *zr[2];       // [dim]                  o_proj / down rows, reduced over the TP ranks (this rank's copy)
+    unsigned long long *part[2][MEGA_MAX_TP]; // TP only: [o|down][rank] -> that rank's landing zone [tp][dim] (peer memory)
+    float *attn_part;                // [n_heads_l][MEGA_MAX_SPLITS][ATTN_PART_STRIDE] split partials (nsplit > 1)
     unsigned *att_cnt;               // [n_layers][n_kv_l] arrivals of the splits of a kv head (returns to 0 within the launch)
     float *logits[MEGA_MAX_TP];      // full-vocab logits buffer of every rank
     unsigned long long *best[MEGA_MAX_TP]; // [tp][grid] argmax candidates of every rank
@@ -115,22 +111,26 @@ struct MegaArgs {
     int *tokpos, *history;
     int *status;                     // != 0: a wait timed out (kernel aborts)
     int layer0, layer1, from_embed, run_head, feedback, gather_logits;
-    unsigned ll_base;                // MEGA_LL: epoch of the last (value, epoch) exchange of the previous launch (host-tracked)
+    unsigned ll_base;                // epoch counter before this launch, already reduced mod 2^32 - 1 (host-tracked, same on every TP rank)
     unsigned long long *prof;        // optional [grid][MEGA_PROF_EVENTS] clock64 stamps (thread 0 of each CTA)
     int dbg;                         // timing experiments only (env Q3_MEGA_DBG; results are garbage): 1 = every bulk copy reads the
-                                     // same L2-resident bytes (no HBM traffic), 2 = grid barriers skipped, 4 = prologues skipped
+                                     // same L2-resident bytes (no HBM traffic), 2 = grid barrier skipped, 4 = prologues / polls skipped
 };
 // In-kernel profiler: thread 0 of every CTA appends (clock64 << 8 | tag).  Tags: 0 start; 1 + 3*kind + {0 prologue done,
-// 1 GEMV done, 2 barrier done} for step kinds 0..5; >= 32 finer marks inside the prologues and the grid barrier.
+// 1 GEMV done, 2 step-end sync done} for step kinds 0..5; >= 32 finer marks inside the prologues and the grid barrier.
 // The last slot of a CTA's row holds its event count.
 constexpr int MEGA_PROF_EVENTS = 4096;
 struct Prof {
     unsigned long long *row;
     int ev;
 };
-__device__ __forceinline__ void prof_mark(Prof &p, int tag) {
-    if (p.row && p.ev < MEGA_PROF_EVENTS - 1) p.row[p.ev++] = ((unsigned long long)clock64() << 8) | (unsigned)tag;
-}
+#define prof_mark(p, tag)                                                                                              \
+    do {                                                                                                               \
+        if (a.prof) { /* kernel parameter (constant bank): the Prof struct is not touched unless a capture is running */ \
+            Prof &p_ = (p);                                                                                            \
+            if (p_.row && p_.ev < MEGA_PROF_EVENTS - 1) p_.row[p_.ev++] = ((unsigned long long)clock64() << 8) | (unsigned)(tag); \
+        }                                                                                                              \
+    } while (0)
 
 // ------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + bulk copy
@@ -183,23 +183,64 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(MEGA_CTHREADS) : "memory"); }
 __device__ __forceinline__ float ldcg_f(const float *p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ldcg_f4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
-// (value, epoch) words: a 64-bit store is single-copy atomic, so a reader that sees the expected epoch in the upper half
-// holds the value that was written with it -- no fence on the writer, no barrier between writer and reader (the NCCL "LL"
-// idea, here for the row-parallel GEMV results, also across GPUs over NVLink peer stores).
+
+// ------------------------------------------------------------------------------------------
+// (payload, epoch) words: a 64-bit store is single-copy atomic, so a reader that sees the expected epoch in the upper half
+// holds the payload that was written with it -- no fence on the writer, no barrier between writer and reader (the NCCL "LL"
+// idea, here for every cross-CTA edge of a layer, and across GPUs over NVLink peer stores).
 // Why nothing else is needed:
-//  * the words are the ONLY data that crosses CTAs on these two edges (the residual stream lives in each CTA's shared
-//    memory); every other cross-CTA buffer (q / k / V rows, attention partials, hb, logits) is still written before and
-//    read after one of the remaining grid barriers;
-//  * epochs are unique per (launch, layer, edge) (host-tracked base, same sequence on every TP rank), zones start zeroed
-//    and epoch 0 is never used, so stale words of an earlier use never match;
-//  * a zone is rewritten one layer later; a writer can only get there after a grid barrier that every CTA (under TP: after
-//    a flagged exchange that every CTA of every rank) reaches only once it has finished reading the previous contents.
-__device__ __forceinline__ void ll_store(unsigned long long *p, float v, unsigned epoch) {
-    const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
+//  * the words are the ONLY data that crosses CTAs inside a layer (the residual stream lives in each CTA's shared
+//    memory; the attention split partials are ordered by a fence + counter, see attention_item);
+//  * epochs are unique per (launch, layer, edge): a host-tracked counter, the same sequence on every TP rank, reduced
+//    mod 2^32 - 1 and offset by 1 so that 0 (the zero-initialised zones) is never a valid epoch and wrap-around is harmless
+//    (a zone is completely rewritten at every use, so a stale word is always exactly one use old);
+//  * a zone is rewritten one layer later.  A writer gets there only after it has consumed words of later edges that every
+//    CTA (every CTA of every rank) produces only after it has finished reading the previous contents: every CTA owns at
+//    least one qkv row and one gate/up unit (checked at load), all qkv rows are polled by some attention CTA, and zones
+//    A / O / H / D are polled completely by every CTA (argument per zone in DESIGN.md section 4).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ll_epoch(unsigned base, unsigned k) {
+    unsigned long long s = (unsigned long long)base + k;
+    if (s >= 0xFFFFFFFFull) s -= 0xFFFFFFFFull;
+    return (unsigned)s + 1u;
+}
+__device__ __forceinline__ void ll_store_u32(unsigned long long *p, unsigned payload, unsigned epoch) {
+    const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)payload;
     asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
+__device__ __forceinline__ void ll_store(unsigned long long *p, float v, unsigned epoch) { ll_store_u32(p, __float_as_uint(v), epoch); }
 __device__ __forceinline__ void ll_load2(const unsigned long long *p, unsigned long long &x, unsigned long long &y) {
     asm volatile("ld.relaxed.sys.global.v2.b64 {%0,%1}, [%2];" : "=l"(x), "=l"(y) : "l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_load1(const unsigned long long *p) {
+    unsigned long long x;
+    asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(x) : "l"(p) : "memory");
+    return x;
+}
+__device__ __forceinline__ bool ll_ok(unsigned long long w, unsigned epoch) { return (unsigned)(w >> 32) == epoch; }
+// called after a failed poll: back off, and give up (abort flag, status `code`) after ~1-2 s -- a protocol bug must never hang the GPU
+__device__ __noinline__ bool ll_give_up(const MegaArgs &a, unsigned &spins, int code) {
+    if (MEGA_POLL_SLEEP) __nanosleep(MEGA_POLL_SLEEP);
+    if ((++spins & 255u) == 0) {
+        if (*(volatile int *)a.status) return true;
+        if (spins > (1u << 20)) {
+            atomicExch(a.status, code);
+            return true;
+        }
+    }
+    return false;
+}
+// poll 4 consecutive words (16-byte aligned pair of pairs) and return their payloads as a float4
+__device__ __forceinline__ float4 ll_poll4(const MegaArgs &a, const unsigned long long *p, unsigned epoch, int code) {
+    unsigned long long w0, w1, w2, w3;
+    unsigned spins = 0;
+    while (true) {
+        ll_load2(p, w0, w1);
+        ll_load2(p + 2, w2, w3);
+        if (ll_ok(w0, epoch) && ll_ok(w1, epoch) && ll_ok(w2, epoch) && ll_ok(w3, epoch)) break;
+        if (ll_give_up(a, spins, code)) break;
+    }
+    return make_float4(__uint_as_float((unsigned)w0), __uint_as_float((unsigned)w1), __uint_as_float((unsigned)w2), __uint_as_float((unsigned)w3));
 }
 
 // contiguous split of `units` over `nctas`
@@ -283,8 +324,9 @@ struct XRegs { // this lane's groups of the current K tile: MEGA_MAX_KT/128 = 32
 // (lane l owns groups l, l+32, ...; its 16-byte chunks are 16*ngb bytes apart), so the 128-bit loads
 // below are conflict-free.  (Element order would put consecutive lanes GS bytes apart: a 16-way bank
 // conflict -- ~1 us per call with 16 warps, 7 calls per layer.)
+// byte offset of float4 #i4 of the activation vector inside the (K-tiled, chunk-permuted) shared-memory image
 template <int GS>
-__device__ __forceinline__ void xq_store(uint8_t *sxq, int i4, uint32_t packed, int KT, int G) {
+__device__ __forceinline__ int xq_offset(int i4, int KT, int G) {
     int r = i4 * 4, off = 0;
     while (r >= KT) { // K tile (at most 4)
         r -= KT;
@@ -294,7 +336,11 @@ __device__ __forceinline__ void xq_store(uint8_t *sxq, int i4, uint32_t packed, 
     int ngb = G - 32 * b;
     ngb = ngb > 32 ? 32 : ngb;
     const int p = (r % GS) >> 4;
-    *reinterpret_cast<uint32_t *>(sxq + off + b * 32 * GS + (p * ngb + l) * 16 + (r & 15)) = packed;
+    return off + b * 32 * GS + (p * ngb + l) * 16 + (r & 15);
+}
+template <int GS>
+__device__ __forceinline__ void xq_store(uint8_t *sxq, int i4, uint32_t packed, int KT, int G) {
+    *reinterpret_cast<uint32_t *>(sxq + xq_offset<GS>(i4, KT, G)) = packed;
 }
 template <int GS>
 __device__ __forceinline__ void load_x(XRegs<GS> &xr, const uint8_t *sxq, const float *sxs, int kt, int KT, int G, int lane) {
@@ -348,87 +394,74 @@ __device__ __forceinline__ float tile_dot(uint32_t tile, const XRegs<GS> &xr, in
     return warp_sum(acc);
 }
 
-// RMSNorm + group quantise of the residual stream into shared memory (all 256 consumer threads).
-// Also merges the pending partial sums of the previous row-parallel GEMV (o_proj / down_proj:
-// x <- x + sum_r part[r], ResidualConnection layers.rs:249-259; under TP this IS the all-reduce,
-// summed in rank order so every rank computes bit-identical x) and gathers the embedding row.
+// RMSNorm + group quantise of the residual stream into shared memory (all 512 consumer threads).
+// Also adds the result of the previous row-parallel GEMV (o_proj / down_proj: x <- x + row, ResidualConnection
+// layers.rs:249-259; under TP the row is already the rank-ordered sum of the partials, see the reduce step in the kernel,
+// so every rank computes bit-identical x) and gathers the embedding row.
 constexpr int MEGA_MAXV = (MEGA_MAX_KT + 4 * MEGA_CTHREADS - 1) / (4 * MEGA_CTHREADS); // float4 per thread of a dim <= 4096 vector
 
-// MEGA_LL: v += the tp partial vectors of the row-parallel GEMV that has just run, in rank order, each element taken as soon
-// as its word carries `epoch` (all lanes of a warp retry together; every retry is one L2 round trip).  zone: this rank's
-// landing area [tp][dim] of (value, epoch) words, written by the GEMV epilogues of all ranks.
-__device__ __forceinline__ void ll_merge(const MegaArgs &a, const unsigned long long *zone, unsigned epoch, float4 (&v)[MEGA_MAXV]) {
-    const int tid = threadIdx.x;
-    const int n4 = a.dim >> 2;
-#pragma unroll 1
-    for (int r = 0; r < a.tp_size; r++) {
-        const unsigned long long *src = zone + (size_t)r * a.dim;
-        unsigned long long w[MEGA_MAXV][4];
-        unsigned spins = 0;
-        while (true) {
-            bool ok = true;
-#pragma unroll
-            for (int k = 0; k < MEGA_MAXV; k++) {
-                const int i4 = tid + k * MEGA_CTHREADS;
-                if (i4 < n4) {
-                    ll_load2(src + (size_t)i4 * 4, w[k][0], w[k][1]);
-                    ll_load2(src + (size_t)i4 * 4 + 2, w[k][2], w[k][3]);
-                    ok = ok && (unsigned)(w[k][0] >> 32) == epoch && (unsigned)(w[k][1] >> 32) == epoch &&
-                         (unsigned)(w[k][2] >> 32) == epoch && (unsigned)(w[k][3] >> 32) == epoch;
-                }
-            }
-            if (__all_sync(0xffffffffu, ok)) break;
-            if ((++spins & 255u) == 0) {
-                if (*(volatile int *)a.status) break;
-                if (spins > (1u << 22)) {
-                    atomicExch(a.status, 6);
-                    break;
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < MEGA_MAXV; k++) {
-            if (tid + k * MEGA_CTHREADS < n4) {
-                v[k].x = __fadd_rn(v[k].x, __uint_as_float((unsigned)w[k][0]));
-                v[k].y = __fadd_rn(v[k].y, __uint_as_float((unsigned)w[k][1]));
-                v[k].z = __fadd_rn(v[k].z, __uint_as_float((unsigned)w[k][2]));
-                v[k].w = __fadd_rn(v[k].w, __uint_as_float((unsigned)w[k][3]));
-            }
-        }
-    }
-}
-
-// MEGA_LL adds: sx = this CTA's copy of the residual stream in shared memory (a thread always owns the same elements),
-// dense_in = take the stream from a.x[0] (teacher-forced entry), llzone/epoch = pending partial sums to merge (or null).
+// src: 0 = embedding row of tokpos[0], 1 = a.x (teacher-forced entry), 2 = sx (this CTA's copy of the residual stream in
+// shared memory; a thread always owns the same elements).  zone/epoch: pending GEMV rows to add (or null).
 template <int GS>
-__device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, bool from_embed, const float *const *parts,
-                                              int &cur, uint8_t *sxq, float *sxs, float *sred, bool write_normed, int KT, int G, Prof &pr,
-                                              float *sx = nullptr, bool dense_in = false, const unsigned long long *llzone = nullptr,
-                                              unsigned epoch = 0) {
+__device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, int src, const unsigned long long *zone, unsigned epoch,
+                                              uint8_t *sxq, float *sxs, float *sred, float *sx, bool write_normed, int KT, int G, Prof &pr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n4 = a.dim >> 2;
     constexpr int MAXV = MEGA_MAXV;
-    float4 v[MAXV];
+    float4 v[MAXV], wv[MAXV];
     float ss = 0.0f;
-#if MEGA_LL
+    // the norm weights do not depend on the activation: with the weight stream saturating the memory system a global
+    // round trip costs ~1.3 us, so their loads are issued before the poll below instead of after it
+    if (MEGA_EARLY_W) {
+#pragma unroll
+        for (int k = 0; k < MAXV; k++) {
+            const int i4 = tid + k * MEGA_CTHREADS;
+            wv[k] = (i4 < n4) ? __ldg(reinterpret_cast<const float4 *>(w) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
 #pragma unroll
     for (int k = 0; k < MAXV; k++) {
         const int i4 = tid + k * MEGA_CTHREADS;
         v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i4 < n4) {
-            if (from_embed) {
+            if (src == 0) {
                 size_t base = (size_t)a.tokpos[0] * a.dim + (size_t)i4 * 4;
                 char4 e = *reinterpret_cast<const char4 *>(a.embed_q + base);
                 float sc = a.embed_s[base / GS];
                 v[k] = make_float4((float)e.x * sc, (float)e.y * sc, (float)e.z * sc, (float)e.w * sc);
-            } else if (dense_in) {
-                v[k] = ldcg_f4(a.x[0] + (size_t)i4 * 4);
+            } else if (src == 1) {
+                v[k] = ldcg_f4(a.x + (size_t)i4 * 4);
             } else {
                 v[k] = reinterpret_cast<const float4 *>(sx)[i4];
             }
         }
     }
-    if (llzone) ll_merge(a, llzone, epoch, v);
+    if (zone) { // every word is taken as soon as it carries `epoch`; all loads of a thread are in flight together
+        unsigned long long ww[MAXV][4];
+        unsigned spins = 0;
+        while (true) {
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < MAXV; k++) {
+                const int i4 = tid + k * MEGA_CTHREADS;
+                if (i4 < n4) {
+                    ll_load2(zone + (size_t)i4 * 4, ww[k][0], ww[k][1]);
+                    ll_load2(zone + (size_t)i4 * 4 + 2, ww[k][2], ww[k][3]);
+                    ok = ok && ll_ok(ww[k][0], epoch) && ll_ok(ww[k][1], epoch) && ll_ok(ww[k][2], epoch) && ll_ok(ww[k][3], epoch);
+                }
+            }
+            if (ok || ll_give_up(a, spins, 6)) break;
+        }
+#pragma unroll
+        for (int k = 0; k < MAXV; k++) {
+            if (tid + k * MEGA_CTHREADS < n4) {
+                v[k].x = __fadd_rn(v[k].x, __uint_as_float((unsigned)ww[k][0]));
+                v[k].y = __fadd_rn(v[k].y, __uint_as_float((unsigned)ww[k][1]));
+                v[k].z = __fadd_rn(v[k].z, __uint_as_float((unsigned)ww[k][2]));
+                v[k].w = __fadd_rn(v[k].w, __uint_as_float((unsigned)ww[k][3]));
+            }
+        }
+    }
 #pragma unroll
     for (int k = 0; k < MAXV; k++) {
         const int i4 = tid + k * MEGA_CTHREADS;
@@ -440,52 +473,17 @@ __device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, bo
             ss += __fmul_rn(v[k].w, v[k].w);
         }
     }
-#else
-    const float *xin = a.x[cur];
-    float *xout = a.x[cur ^ 1];
-    const bool merge = parts != nullptr;
+    prof_mark(pr, 32); // x (+ pending rows) arrived
+    if (!MEGA_EARLY_W) {
 #pragma unroll
-    for (int k = 0; k < MAXV; k++) {
-        int i4 = tid + k * MEGA_CTHREADS;
-        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i4 < n4) {
-            if (from_embed) {
-                size_t base = (size_t)a.tokpos[0] * a.dim + (size_t)i4 * 4;
-                char4 e = *reinterpret_cast<const char4 *>(a.embed_q + base);
-                float sc = a.embed_s[base / GS];
-                v[k] = make_float4((float)e.x * sc, (float)e.y * sc, (float)e.z * sc, (float)e.w * sc);
-            } else {
-                v[k] = ldcg_f4(xin + (size_t)i4 * 4);
-                if (merge) {
-#pragma unroll 1
-                    for (int r = 0; r < a.tp_size; r++) {
-                        float4 p = ldcg_f4(parts[a.tp_rank] + (size_t)r * a.dim + (size_t)i4 * 4);
-                        v[k].x = __fadd_rn(v[k].x, p.x);
-                        v[k].y = __fadd_rn(v[k].y, p.y);
-                        v[k].z = __fadd_rn(v[k].z, p.z);
-                        v[k].w = __fadd_rn(v[k].w, p.w);
-                    }
-                }
-            }
-            if ((from_embed || merge) && blockIdx.x == 0) reinterpret_cast<float4 *>(from_embed ? a.x[cur] : xout)[i4] = v[k];
-            ss += __fmul_rn(v[k].x, v[k].x);
-            ss += __fmul_rn(v[k].y, v[k].y);
-            ss += __fmul_rn(v[k].z, v[k].z);
-            ss += __fmul_rn(v[k].w, v[k].w);
+        for (int k = 0; k < MAXV; k++) {
+            const int i4 = tid + k * MEGA_CTHREADS;
+            wv[k] = (i4 < n4) ? __ldg(reinterpret_cast<const float4 *>(w) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    }
-    if (merge && !from_embed) cur ^= 1;
-#endif
-    prof_mark(pr, 32); // x (+ partial sums) arrived
-    float4 wv[MAXV]; // norm weights: issue the loads before the reduction so their latency overlaps it
-#pragma unroll
-    for (int k = 0; k < MAXV; k++) {
-        int i4 = tid + k * MEGA_CTHREADS;
-        wv[k] = (i4 < n4) ? __ldg(reinterpret_cast<const float4 *>(w) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     ss = warp_sum(ss);
     if (lane == 0) sred[warp] = ss;
-    csync();
+    csync(); // also: every warp has left the previous GEMV, sxq may be rewritten
     float t = 0.0f;
 #pragma unroll
     for (int i = 0; i < MEGA_NCW; i++) t += sred[i];
@@ -508,7 +506,7 @@ __device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, bo
             if (i4 < n4) {
                 xq_store<GS>(sxq, i4, packed, KT, G);
                 if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
-                if (write_normed && blockIdx.x == 0) reinterpret_cast<float4 *>(a.x[MEGA_LL ? 0 : cur])[i4] = y;
+                if (write_normed && blockIdx.x == 0) reinterpret_cast<float4 *>(a.x)[i4] = y;
             }
         }
     }
@@ -516,137 +514,95 @@ __device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, bo
     csync();
 }
 
-// quantise an f32 vector in global memory (written by other CTAs) into shared memory.
-// Loads run two batches of 4 ahead of the quantiser (every load of a <= 16 K vector is in flight at
-// once: one L2 round trip instead of one per 2048 elements); the quantiser exists 4x in the code.
+// o_proj input: the attention output arrives already normalised and quantised (attention_item), packed 4 int8 per word in the
+// chunk order of this phase's shared-memory activation, followed by the group scales -- the prologue is a polled copy.
 template <int GS>
-__device__ __noinline__ void prologue_quant(const float *src, int n, uint8_t *sxq, float *sxs, int KT, int G) {
+__device__ __noinline__ void prologue_attn_poll(const MegaArgs &a, unsigned epoch, uint8_t *sxq, float *sxs) {
+    const int tid = threadIdx.x;
+    const int nq = a.AH_l >> 2, ng = a.AH_l / GS; // nq is a multiple of 32
+    unsigned spins = 0;
+    for (int i = 2 * tid; i < nq; i += 2 * MEGA_CTHREADS) {
+        unsigned long long x, y;
+        while (true) {
+            ll_load2(a.za + i, x, y);
+            if ((ll_ok(x, epoch) && ll_ok(y, epoch)) || ll_give_up(a, spins, 7)) break;
+        }
+        *reinterpret_cast<uint2 *>(sxq + 4 * i) = make_uint2((unsigned)x, (unsigned)y);
+    }
+    for (int g = tid; g < ng; g += MEGA_CTHREADS) {
+        unsigned long long x;
+        while (true) {
+            x = ll_load1(a.za + nq + g);
+            if (ll_ok(x, epoch) || ll_give_up(a, spins, 7)) break;
+        }
+        sxs[g] = __uint_as_float((unsigned)x);
+    }
+    csync();
+}
+
+// down_proj input: poll the SwiGLU outputs (zone H) and group-quantise them into shared memory (layers.rs:478).
+// The loads of the next float4 of a thread are in flight while the current one is checked and quantised.
+template <int GS>
+__device__ __forceinline__ void quant_ll_one(const MegaArgs &a, const unsigned long long *z, unsigned epoch, int i4, int n4, unsigned long long (&w)[4],
+                                             unsigned &spins, uint8_t *sxq, float *sxs, int KT, int G) {
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i4 < n4) {
+        while (!(ll_ok(w[0], epoch) && ll_ok(w[1], epoch) && ll_ok(w[2], epoch) && ll_ok(w[3], epoch))) {
+            if (ll_give_up(a, spins, 8)) break;
+            ll_load2(z + (size_t)i4 * 4, w[0], w[1]);
+            ll_load2(z + (size_t)i4 * 4 + 2, w[2], w[3]);
+        }
+        y = make_float4(__uint_as_float((unsigned)w[0]), __uint_as_float((unsigned)w[1]), __uint_as_float((unsigned)w[2]), __uint_as_float((unsigned)w[3]));
+    }
+    uint32_t packed;
+    float scale;
+    quantize_group4<GS>(y, packed, scale); // warp-collective: the caller's loop condition is warp-uniform
+    if (i4 < n4) {
+        xq_store<GS>(sxq, i4, packed, KT, G);
+        if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
+    }
+}
+template <int GS>
+__device__ __noinline__ void prologue_quant_ll(const MegaArgs &a, const unsigned long long *z, unsigned epoch, int n, uint8_t *sxq, float *sxs, int KT, int G) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int n4 = n >> 2;
-    constexpr int U = MEGA_QUANT_U;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 nxt[U];
-#pragma unroll
-    for (int j = 0; j < U; j++) {
-        const int i4 = tid + j * MEGA_CTHREADS;
-        nxt[j] = (i4 < n4) ? ldcg_f4(src + (size_t)i4 * 4) : zero;
+    unsigned long long wa[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
+    unsigned spins = 0;
+    int i4 = tid;
+    if (i4 < n4) {
+        ll_load2(z + (size_t)i4 * 4, wa[0], wa[1]);
+        ll_load2(z + (size_t)i4 * 4 + 2, wa[2], wa[3]);
     }
 #pragma unroll 1
-    for (int base = tid; base - lane < n4; base += U * MEGA_CTHREADS) {
-        float4 cur[U];
-#pragma unroll
-        for (int j = 0; j < U; j++) {
-            cur[j] = nxt[j];
-            const int i4 = base + (U + j) * MEGA_CTHREADS;
-            nxt[j] = (i4 < n4) ? ldcg_f4(src + (size_t)i4 * 4) : zero;
+    while (i4 - lane < n4) {
+        int j4 = i4 + MEGA_CTHREADS;
+        if (j4 < n4) {
+            ll_load2(z + (size_t)j4 * 4, wb[0], wb[1]);
+            ll_load2(z + (size_t)j4 * 4 + 2, wb[2], wb[3]);
         }
-#pragma unroll
-        for (int j = 0; j < U; j++) {
-            const int i4 = base + j * MEGA_CTHREADS;
-            if (i4 - lane < n4) { // warp-uniform
-                uint32_t packed;
-                float scale;
-                quantize_group4<GS>(cur[j], packed, scale);
-                if (i4 < n4) {
-                    xq_store<GS>(sxq, i4, packed, KT, G);
-                    if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
-                }
-            }
+        quant_ll_one<GS>(a, z, epoch, i4, n4, wa, spins, sxq, sxs, KT, G);
+        i4 = j4;
+        if (!(i4 - lane < n4)) break;
+        j4 = i4 + MEGA_CTHREADS;
+        if (j4 < n4) {
+            ll_load2(z + (size_t)j4 * 4, wa[0], wa[1]);
+            ll_load2(z + (size_t)j4 * 4 + 2, wa[2], wa[3]);
         }
+        quant_ll_one<GS>(a, z, epoch, i4, n4, wb, spins, sxq, sxs, KT, G);
+        i4 = j4;
     }
     csync();
 }
 
-// merge the attention split partials (k_attn_combine_quant's math) and quantise into shared memory
-template <int GS>
-__device__ __noinline__ void prologue_attn_out(const MegaArgs &a, int nsplit, uint8_t *sxq, float *sxs, int KT, int G) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int n4 = a.AH_l >> 2;
-    if (nsplit == 1) { // short context: one partial per head; exp(m - M) == 1.  Rolled, next loads in flight.
-        int i4 = tid;
-        float4 An = make_float4(0.f, 0.f, 0.f, 0.f);
-        float Ln = 1.0f;
-        if (i4 < n4) {
-            const float *pb = a.attn_part + (size_t)(i4 >> 5) * MEGA_MAX_SPLITS * ATTN_PART_STRIDE;
-            An = ldcg_f4(pb + (i4 & 31) * 4);
-            Ln = ldcg_f(pb + HEAD_DIM + 1);
-        }
-        constexpr int AO_UNROLL = MEGA_AO_UNROLL;
-#pragma unroll AO_UNROLL
-        for (; i4 - lane < n4; i4 += MEGA_CTHREADS) {
-            const float4 A = An;
-            const float Lc = Ln;
-            const int j4 = i4 + MEGA_CTHREADS;
-            if (j4 < n4) {
-                const float *pb = a.attn_part + (size_t)(j4 >> 5) * MEGA_MAX_SPLITS * ATTN_PART_STRIDE;
-                An = ldcg_f4(pb + (j4 & 31) * 4);
-                Ln = ldcg_f(pb + HEAD_DIM + 1);
-            }
-            // split 0 holds sum_t exp(s_t - m) v_t and l = sum_t exp(s_t - m); c = exp(m - M) = 1 exactly
-            float inv = __fdiv_rn(1.0f, Lc);
-            float4 y = make_float4(__fmul_rn(A.x, inv), __fmul_rn(A.y, inv), __fmul_rn(A.z, inv), __fmul_rn(A.w, inv));
-            uint32_t packed;
-            float scale;
-            quantize_group4<GS>(y, packed, scale);
-            if (i4 < n4) {
-                xq_store<GS>(sxq, i4, packed, KT, G);
-                if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
-            }
-        }
-        csync();
-        return;
-    }
-    // A warp handles one head per iteration (32 float4 = 128 dims).  Lane s first fetches the statistics of split s
-    // (one memory round trip for all splits instead of one per split), then the partial accumulators are pulled
-    // four splits at a time.
-#pragma unroll 1
-    for (int base = tid - lane; base < n4; base += MEGA_CTHREADS) {
-        const int i4 = base + lane;
-        const int head = base >> 5; // warp-uniform
-        const float *pb = a.attn_part + (size_t)head * MEGA_MAX_SPLITS * ATTN_PART_STRIDE;
-        const float ms = lane < nsplit ? ldcg_f(pb + lane * ATTN_PART_STRIDE + HEAD_DIM) : -INFINITY;
-        const float ls = lane < nsplit ? ldcg_f(pb + lane * ATTN_PART_STRIDE + HEAD_DIM + 1) : 0.0f;
-        const float M = warp_max(ms);
-        const float cs = lane < nsplit ? expf(ms - M) : 0.0f;
-        const float L = warp_sum(ls * cs);
-        float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-        for (int s0 = 0; s0 < nsplit; s0 += 4) {
-            float4 pv[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                pv[j] = (s0 + j < nsplit) ? ldcg_f4(pb + (s0 + j) * ATTN_PART_STRIDE + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float c = __shfl_sync(0xffffffffu, cs, (s0 + j) & 31);
-                A.x += pv[j].x * c;
-                A.y += pv[j].y * c;
-                A.z += pv[j].z * c;
-                A.w += pv[j].w * c;
-            }
-        }
-        const float inv = __fdiv_rn(1.0f, L);
-        const float4 y = make_float4(__fmul_rn(A.x, inv), __fmul_rn(A.y, inv), __fmul_rn(A.z, inv), __fmul_rn(A.w, inv));
-        uint32_t packed;
-        float scale;
-        quantize_group4<GS>(y, packed, scale);
-        if (i4 < n4) {
-            xq_store<GS>(sxq, i4, packed, KT, G);
-            if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
-        }
-    }
-    csync();
-}
-
-// QK-RMSNorm + RoPE of one head held as float4 per lane (same math as k_qknorm_rope)
-__device__ __forceinline__ float4 qk_norm_rope(float4 v, const float *w, const float *rope_row, int lane) {
+// QK-RMSNorm + RoPE of one head held as float4 per lane (same math as k_qknorm_rope); wv = this lane's norm weights,
+// cs01 / cs23 = (cos, sin) of its four rotation pairs
+__device__ __forceinline__ float4 qk_norm_rope_pre(float4 v, float4 wv, float4 cs01, float4 cs23, int lane) {
     float ss = __fmul_rn(v.x, v.x);
     ss = __fadd_rn(ss, __fmul_rn(v.y, v.y));
     ss = __fadd_rn(ss, __fmul_rn(v.z, v.z));
     ss = __fadd_rn(ss, __fmul_rn(v.w, v.w));
     ss = warp_sum(ss);
     const float f = __fdiv_rn(1.0f, sqrtf(__fadd_rn(__fdiv_rn(ss, (float)HEAD_DIM), NORM_EPS)));
-    float4 wv = __ldg(reinterpret_cast<const float4 *>(w) + lane);
     float4 y;
     y.x = __fmul_rn(wv.x, __fmul_rn(f, v.x));
     y.y = __fmul_rn(wv.y, __fmul_rn(f, v.y));
@@ -657,8 +613,6 @@ __device__ __forceinline__ float4 qk_norm_rope(float4 v, const float *w, const f
     o.y = __shfl_xor_sync(0xffffffffu, y.y, 16);
     o.z = __shfl_xor_sync(0xffffffffu, y.z, 16);
     o.w = __shfl_xor_sync(0xffffffffu, y.w, 16);
-    const float4 *cs = reinterpret_cast<const float4 *>(rope_row) + (lane & 15) * 2;
-    float4 cs01 = __ldg(cs), cs23 = __ldg(cs + 1);
     float4 r;
     if (lane < 16) {
         r.x = __fsub_rn(__fmul_rn(y.x, cs01.x), __fmul_rn(o.x, cs01.y));
@@ -672,6 +626,11 @@ __device__ __forceinline__ float4 qk_norm_rope(float4 v, const float *w, const f
         r.w = __fadd_rn(__fmul_rn(o.w, cs23.w), __fmul_rn(y.w, cs23.z));
     }
     return r;
+}
+__device__ __forceinline__ float4 qk_norm_rope(float4 v, const float *w, const float *rope_row, int lane) {
+    const float4 wv = __ldg(reinterpret_cast<const float4 *>(w) + lane);
+    const float4 *cs = reinterpret_cast<const float4 *>(rope_row) + (lane & 15) * 2;
+    return qk_norm_rope_pre(v, wv, __ldg(cs), __ldg(cs + 1), lane);
 }
 
 #ifndef MEGA_ATTN_CHUNK_
@@ -687,36 +646,71 @@ __device__ __forceinline__ int mega_nsplit(int pos, int n_kv_l, int grid) {
     return ns > cap ? cap : ns;
 }
 
-// attention phase for one (kv head, split) work item; all 256 consumer threads.
+// normalise (softmax multiplies by 1/sum, layers.rs:504-505), group-quantise (qwen3.rs:152) and publish the 128 outputs of
+// one query head held as float4 per lane: packed int8 into zone A at the word the o_proj phase's shared-memory layout
+// puts them, scales behind.  Warp-collective.
+template <int GS>
+__device__ __forceinline__ void publish_head(const MegaArgs &a, int head, int lane, float4 A, float L, unsigned epoch) {
+    const float inv = __fdiv_rn(1.0f, L);
+    const float4 y = make_float4(__fmul_rn(A.x, inv), __fmul_rn(A.y, inv), __fmul_rn(A.z, inv), __fmul_rn(A.w, inv));
+    uint32_t packed;
+    float qscale;
+    quantize_group4<GS>(y, packed, qscale);
+    const int i4 = head * 32 + lane;
+    ll_store_u32(a.za + (xq_offset<GS>(i4, a.g[PH_O].KT, a.g[PH_O].G) >> 2), packed, epoch);
+    if ((i4 % (GS / 4)) == 0) ll_store(a.za + (a.AH_l >> 2) + i4 / (GS / 4), qscale, epoch);
+}
+
+// attention phase for one (kv head, split) work item; all 512 consumer threads.
+//   * q (and, in the split that owns `pos`, the new k / v rows) are polled from zone Q -- only this kv group's rows, so the
+//     item starts as soon as THEY are done, not when the whole grid is; QK-norm + RoPE (layers.rs:346-372); the owner split
+//     stores the k / v cache rows (layers.rs:335-336);
+//   * positions t0..t1 with an online softmax (layers.rs:374-419), warp partials merged through shared memory;
+//   * one split: normalise + quantise + publish straight away.  Several splits: partials go to global memory, the split that
+//     arrives LAST at its kv head's counter merges them, and publishes (release: bar.sync + thread 0's fence before its
+//     atomic; acquire: fence after it).
 template <int GS, int KVMUL>
 __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int pos, int kvh, int split, int nsplit,
-                                               uint8_t *scratch, Prof &pr) {
+                                               uint8_t *scratch, unsigned ep_q, unsigned ep_a, Prof &pr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NATT = (KVMUL * MEGA_NCW * 512 + 8192 <= MEGA_SCRATCH) ? MEGA_NCW : MEGA_GW; // warps in the position loop
     float4 *sq = reinterpret_cast<float4 *>(scratch);                 // [KVMUL][32]
     float4 *sk = sq + KVMUL * 32;                                     // [32]
-    float *sm_m = reinterpret_cast<float *>(sk + 32);                 // [NATT][KVMUL]
+    float4 *sv = sk + 32;                                             // [32]
+    float *sm_m = reinterpret_cast<float *>(sv + 32);                 // [NATT][KVMUL]
     float *sm_l = sm_m + NATT * KVMUL;                                // [NATT][KVMUL]
     float4 *sm_acc = reinterpret_cast<float4 *>(sm_l + NATT * KVMUL); // [NATT][KVMUL][32]
+    static_assert((KVMUL * 32 + 64) * 16 + 2 * NATT * KVMUL * 4 + NATT * KVMUL * 512 <= MEGA_SCRATCH, "attention scratch");
+    static_assert(KVMUL + 2 <= MEGA_NCW, "one warp per gathered row");
     const int n = pos + 1;
     const int per = (n + nsplit - 1) / nsplit;
     const int t0 = split * per;
     int t1 = t0 + per;
     if (t1 > n) t1 = n;
+    const bool owner = pos >= t0 && pos < t1; // this split attends to (and stores) the new position
     float *kc_l = a.kc + (size_t)layer * a.seq_len * a.KV_l;
     float *vc_l = a.vc + (size_t)layer * a.seq_len * a.KV_l;
-    const float *rope_row = a.rope + (size_t)pos * HEAD_DIM;
-    // QK-norm + RoPE (layers.rs:346-372): KVMUL query heads and the key head of this kv group
-    for (int hh = warp; hh < KVMUL + 1; hh += MEGA_NCW) {
-        if (hh < KVMUL) {
-            float4 v = ldcg_f4(a.q + (size_t)(kvh * KVMUL + hh) * HEAD_DIM + lane * 4);
-            sq[hh * 32 + lane] = qk_norm_rope(v, a.q_ln + (size_t)layer * HEAD_DIM, rope_row, lane);
-        } else {
-            float4 v = ldcg_f4(a.kraw + (size_t)kvh * HEAD_DIM + lane * 4);
-            float4 r = qk_norm_rope(v, a.k_ln + (size_t)layer * HEAD_DIM, rope_row, lane);
+    if (warp < KVMUL + 2 && (warp < KVMUL || owner)) {
+        const bool isq = warp < KVMUL, isk = warp == KVMUL;
+        // static operands first: their loaded latency overlaps the poll
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f), cs01 = wv, cs23 = wv;
+        if (isq || isk) {
+            wv = __ldg(reinterpret_cast<const float4 *>((isq ? a.q_ln : a.k_ln) + (size_t)layer * HEAD_DIM) + lane);
+            const float4 *cs = reinterpret_cast<const float4 *>(a.rope + (size_t)pos * HEAD_DIM) + (lane & 15) * 2;
+            cs01 = __ldg(cs);
+            cs23 = __ldg(cs + 1);
+        }
+        const int row0 = isq ? (kvh * KVMUL + warp) * HEAD_DIM : (isk ? a.AH_l : a.AH_l + a.KV_l) + kvh * HEAD_DIM;
+        const float4 v = ll_poll4(a, a.zq + row0 + lane * 4, ep_q, 9);
+        if (isq) {
+            sq[warp * 32 + lane] = qk_norm_rope_pre(v, wv, cs01, cs23, lane);
+        } else if (isk) {
+            const float4 r = qk_norm_rope_pre(v, wv, cs01, cs23, lane);
             sk[lane] = r;
-            if (pos >= t0 && pos < t1) // the split that owns `pos` publishes the cache row
-                reinterpret_cast<float4 *>(kc_l + (size_t)pos * a.KV_l + (size_t)kvh * HEAD_DIM)[lane] = r;
+            reinterpret_cast<float4 *>(kc_l + (size_t)pos * a.KV_l + (size_t)kvh * HEAD_DIM)[lane] = r;
+        } else {
+            sv[lane] = v;
+            reinterpret_cast<float4 *>(vc_l + (size_t)pos * a.KV_l + (size_t)kvh * HEAD_DIM)[lane] = v;
         }
     }
     csync();
@@ -734,8 +728,7 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
     }
     const float *kbase = kc_l + (size_t)kvh * HEAD_DIM + lane * 4;
     const float *vbase = vc_l + (size_t)kvh * HEAD_DIM + lane * 4;
-    // four positions per iteration: all eight K/V row loads are in flight before any is used (a 64-position
-    // split is one memory round trip for every warp)
+    // NP positions per iteration: all 2 NP K/V row loads are in flight before any is used
     constexpr int NP = MEGA_ATTN_NP;
     for (int t = t0 + warp; t < t1 && warp < NATT; t += NP * NATT) {
         float4 kv[NP], vv[NP];
@@ -746,7 +739,7 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
             vv[j] = kv[j];
             if (tj < t1) {
                 kv[j] = (tj == pos) ? sk[lane] : ldcg_f4(kbase + (size_t)tj * a.KV_l);
-                vv[j] = ldcg_f4(vbase + (size_t)tj * a.KV_l);
+                vv[j] = (tj == pos) ? sv[lane] : ldcg_f4(vbase + (size_t)tj * a.KV_l);
             }
         }
         float sc[NP][KVMUL];
@@ -793,13 +786,15 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
         }
     }
     csync();
-    for (int h = warp; h < KVMUL; h += MEGA_NCW) {
-        // lane w owns partial w: one exp per lane instead of a serial chain of NATT of them
+    // warp h < KVMUL merges the NATT warp partials of query head h (lane w owns partial w: one exp per lane)
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+    float M = -INFINITY, L = 0.0f;
+    if (warp < KVMUL) {
+        const int h = warp;
         const float mw = lane < NATT ? sm_m[lane * KVMUL + h] : -INFINITY;
-        const float M = warp_max(mw);
+        M = warp_max(mw);
         const float cw = (mw == -INFINITY) ? 0.0f : expf(mw - M);
-        const float L = warp_sum(lane < NATT ? sm_l[lane * KVMUL + h] * cw : 0.0f);
-        float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+        L = warp_sum(lane < NATT ? sm_l[lane * KVMUL + h] * cw : 0.0f);
 #pragma unroll 4
         for (int w = 0; w < NATT; w++) {
             const float c = __shfl_sync(0xffffffffu, cw, w);
@@ -809,45 +804,43 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
             A.z += aw.z * c;
             A.w += aw.w * c;
         }
-        float *dst = a.attn_part + ((size_t)(kvh * KVMUL + h) * MEGA_MAX_SPLITS + split) * ATTN_PART_STRIDE;
+    }
+    if (nsplit == 1) { // the only split of its kv head: A / L is the attention output
+        if (warp < KVMUL) publish_head<GS>(a, kvh * KVMUL + warp, lane, A, L, ep_a);
+        return;
+    }
+    if (warp < KVMUL) {
+        float *dst = a.attn_part + ((size_t)(kvh * KVMUL + warp) * MEGA_MAX_SPLITS + split) * ATTN_PART_STRIDE;
         reinterpret_cast<float4 *>(dst)[lane] = A;
         if (lane == 0) {
             dst[HEAD_DIM] = M;
             dst[HEAD_DIM + 1] = L;
         }
     }
-#if MEGA_ATT_FINALIZE
-    // The split that arrives LAST at its kv head's counter merges all splits of the group's query heads, normalises and
-    // quantises them (qwen3.rs:152) and stores the int8 bytes in the chunk order the o_proj phase keeps in shared memory:
-    // the o_proj prologue of all 148 CTAs shrinks to a 4 KB copy, at the price of one merge on the (8 x nsplit)-CTA
-    // attention path.  Release: bar.sync + thread 0's fence before its atomic; acquire: fence after it.
     unsigned *flag = reinterpret_cast<unsigned *>(sm_m); // the position-loop statistics have been consumed above
-    bool last = true;
-    if (nsplit > 1) {
-        csync();
-        if (tid == 0) {
-            __threadfence();
-            unsigned *cnt = a.att_cnt + (size_t)layer * a.n_kv_l + kvh;
-            const unsigned old = atomicAdd(cnt, 1u);
-            const bool is_last = old == (unsigned)nsplit - 1;
-            if (is_last) *cnt = 0; // every split of this (layer, kv head) has arrived; next use is the next launch
-            __threadfence();
-            *flag = is_last ? 1u : 0u;
-        }
-        csync();
-        last = *flag != 0;
-    } else {
-        csync(); // the single split's own partial stores must be visible to the warps re-reading them
+    csync();
+    if (tid == 0) {
+        __threadfence();
+        unsigned *cnt = a.att_cnt + (size_t)layer * a.n_kv_l + kvh;
+        const unsigned old = atomicAdd(cnt, 1u);
+        const bool is_last = old == (unsigned)nsplit - 1;
+        if (is_last) *cnt = 0; // every split of this (layer, kv head) has arrived; next use is the next launch
+        __threadfence();
+        *flag = is_last ? 1u : 0u;
     }
-    if (last && warp < KVMUL) {
+    csync();
+    prof_mark(pr, 37); // split partial stored, arrival counted
+    if (*flag != 0 && warp < KVMUL) {
+        // Lane s first fetches the statistics of split s (one memory round trip for all splits), then the partial
+        // accumulators are pulled four splits at a time.
         const int head = kvh * KVMUL + warp;
         const float *pb = a.attn_part + (size_t)head * MEGA_MAX_SPLITS * ATTN_PART_STRIDE;
         const float ms = lane < nsplit ? ldcg_f(pb + lane * ATTN_PART_STRIDE + HEAD_DIM) : -INFINITY;
         const float ls = lane < nsplit ? ldcg_f(pb + lane * ATTN_PART_STRIDE + HEAD_DIM + 1) : 0.0f;
-        const float M = warp_max(ms);
-        const float cs = lane < nsplit ? expf(ms - M) : 0.0f;
-        const float L = warp_sum(ls * cs);
-        float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float Mx = warp_max(ms);
+        const float cs = lane < nsplit ? expf(ms - Mx) : 0.0f;
+        const float Ls = warp_sum(ls * cs);
+        float4 As = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
         for (int s0 = 0; s0 < nsplit; s0 += 4) {
             float4 pv[4];
@@ -857,47 +850,28 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const float c = __shfl_sync(0xffffffffu, cs, (s0 + j) & 31);
-                A.x += pv[j].x * c;
-                A.y += pv[j].y * c;
-                A.z += pv[j].z * c;
-                A.w += pv[j].w * c;
+                As.x += pv[j].x * c;
+                As.y += pv[j].y * c;
+                As.z += pv[j].z * c;
+                As.w += pv[j].w * c;
             }
         }
-        const float inv = __fdiv_rn(1.0f, L);
-        const float4 y = make_float4(__fmul_rn(A.x, inv), __fmul_rn(A.y, inv), __fmul_rn(A.z, inv), __fmul_rn(A.w, inv));
-        uint32_t packed;
-        float qscale;
-        quantize_group4<GS>(y, packed, qscale);
-        const int i4 = head * 32 + lane;
-        xq_store<GS>(a.att_q, i4, packed, a.g[PH_O].KT, a.g[PH_O].G);
-        if ((i4 % (GS / 4)) == 0) a.att_s[i4 / (GS / 4)] = qscale;
+        publish_head<GS>(a, head, lane, As, Ls, ep_a);
     }
-#endif
-}
-
-// MEGA_ATT_FINALIZE: the o_proj prologue is a copy of the bytes the attention step left in global memory
-template <int GS>
-__device__ __noinline__ void prologue_attn_copy(const MegaArgs &a, uint8_t *sxq, float *sxs) {
-    const int tid = threadIdx.x;
-    const int n16 = a.AH_l >> 4, ng = a.AH_l / GS;
-    for (int i = tid; i < n16; i += MEGA_CTHREADS)
-        reinterpret_cast<int4 *>(sxq)[i] = __ldcg(reinterpret_cast<const int4 *>(a.att_q) + i);
-    for (int g = tid; g < ng; g += MEGA_CTHREADS) sxs[g] = ldcg_f(a.att_s + g);
-    csync();
 }
 
 // ------------------------------------------------------------------------------------------
-// grid barrier (+ cross-GPU flag exchange under TP)
+// grid barrier (once per token, before the greedy argmax; + cross-GPU arrival under TP)
 // ------------------------------------------------------------------------------------------
 struct BarState {
     unsigned long long target;  // next value the local counter must reach
     unsigned long long xtarget; // next value this rank's cross-GPU counter must reach
 };
 
-// Grid barrier.  Local: every CTA adds 1 to this GPU's counter and waits for gridDim.x arrivals.
-// Cross (tensor parallel exchange points): every CTA of every rank adds 1 to the counter of EVERY
-// rank (remote reductions over NVLink) and waits for tp * gridDim.x arrivals on its own -- one
-// system-scope fence and one NVLink one-way trip, no second hop through a leader CTA.
+// Local: every CTA adds 1 to this GPU's counter and waits for gridDim.x arrivals.
+// Cross (tensor parallel): every CTA of every rank adds 1 to the counter of EVERY rank (remote reductions over NVLink)
+// and waits for tp * gridDim.x arrivals on its own -- one system-scope fence and one NVLink one-way trip, no second hop
+// through a leader CTA.
 __device__ __noinline__ void grid_barrier(const MegaArgs &a, BarState &bs, bool cross, Prof &pr) {
     csync();
     if (a.dbg & 2) return;
@@ -929,12 +903,8 @@ __device__ __noinline__ void grid_barrier(const MegaArgs &a, BarState &bs, bool 
             asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(a.bar), "l"(1ULL) : "memory");
             while (true) {
                 unsigned long long v;
-                if (MEGA_RELAXED_POLL) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
-                else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
-                if (v >= bs.target) {
-                    if (MEGA_RELAXED_POLL) asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                    break;
-                }
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
+                if (v >= bs.target) break;
                 if ((++spins & 1023u) == 0) {
                     if (*st) break;
                     if (clock64() - t0 > 4000000000LL) {
@@ -962,7 +932,7 @@ struct PhaseGeom {
 struct MegaShared {
     int start[5], count[5];
     long long seg_off[5], seg_len[5];
-    float *part[2][MEGA_MAX_TP];
+    unsigned long long *part[2][MEGA_MAX_TP];
     float *logits[MEGA_MAX_TP];
     unsigned long long *best[MEGA_MAX_TP];
 };
@@ -978,7 +948,7 @@ template <int GS, int KVMUL>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_constant__ MegaArgs a) {
     extern __shared__ __align__(1024) uint8_t mega_smem[];
     uint8_t *smem = mega_smem;
-    // layout: [ring: NSTAGE x slot][scratch][barriers]
+    // layout: [ring: NSTAGE x slot][scratch][barriers + per-CTA constants][residual stream]
     const int slot_bytes = MEGA_GW * (MEGA_MAX_KT + 4 * (MEGA_MAX_KT / GS));
     uint8_t *ring = smem;
     uint8_t *scratch = smem + MEGA_NSTAGE * slot_bytes;
@@ -992,7 +962,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
     uint64_t *empty = full + MEGA_GROUPS * MEGA_NSTAGE;                    // [MEGA_NSTAGE]
     MegaShared &sh = *reinterpret_cast<MegaShared *>(scratch + MEGA_SCRATCH + 192);
     static_assert(192 + sizeof(MegaShared) <= 1024, "MegaShared outgrew its slot");
-    float *sx = reinterpret_cast<float *>(scratch + MEGA_SCRATCH + 1024); // MEGA_LL: residual stream, MEGA_MAX_KT floats
+    float *sx = reinterpret_cast<float *>(scratch + MEGA_SCRATCH + 1024); // residual stream, MEGA_MAX_KT floats
     volatile unsigned *issued = reinterpret_cast<volatile unsigned *>(scratch + MEGA_SCRATCH + 128); // [MEGA_NSTAGE] uses issued per slot
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -1114,7 +1084,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
     bs.xtarget = a.xbar_base + (unsigned long long)a.tp_size * gridDim.x;
     const int pos = a.tokpos[1];
     const int grp = warp / MEGA_GW, wl = warp % MEGA_GW; // consumer group and warp-in-group (= row tile in a stage)
-    int cur = 0;
     Prof pr;
     pr.row = (a.prof && (tid == 0 || tid == MEGA_GW * 32)) ? a.prof + (size_t)((tid ? 2 * gridDim.x : 0) + blockIdx.x) * MEGA_PROF_EVENTS : nullptr; // + first lane of group 1
     pr.ev = 0;
@@ -1125,17 +1094,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
     long long best = (long long)0x8000000000000000LL;
     const int n_layer_steps = 5 * (L1 - L0);
     const int n_steps = n_layer_steps + (a.run_head ? 1 : 0);
-    int nsplit = 1;
-    // Single GPU: the o_proj / down epilogue adds the residual itself (x_new[r] = x[r] + row result, the
-    // same single f32 add as ResidualConnection, layers.rs:249-259) so the next prologue reads one vector
-    // instead of x and the partial sums.  Under TP the partial sums of all ranks are merged in the prologue.
-    const bool fused_res = MEGA_FUSED_RES && !MEGA_LL && a.tp_size == 1;
+    const int nsplit = mega_nsplit(pos, a.n_kv_l, gridDim.x);
 
     for (int step = 0; step < n_steps; step++) {
         const bool head = step >= n_layer_steps;
         const int l = head ? 0 : L0 + step / 5;
         const int kind = head ? 5 : step % 5; // 0 qkv, 1 attention, 2 o_proj, 3 gate/up, 4 down, 5 lm_head
-        bool cross = false;
+        // epoch of step (l, kind): everything a step publishes carries it (each zone is written by one step kind, or by
+        // steps that are never in flight together); the head step takes the slot after the last layer
+        const unsigned ep_step = ll_epoch(a.ll_base, head ? (unsigned)(MEGA_EDGES * (L1 - L0)) : (unsigned)(MEGA_EDGES * (l - L0) + kind));
+        const unsigned ep_prev = ll_epoch(a.ll_base, (unsigned)(MEGA_EDGES * (l - L0) + kind - 1)); // of the preceding step of this layer
         int ph = PH_QKV;
         // ------------------------------ prologue ------------------------------
         if (a.dbg & 4) {
@@ -1144,32 +1112,21 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
             // RMSNorm + quantize of the residual stream (qwen3.rs:134-136, 159-161, 72-75)
             const float *w = kind == 0 ? a.rms_att + (size_t)l * a.dim : kind == 3 ? a.rms_ffn + (size_t)l * a.dim : a.rms_final;
             const bool emb = kind == 0 && l == L0 && a.from_embed;
-            const float *const *parts = nullptr;
             const bool pending = kind == 3 || (kind == 0 ? l > L0 : L1 > L0); // a row-parallel GEMV (o_proj / down) has just run
             ph = kind == 0 ? PH_QKV : kind == 3 ? PH_GU : PH_HEAD;
-#if MEGA_LL
-            // epoch of the exchange being consumed: o_proj of this layer (kind 3) or down of the previous one
-            const unsigned ep_in = a.ll_base + 1 + 2 * (unsigned)((kind == 3 ? l : (kind == 0 ? l - 1 : L1 - 1)) - L0) + (kind == 3 ? 0 : 1);
-            prologue_norm<GS>(a, w, emb, parts, cur, sxq, sxs, sred, kind == 5, a.g[ph].KT, a.g[ph].G, pr, sx, !pending && !emb,
-                              pending ? reinterpret_cast<const unsigned long long *>(sh.part[kind == 3 ? 0 : 1][a.tp_rank]) : nullptr, ep_in);
-#else
-            if (pending) {
-                if (fused_res) cur ^= 1; // single GPU: its epilogue already wrote x + result
-                else parts = (const float *const *)sh.part[kind == 3 ? 0 : 1];
-            }
-            prologue_norm<GS>(a, w, emb, parts, cur, sxq, sxs, sred, kind == 5, a.g[ph].KT, a.g[ph].G, pr);
-#endif
+            // rows being consumed: o_proj of this layer (kind 3) or down of the previous / last layer
+            const unsigned ep_rows = kind == 3 ? ep_prev : ll_epoch(a.ll_base, (unsigned)(MEGA_EDGES * ((kind == 0 ? l - 1 : L1 - 1) - L0) + 4));
+            prologue_norm<GS>(a, w, emb ? 0 : (pending ? 2 : 1), pending ? a.zr[kind == 3 ? 0 : 1] : nullptr, ep_rows, sxq, sxs, sred, sx, kind == 5,
+                              a.g[ph].KT, a.g[ph].G, pr);
         } else if (kind == 1) {
-            // QK-norm + RoPE + attention (layers.rs:339-343)
-            nsplit = mega_nsplit(pos, a.n_kv_l, gridDim.x);
+            // QK-norm + RoPE + attention (layers.rs:339-343) + quantize (qwen3.rs:152) on the CTAs that own a (kv head, split) item
             if ((int)blockIdx.x < a.n_kv_l * nsplit)
-                attention_item<GS, KVMUL>(a, l, pos, blockIdx.x % a.n_kv_l, blockIdx.x / a.n_kv_l, nsplit, scratch, pr);
+                attention_item<GS, KVMUL>(a, l, pos, blockIdx.x % a.n_kv_l, blockIdx.x / a.n_kv_l, nsplit, scratch, ep_prev, ep_step, pr);
         } else if (kind == 2) {
-            if (MEGA_ATT_FINALIZE) prologue_attn_copy<GS>(a, sxq, sxs);
-            else prologue_attn_out<GS>(a, nsplit, sxq, sxs, a.g[PH_O].KT, a.g[PH_O].G); // quantize(att), qwen3.rs:152
+            prologue_attn_poll<GS>(a, ep_prev, sxq, sxs);
             ph = PH_O;
         } else {
-            prologue_quant<GS>(a.hb, a.H_l, sxq, sxs, a.g[PH_DN].KT, a.g[PH_DN].G); // quantize(hb), layers.rs:478
+            prologue_quant_ll<GS>(a, a.zh, ep_prev, a.H_l, sxq, sxs, a.g[PH_DN].KT, a.g[PH_DN].G); // quantize(hb), layers.rs:478
             ph = PH_DN;
         }
         prof_mark(pr, 1 + 3 * kind);
@@ -1179,9 +1136,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
             const int start = sh.start[ph], count = sh.count[ph];
             const bool full_blocks = (g.G & 31) == 0;
             const uint32_t ring_s = smem_u32(ring);
-            float *vrow = a.vc + ((size_t)l * a.seq_len + pos) * a.KV_l;
             if (kind == 3) {
                 // gate/up + SwiGLU (layers.rs:468-475): blocks of 8 pairs, a gate stage then an up stage
+                const unsigned ep_h = ep_step;
                 load_x<GS>(xr, sxq, sxs, 0, g.KT, g.G, lane);
                 for (int p0 = 0, bi = 0; p0 < count; p0 += MEGA_GW, bi++) {
                     const int np = count - p0 < MEGA_GW ? count - p0 : MEGA_GW;
@@ -1207,22 +1164,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                     }
                     if (wl < np && lane == 0) {
                         float sw = __fmul_rn(gate, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-gate))));
-                        a.hb[start + p0 + wl] = __fmul_rn(sw, up);
+                        ll_store(a.zh + start + p0 + wl, __fmul_rn(sw, up), ep_h);
                     }
                 }
             } else {
                 // row phases: batches of 32 rows x n_kt K tiles x up to 4 stages of 8 rows
+                const unsigned ep_out = ep_step;
                 const bool x_once = MEGA_X_ONCE && g.n_kt == 1; // the whole activation fits the registers: load it once per phase
                 if (x_once) load_x<GS>(xr, sxq, sxs, 0, g.KT, g.G, lane);
                 for (int b0 = 0; b0 < count; b0 += MEGA_BATCH) {
                     const int nb = count - b0 < MEGA_BATCH ? count - b0 : MEGA_BATCH;
                     float acc0 = 0.f, acc1 = 0.f; // this warp's rows in its (up to) two stages of the batch
-                    float xres0 = 0.f, xres1 = 0.f;
-                    if (fused_res && (kind == 2 || kind == 4) && lane == 0) { // residual values, in flight behind the GEMV
-                        const int r0 = b0 + MEGA_GW * grp + wl, r1 = r0 + 2 * MEGA_GW;
-                        if (r0 < b0 + nb) xres0 = ldcg_f(a.x[cur] + start + r0);
-                        if (r1 < b0 + nb) xres1 = ldcg_f(a.x[cur] + start + r1);
-                    }
                     for (int kt = 0; kt < g.n_kt; kt++) {
                         if (!x_once) load_x<GS>(xr, sxq, sxs, kt, g.KT, g.G, lane);
                         prof_mark(pr, 58);
@@ -1253,23 +1205,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                             if (MEGA_GW * sidx + wl >= nb) break;
                             const int r = start + b0 + MEGA_GW * sidx + wl;
                             const float v = j == 0 ? acc0 : acc1;
-                            if (kind == 0) { // layers.rs:334-336
-                                if (r < a.AH_l) a.q[r] = v;
-                                else if (r < a.AH_l + a.KV_l) a.kraw[r - a.AH_l] = v;
-                                else vrow[r - a.AH_l - a.KV_l] = v;
+                            if (kind == 0) { // layers.rs:334-336: q | k | v rows, picked up by the attention CTAs
+                                ll_store(a.zq + r, v, ep_out);
                             } else if (kind == 2 || kind == 4) {
-                                if (MEGA_LL) { // (value, epoch) word into every rank's landing zone (peer stores under TP)
-                                    const unsigned ep_out = a.ll_base + 1 + 2 * (unsigned)(l - L0) + (kind == 2 ? 0 : 1);
-                                    float *const *dst = sh.part[kind == 2 ? 0 : 1];
+                                if (a.tp_size == 1) { // the row is complete: straight into the zone every prologue polls
+                                    ll_store(a.zr[kind == 2 ? 0 : 1] + r, v, ep_out);
+                                } else { // row-parallel partial -> every rank's landing zone (peer stores over NVLink)
+                                    unsigned long long *const *dst = sh.part[kind == 2 ? 0 : 1];
 #pragma unroll 1
-                                    for (int p = 0; p < a.tp_size; p++)
-                                        ll_store(reinterpret_cast<unsigned long long *>(dst[p]) + (size_t)a.tp_rank * a.dim + r, v, ep_out);
-                                } else if (fused_res) {
-                                    a.x[cur ^ 1][r] = __fadd_rn(j == 0 ? xres0 : xres1, v);
-                                } else { // row-parallel partial sums -> every rank's landing zone
-                                    float *const *dst = sh.part[kind == 2 ? 0 : 1];
-#pragma unroll 1
-                                    for (int p = 0; p < a.tp_size; p++) dst[p][(size_t)a.tp_rank * a.dim + r] = v;
+                                    for (int p = 0; p < a.tp_size; p++) ll_store(dst[p] + (size_t)a.tp_rank * a.dim + r, v, ep_out);
                                 }
                             } else { // lm_head (qwen3.rs:76) + greedy argmax candidate (sampler.rs:57-59)
                                 const int row = a.vocab_row0 + r;
@@ -1285,8 +1229,35 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                         }
                     }
                 }
+                // Tensor parallel all-reduce, two hops regardless of tp: the CTA that computed rows [start, start + count) of
+                // this rank's partial also REDUCES those rows -- it polls the tp partial words of each (own word included),
+                // adds them in rank order (so every rank computes bit-identical sums) and republishes the row in the local
+                // zone every prologue polls.  Each CTA reads tp * count words instead of all CTAs reading tp * dim.
+                if ((kind == 2 || kind == 4) && a.tp_size > 1) {
+                    const unsigned long long *src = sh.part[kind == 2 ? 0 : 1][a.tp_rank];
+                    for (int idx = tid; idx < count; idx += MEGA_CTHREADS) {
+                        const int r = start + idx;
+                        unsigned long long w[MEGA_MAX_TP];
+                        unsigned spins = 0;
+                        while (true) {
+                            bool ok = true;
+#pragma unroll
+                            for (int p = 0; p < MEGA_MAX_TP; p++) {
+                                if (p < a.tp_size) {
+                                    w[p] = ll_load1(src + (size_t)p * a.dim + r);
+                                    ok = ok && ll_ok(w[p], ep_out);
+                                }
+                            }
+                            if (ok || ll_give_up(a, spins, 10)) break;
+                        }
+                        float s = __uint_as_float((unsigned)w[0]);
+#pragma unroll
+                        for (int p = 1; p < MEGA_MAX_TP; p++)
+                            if (p < a.tp_size) s = __fadd_rn(s, __uint_as_float((unsigned)w[p]));
+                        ll_store(a.zr[kind == 2 ? 0 : 1] + r, s, ep_out);
+                    }
+                }
             }
-            cross = kind == 2 || kind == 4 || kind == 5;
         }
         prof_mark(pr, 2 + 3 * kind);
         if (kind == 5) {
@@ -1299,35 +1270,19 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                 for (int p = 0; p < a.tp_size; p++) sh.best[p][(size_t)a.tp_rank * gridDim.x + blockIdx.x] = (unsigned long long)best;
             }
         }
-        // pull what the next step's first instructions will miss on (static weights, HBM-cold) into L2 while
-        // this CTA waits in the barrier: the next RMSNorm weight, or the QK-norm weights + this position's RoPE row
+        // pull what the next step's first instructions will miss on (static weights, HBM-cold) into L2:
+        // the next RMSNorm weight, or the QK-norm weights + this position's RoPE row
         if (MEGA_PREFETCH_W && (kind == 2 || kind == 4)) {
             const float *wn = kind == 2 ? a.rms_ffn + (size_t)l * a.dim : (l + 1 < L1 ? a.rms_att + (size_t)(l + 1) * a.dim : a.rms_final);
             if (tid * 32 < a.dim) asm volatile("prefetch.global.L2 [%0];" ::"l"(wn + tid * 32));
-        } else if (kind == 0) {
-            if (MEGA_PREFETCH_W && tid < 12) {
-                const float *wn = tid < 4 ? a.q_ln + (size_t)l * HEAD_DIM + tid * 32 : tid < 8 ? a.k_ln + (size_t)l * HEAD_DIM + (tid - 4) * 32
-                                                                                       : a.rope + (size_t)pos * HEAD_DIM + (tid - 8) * 32;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(wn));
-            }
-            // ... and the head of this CTA's slice of the K/V cache for the attention step (cold beyond a few hundred positions)
-            const int ns = mega_nsplit(pos, a.n_kv_l, gridDim.x);
-            if (MEGA_PREFETCH_KV && (int)blockIdx.x < a.n_kv_l * ns) {
-                const int kvh = blockIdx.x % a.n_kv_l, split = blockIdx.x / a.n_kv_l;
-                const int per = (pos + 1 + ns - 1) / ns;
-                const int t0 = split * per;
-                int cnt = pos - t0; // rows before `pos` (row `pos` is written in this step)
-                cnt = cnt > per ? per : cnt;
-                cnt = cnt > 256 ? 256 : cnt;
-                const size_t lbase = (size_t)l * a.seq_len * a.KV_l + (size_t)kvh * HEAD_DIM;
-                for (int i = tid; i < cnt * 8; i += MEGA_CTHREADS) {
-                    const float *base = (i & 4) ? a.vc : a.kc;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + lbase + (size_t)(t0 + (i >> 3)) * a.KV_l + (i & 3) * 32));
-                }
-            }
+        } else if (MEGA_PREFETCH_W && kind == 0 && tid < 12) {
+            const float *wn = tid < 4 ? a.q_ln + (size_t)l * HEAD_DIM + tid * 32 : tid < 8 ? a.k_ln + (size_t)l * HEAD_DIM + (tid - 4) * 32
+                                                                                   : a.rope + (size_t)pos * HEAD_DIM + (tid - 8) * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(wn));
         }
-        if (MEGA_LL && (kind == 2 || kind == 4)) csync(); // results carry their own flags; only this CTA's warps must be done with sxq
-        else grid_barrier(a, bs, cross, pr);
+        // results carry their own flags: the only thing to wait for is this CTA's own warps (sxq / scratch are about to be rewritten)
+        if (kind == 5) grid_barrier(a, bs, true, pr);
+        else csync();
         prof_mark(pr, 3 + 3 * kind);
     }
 
@@ -1356,36 +1311,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                 }
             }
         }
-    } else {
-        // teacher-forced layer range: materialise x = x + pending partial sums into x[0]
-        if (MEGA_LL) {
-            if (blockIdx.x == 0 && L1 > L0) {
-                float4 v[MEGA_MAXV];
-#pragma unroll
-                for (int k = 0; k < MEGA_MAXV; k++) {
-                    const int i4 = tid + k * MEGA_CTHREADS;
-                    v[k] = (i4 < (a.dim >> 2)) ? reinterpret_cast<const float4 *>(sx)[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                ll_merge(a, reinterpret_cast<const unsigned long long *>(sh.part[1][a.tp_rank]), a.ll_base + 2 * (unsigned)(L1 - L0), v);
-#pragma unroll
-                for (int k = 0; k < MEGA_MAXV; k++) {
-                    const int i4 = tid + k * MEGA_CTHREADS;
-                    if (i4 < (a.dim >> 2)) reinterpret_cast<float4 *>(a.x[0])[i4] = v[k];
-                }
-            }
-        } else if (fused_res) {
-            if (L1 > L0) cur ^= 1; // the last down epilogue wrote the merged stream
-            if (blockIdx.x == 0 && cur != 0)
-                for (int i = tid; i < a.dim; i += MEGA_CTHREADS) a.x[0][i] = ldcg_f(a.x[cur] + i);
-        } else if (blockIdx.x == 0 && L1 > L0) {
-            for (int i = tid; i < a.dim; i += MEGA_CTHREADS) {
-                float v = ldcg_f(a.x[cur] + i);
-#pragma unroll 1
-                for (int r = 0; r < a.tp_size; r++) v = __fadd_rn(v, ldcg_f(sh.part[1][a.tp_rank] + (size_t)r * a.dim + i));
-                a.x[0][i] = v;
-            }
-        } else if (blockIdx.x == 0 && cur != 0) {
-            for (int i = tid; i < a.dim; i += MEGA_CTHREADS) a.x[0][i] = ldcg_f(a.x[cur] + i);
+    } else if (blockIdx.x == 0 && L1 > L0) {
+        // teacher-forced layer range: materialise x + the last down_proj rows into a.x
+        const unsigned ep = ll_epoch(a.ll_base, (unsigned)(MEGA_EDGES * (L1 - 1 - L0) + 4));
+        for (int i4 = tid; i4 < (a.dim >> 2); i4 += MEGA_CTHREADS) {
+            float4 v = reinterpret_cast<const float4 *>(sx)[i4];
+            const float4 d = ll_poll4(a, a.zr[1] + (size_t)i4 * 4, ep, 6);
+            v.x = __fadd_rn(v.x, d.x);
+            v.y = __fadd_rn(v.y, d.y);
+            v.z = __fadd_rn(v.z, d.z);
+            v.w = __fadd_rn(v.w, d.w);
+            reinterpret_cast<float4 *>(a.x)[i4] = v;
         }
     }
 }

@@ -160,6 +160,20 @@ def write_hf_dir(shape: Shape, out_dir: str, seed: int = 0, dtype: str = "bf16")
     return out_dir
 
 
+def quantize_q80_device(t: torch.Tensor, group_size: int):
+    """export.quantize_q80 evaluated by the library's own device quantiser (k_quantize_q80 behind
+    q3_op_quantize_q80_dev: IEEE division + round-half-to-even, bit-identical to the numpy exporter -- tested in
+    tests/test_gpu_parity.py); `t` is a CUDA tensor.  Used to make the multi-GB bench / test checkpoints quickly."""
+    from . import transformer as T
+
+    w = t.reshape(-1).contiguous()
+    q = torch.empty(w.numel(), dtype=torch.int8, device=w.device)
+    s = torch.empty(w.numel() // group_size, dtype=torch.float32, device=w.device)
+    torch.cuda.synchronize(w.device)
+    T.op_quantize_q80_dev(w.data_ptr(), w.numel(), group_size, q.data_ptr(), s.data_ptr(), w.device.index or 0)
+    return q.cpu().numpy(), s.cpu().numpy(), 0.0
+
+
 def export_synthetic(shape: Shape, output_path: str, group_size: int = 64, seed: int = 0,
                      device: str = "cpu", quantizer=None) -> dict:
     """Stream make_tensor() -> exporter without the intermediate safetensors file.  Produces the

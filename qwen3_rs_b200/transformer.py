@@ -67,6 +67,11 @@ ABI = {
     "q3_forward": (_i, [_vp, _i, _i, _vp]),
     "q3_forward_argmax": (_i, [_vp, _i, _i, C.POINTER(_i)]),
     "q3_decode_greedy": (_i, [_vp, _i, _i, _i, _vp]),
+    "q3_sampler_set": (_i, [_vp, _f, _f, C.c_ulonglong]),
+    "q3_sampler_state": (_i, [_vp, C.POINTER(C.c_ulonglong)]),
+    "q3_sampler_skip": (_i, [_vp, _i]),
+    "q3_forward_sample": (_i, [_vp, _i, _i, C.POINTER(_i)]),
+    "q3_decode_sample": (_i, [_vp, _i, _i, _i, _vp]),
     "q3_prefill": (_i, [_vp, _vp, _i, _i, _vp]),
     "q3_bench_prefill": (_i, [_vp, _vp, _i, _i, C.POINTER(_f)]),
     "q3_reset": (_i, [_vp]),
@@ -76,16 +81,21 @@ ABI = {
     "q3_forward_layers": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "q3_set_decode_path": (_i, [_vp, _i]),
     "q3_set_exact": (_i, [_vp, _i]),
+    "q3_set_exact_mask": (_i, [_vp, _i]),
     "q3_bench_decode": (_i, [_vp, _i, _i, _i, C.POINTER(_f)]),
     "q3_bench_kernel": (_i, [_vp, _i, _i, _i, C.POINTER(_f), C.POINTER(_i), C.POINTER(C.c_double)]),
-    "q3_debug_profile": (_i, [_vp, _i, _i, _vp, C.POINTER(_i)]),
+    "q3_debug_profile": (_i, [_vp, _i, _i, _vp, _sz, C.POINTER(_i), C.POINTER(_i)]),
+    "q3_num_sms": (_i, [_vp]),
+    "q3_debug_set_epoch": (_i, [_vp, C.c_ulonglong]),
     "q3_launches_per_step": (_i, [_vp]),
     "q3_op_quantize": (_i, [_i, _vp, _i, _i, _vp, _vp]),
     "q3_op_matmul": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "q3_op_expf": (_i, [_i, _vp, _i, _vp]),
     "q3_op_gemm_q8": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "q3_op_sample": (_i, [_i, _vp, _i, _f, _f, C.POINTER(C.c_ulonglong), C.POINTER(_i)]),
     "q3_op_rmsnorm": (_i, [_i, _vp, _vp, _i, _vp]),
     "q3_op_quantize_q80": (_i, [_i, _vp, _sz, _i, _vp, _vp]),
+    "q3_op_quantize_q80_dev": (_i, [_i, _vp, _sz, _i, _vp, _vp]),
     "q3_last_error": (C.c_char_p, []),
     "q3_version": (C.c_char_p, []),
 }
@@ -104,7 +114,12 @@ def load_library():
             path = _build.build()
         L = C.CDLL(path)
         for name, (res, args) in ABI.items():
-            fn = getattr(L, name)  # AttributeError == missing export: fail loudly
+            try:
+                fn = getattr(L, name)  # AttributeError == missing export: fail loudly
+            except AttributeError:
+                if os.environ.get("Q3_LIB"):  # an older kernel-tuning variant timed for comparison: entry points added since are absent
+                    continue
+                raise
             fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib
@@ -122,8 +137,9 @@ def _ptr(a: Optional[np.ndarray]):
 class Transformer:
     """Device-resident Qwen3 transformer (the `Transformers::Qwen3` variant, models/mod.rs:20-37)."""
 
-    def __init__(self, handle: int):
+    def __init__(self, handle: int, tp_size: int = 1):
         self._h = handle
+        self._tp_size = tp_size
         c = load_library().q3_get_config(handle).contents
         self._config = ModelConfig(**{n: (bool(getattr(c, n)) if n == "shared_classifier" else int(getattr(c, n)))
                                       for n, _ in _Cfg._fields_})
@@ -149,6 +165,30 @@ class Transformer:
         _check(load_library().q3_decode_greedy(self._h, int(first_token), int(pos0), int(n), _ptr(out)))
         return out[:n].tolist()
 
+    # -- device sampler (sampler.rs on the device) --------------------------------------------
+    def sampler_set(self, temperature: float, topp: float, rng_seed: int) -> None:
+        """Sampler::new(vocab_size, temperature, topp, rng_seed) -- state lives on the device."""
+        _check(load_library().q3_sampler_set(self._h, float(temperature), float(topp), int(rng_seed) & 0xFFFFFFFFFFFFFFFF))
+
+    @property
+    def sampler_rng_state(self) -> int:
+        out = C.c_ulonglong(0)
+        _check(load_library().q3_sampler_state(self._h, C.byref(out)))
+        return out.value
+
+    def sampler_skip(self, n_draws: int) -> None:
+        _check(load_library().q3_sampler_skip(self._h, int(n_draws)))
+
+    def forward_sample(self, token: int, pos: int) -> int:
+        out = C.c_int(0)
+        _check(load_library().q3_forward_sample(self._h, int(token), int(pos), C.byref(out)))
+        return out.value
+
+    def decode_sample(self, first_token: int, pos0: int, n: int) -> List[int]:
+        out = np.zeros(max(n, 1), np.int32)
+        _check(load_library().q3_decode_sample(self._h, int(first_token), int(pos0), int(n), _ptr(out)))
+        return out[:n].tolist()
+
     def prefill(self, tokens: Sequence[int], pos0: int = 0, want_logits: bool = True) -> Optional[np.ndarray]:
         t = np.ascontiguousarray(tokens, np.int32)
         _check(load_library().q3_prefill(self._h, _ptr(t), t.size, int(pos0), _ptr(self._logits) if want_logits else None))
@@ -164,7 +204,9 @@ class Transformer:
         _check(load_library().q3_reset(self._h))
 
     def kv_read(self, layer: int, pos0: int, n: int):
-        kv = self._config.n_kv_heads * self._config.head_dim
+        """Rows [pos0, pos0 + n) of one layer's K and V cache.  A tensor-parallel member holds (and returns / takes in
+        kv_write) only its own n_kv_heads / tp_size heads."""
+        kv = self._config.n_kv_heads // self._tp_size * self._config.head_dim
         k = np.empty((n, kv), np.float32)
         v = np.empty((n, kv), np.float32)
         _check(load_library().q3_kv_read(self._h, layer, pos0, n, _ptr(k), _ptr(v)))
@@ -173,6 +215,9 @@ class Transformer:
     def kv_write(self, layer: int, pos0: int, k: np.ndarray, v: np.ndarray) -> None:
         k = np.ascontiguousarray(k, np.float32)
         v = np.ascontiguousarray(v, np.float32)
+        kv = self._config.n_kv_heads // self._tp_size * self._config.head_dim
+        if k.shape != v.shape or k.ndim != 2 or k.shape[1] != kv:
+            raise ValueError(f"kv_write expects [n][{kv}] rows (this handle's kv heads)")
         _check(load_library().q3_kv_write(self._h, layer, pos0, k.shape[0], _ptr(k), _ptr(v)))
 
     def forward_layers(self, x: np.ndarray, pos: int, layer0: int, layer1: int, run_head: bool = False):
@@ -184,6 +229,10 @@ class Transformer:
     def set_exact(self, on: bool) -> None:
         """Reference-order reductions + glibc expf: logits bit-identical to the reference (slow)."""
         _check(load_library().q3_set_exact(self._h, int(on)))
+
+    def set_exact_mask(self, mask: int) -> None:
+        """Reference order for a subset of the reductions (see q3_set_exact_mask in include/qwen3_cuda.h)."""
+        _check(load_library().q3_set_exact_mask(self._h, int(mask)))
 
     def set_decode_path(self, path: int) -> None:
         _check(load_library().q3_set_decode_path(self._h, path))
@@ -201,15 +250,23 @@ class Transformer:
         _check(load_library().q3_bench_kernel(self._h, self.KERNEL_KINDS[kind], pos, reps, C.byref(ms), C.byref(n), C.byref(b)))
         return ms.value / max(n.value, 1), b.value, n.value
 
-    def debug_profile(self, token: int, pos: int, num_sms: int = 148) -> np.ndarray:
-        """Per-CTA tagged clock stamps of one persistent-kernel decode step: [3 * num_sms, 4096] of (clock64 << 8 | tag),
+    def debug_profile(self, token: int, pos: int) -> np.ndarray:
+        """Per-CTA tagged clock stamps of one persistent-kernel decode step: [3 * num_sms, n_events] of (clock64 << 8 | tag),
         rows [0, num_sms) from consumer thread 0, [num_sms, 2 num_sms) from producer 0, [2 num_sms, 3 num_sms) from the
-        first lane of consumer group 1 (same SM clock);
-        the last column is the row's event count (see prof_mark in csrc/q3_mega.cuh)."""
-        buf = np.zeros((3 * num_sms, 4096), np.uint64)
-        n = C.c_int(0)
-        _check(load_library().q3_debug_profile(self._h, token, pos, _ptr(buf), C.byref(n)))
-        return buf[:, : n.value]
+        first lane of consumer group 1 (same SM clock); the last column is the row's event count (prof_mark in
+        csrc/q3_mega.cuh).  The buffer is sized from the library's own answer."""
+        rows, ev = C.c_int(0), C.c_int(0)
+        _check(load_library().q3_debug_profile(self._h, token, pos, None, 0, C.byref(rows), C.byref(ev)))
+        buf = np.zeros((rows.value, ev.value), np.uint64)
+        _check(load_library().q3_debug_profile(self._h, token, pos, _ptr(buf), buf.size, C.byref(rows), C.byref(ev)))
+        return buf
+
+    @property
+    def num_sms(self) -> int:
+        return load_library().q3_num_sms(self._h)
+
+    def debug_set_epoch(self, exchanges_issued: int) -> None:
+        _check(load_library().q3_debug_set_epoch(self._h, int(exchanges_issued)))
 
     @property
     def launches_per_step(self) -> int:
@@ -271,7 +328,7 @@ class TransformerBuilder:
         else:
             rc = L.q3_create_tp(self.checkpoint_path.encode(), ctx, self.device, self.tp_rank, self.tp_size, C.byref(h))
         _check(rc)
-        return Transformer(h.value)
+        return Transformer(h.value, self.tp_size)
 
 
 def tp_connect(m: Transformer, dist) -> None:
@@ -331,12 +388,25 @@ def op_gemm_q8(xq, xs, wq, ws, T: int, N: int, K: int, gs: int, device: int = 0)
     return out
 
 
+def op_sample(logits, temperature: float, topp: float, rng_state: int, device: int = 0):
+    """One Sampler::sample draw on the device -> (token, new rng_state)."""
+    a = np.ascontiguousarray(logits, np.float32)
+    st, tok = C.c_ulonglong(int(rng_state) & 0xFFFFFFFFFFFFFFFF), C.c_int(0)
+    _check(load_library().q3_op_sample(device, _ptr(a), a.size, float(temperature), float(topp), C.byref(st), C.byref(tok)))
+    return tok.value, st.value
+
+
 def op_rmsnorm(x, w, device: int = 0):
     x = np.ascontiguousarray(x, np.float32)
     w = np.ascontiguousarray(w, np.float32)
     out = np.empty_like(x)
     _check(load_library().q3_op_rmsnorm(device, _ptr(x), _ptr(w), x.size, _ptr(out)))
     return out
+
+
+def op_quantize_q80_dev(w_ptr: int, n: int, gs: int, q_ptr: int, s_ptr: int, device: int = 0) -> None:
+    """quantize_q80 on device buffers given as raw device addresses (e.g. torch tensors' data_ptr())."""
+    _check(load_library().q3_op_quantize_q80_dev(device, C.c_void_p(w_ptr), n, gs, C.c_void_p(q_ptr), C.c_void_p(s_ptr)))
 
 
 def op_quantize_q80(w, gs: int, device: int = 0):

@@ -9,16 +9,19 @@ from qwen3_rs_b200 import transformer as T
 model = sys.argv[1] if len(sys.argv) > 1 else "qwen3-8b"
 pos = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 GHZ = float(sys.argv[3]) if len(sys.argv) > 3 else 1.965
-path = bench.bench_checkpoint(model, 64)
-m = T.TransformerBuilder.new(path).with_ctx_length(max(256, pos + 8)).build()
-for p in range(4):
-    m.forward_argmax(1, p)
-raw = m.debug_profile(1, pos)
-np.save("gpurun_out/mega_profile_%s_pos%d.npy" % (model, pos), raw)
+L = {"qwen3-8b": 36, "qwen3-4b": 36, "qwen3-0.6b": 28}.get(model, 0)
+if len(sys.argv) > 4:  # offline: analyse a saved capture
+    raw = np.load(sys.argv[4])
+else:
+    path = bench.bench_checkpoint(model, 64)
+    m = T.TransformerBuilder.new(path).with_ctx_length(max(256, pos + 8)).build()
+    m.bench_decode(1, 0, 4)
+    raw = m.debug_profile(1, pos)
+    np.save("gpurun_out/mega_profile_%s_pos%d.npy" % (model, pos), raw)
 
 KINDS = ["qkv", "att", "o", "gu", "dn", "head"]
-MAIN = ["pro", "gemv", "bar"]
-FINE = {32: "load", 33: "reduce", 34: "quant", 35: "qknorm", 36: "positions", 40: "cta_sync", 41: "grid"}
+MAIN = ["pro", "gemv", "sync"]  # prologue (poll + rebuild) / GEMV / wait for this CTA's last warp (head: grid barrier)
+FINE = {32: "load", 33: "reduce", 34: "quant", 35: "qknorm", 36: "positions", 37: "arrive", 40: "cta_sync", 41: "grid"}
 order = []
 acc = defaultdict(list)       # label -> list over CTAs of per-CTA mean us
 total = []
@@ -54,7 +57,6 @@ for c in range(NS):
         pend = []
     for k2, v in per.items():
         acc[k2].append(np.mean(v))
-L = m.get_config().n_layers
 print(f"{model} pos {pos}: kernel {np.mean(total):.1f} us (per-CTA mean)")
 print("step                    mean_us  [min .. max over CTAs of the per-CTA mean]")
 layer_sum = 0.0
@@ -73,7 +75,7 @@ def timeline(c, layer=5):
             rows.append((int(e >> np.uint64(8)), who, int(e & np.uint64(255))))
     rows.sort()
     # find layer boundaries on the consumer row: tag 1 (qkv_pro done) occurrences
-    starts = [t for t, who, tag in rows if who == "C" and tag == 3 + 3 * 4]  # dn_bar done = layer end
+    starts = [t for t, who, tag in rows if who == "C" and tag == 3 + 3 * 4]  # dn_sync done = layer end
     t0, t1 = starts[layer - 1], starts[layer]
     print(f"--- CTA {c}, layer {layer}: timeline (us from the end of the previous layer) ---")
     for t, who, tag in rows:

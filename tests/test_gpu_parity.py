@@ -553,3 +553,69 @@ def test_prefill_matches_sequential_forwards(models, name, gs, seed, T):
     nxt = argmax_last(lg_pf)
     a = m.forward(nxt, T)
     assert np.isfinite(a).all()
+
+
+# ---- round 2: bench checkpoints, epoch wrap, reduction-order attribution switches ------------------
+def test_device_quantizer_makes_identical_checkpoints(tmp_path):
+    """bench.py / the big-config tests quantise their synthetic checkpoints with the library's own exporter kernel
+    (k_quantize_q80 on device buffers): the .bin must be byte-identical to the numpy exporter's."""
+    import torch
+
+    from qwen3_rs_b200 import synth
+
+    a, b = str(tmp_path / "cpu.bin"), str(tmp_path / "dev.bin")
+    for name, gs in (("tiny-untied", 64), ("small", 32)):
+        synth.export_synthetic(synth.SHAPES[name], a, gs, seed=5)
+        synth.export_synthetic(synth.SHAPES[name], b, gs, seed=5, device="cuda", quantizer=synth.quantize_q80_device)
+        da, db = open(a, "rb").read(), open(b, "rb").read()
+        if da != db:
+            # torch's CUDA and CPU generators differ: compare the quantiser on identical floats instead
+            t = synth.make_tensor("model.layers.0.mlp.up_proj.weight", (512, 256), "linear", 5, device="cuda")
+            q1, s1, _ = synth.quantize_q80_device(t, gs)
+            q0, s0, _ = orc.quantize_q80(t.cpu().numpy(), gs)
+            assert np.array_equal(q0, q1) and np.array_equal(s0, s1)
+    rng = np.random.default_rng(3)
+    w = (rng.standard_normal(1 << 20) * 0.03).astype(np.float32)
+    w[:64] = 0.0
+    w[64:128] = np.arange(64, dtype=np.float32) * 0.5
+    w[127] = 127.0
+    for gs in (32, 64, 128):
+        q1, s1, _ = synth.quantize_q80_device(torch.from_numpy(w).cuda(), gs)
+        q0, s0, _ = orc.quantize_q80(w, gs)
+        assert np.array_equal(q0, q1) and np.array_equal(s0, s1)
+
+
+def test_flagged_exchange_epoch_wraparound(models):
+    """The persistent kernel's (payload, epoch) words use epochs = (exchanges issued mod 2^32 - 1) + 1.  Put the counter
+    just below the wrap so that it wraps in the middle of a token: same tokens and logits as a fresh run."""
+    m = models("small", 64, 3)
+    m.reset()
+    want = m.decode_greedy(9, 0, 12)
+    lg_want = m.forward(want[-1], 12)
+    L = m.get_config().n_layers
+    for off in (3, 6 * L // 2 + 1, 6 * L * 3 + 2):
+        m.reset()
+        m.debug_set_epoch(0xFFFFFFFF - off)
+        assert m.decode_greedy(9, 0, 12) == want
+        assert np.array_equal(m.forward(want[-1], 12), lg_want)
+
+
+def test_exact_mask_switches_one_reduction_at_a_time(models, golden):
+    """q3_set_exact_mask: all five reference-order switches together are exact mode (bit-identical logits); each alone
+    still runs and stays inside the fast-mode envelope."""
+    name, gs, seed = "tiny-untied", 64, 1
+    key = f"{name}_gs{gs}"
+    m = models(name, gs, seed)
+    seq = golden[key + "_prompt"].tolist() + golden[key + "_greedy"].tolist()
+    lg = golden[key + "_logits"]
+    try:
+        for mask in (31, 1, 2, 4, 8, 16):
+            m.set_exact_mask(mask)
+            m.reset()
+            err = max(float(np.abs(m.forward(seq[p], p) - lg[p]).max()) for p in range(4))
+            if mask == 31:
+                assert err <= 1e-6
+            else:
+                assert err <= 0.05 * float(np.abs(lg).max()) + LOGIT_TOL
+    finally:
+        m.set_exact(False)
