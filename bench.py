@@ -421,10 +421,14 @@ def main():
         m.bench_decode(tok0, p0, min(tps, pos_start - p0))
     tok, p = tok0, pos_start
     e2e_tokens = n_tok
+    if world > 1:
+        # the caller lives on rank 0: it alone receives the full-vocabulary logits (the other ranks push their shard to it and
+        # take the same token from the device argmax -- identical by construction, checked below)
+        m.tp_set_logits_root(0)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_tokens):
-        tok = argmax_last(m.forward(tok, p))
+        tok = argmax_last(m.forward(tok, p)) if rank == 0 else m.forward_argmax(tok, p)
         p += 1
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -432,6 +436,14 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_val = e2e_tokens / e2e_t.item()
+    if world > 1:
+        m.tp_set_logits_root(-1)
+        toks = torch.tensor([tok], dtype=torch.int64, device="cuda")
+        lo, hi = toks.clone(), toks.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if lo.item() != hi.item():
+            raise SystemExit("bench.py: tensor-parallel ranks diverged in the end-to-end loop")
 
     if rank != 0:
         m.close()

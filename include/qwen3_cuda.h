@@ -70,6 +70,12 @@ int q3_tp_export(q3_handle *h, void *blob_out);
 /* blobs: tp_size blobs, rank-major (all-gathered by the host, e.g. torch.distributed). */
 int q3_tp_connect(q3_handle *h, const void *blobs);
 
+/* Tensor parallel: by default q3_forward(logits_host != NULL) returns the full-vocabulary logits on EVERY rank (each
+ * rank pushes its vocabulary shard to all peers).  With a logits root only that rank may ask for logits; the others call
+ * q3_forward(..., NULL) / q3_forward_argmax for the same step and push their shard to the root alone.  root < 0 restores
+ * the default.  Must be set identically on every rank. */
+int q3_tp_set_logits_root(q3_handle *h, int root);
+
 void q3_destroy(q3_handle *h);
 
 /* ---- Transformer::get_config (models/mod.rs:17) ------------------------------------------- */

@@ -107,6 +107,7 @@ struct q3_handle {
     int *d_status = nullptr;  // device abort flag raised by a timed-out wait inside the kernel
     unsigned long long *part_buf[2] = {nullptr, nullptr};            // TP landing zones [tp][dim] (inside xchg: peers write them)
     unsigned long long *zq = nullptr, *za = nullptr, *zh = nullptr, *zr[2] = {nullptr, nullptr}; // local (payload, epoch) zones
+    int logits_root = -1;     // TP: >= 0 = only this rank receives the other ranks' vocabulary shards (q3_tp_set_logits_root)
     bool poisoned = false;    // a wait timed out under tensor parallelism: the ranks' epoch / barrier sequences may have diverged
     unsigned long long *d_best = nullptr, *d_bar = nullptr;
     unsigned int *d_flags = nullptr;
@@ -626,7 +627,9 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
 static int launch_mega(q3_handle *h, int l0, int l1, bool from_embed, bool run_head, bool feedback, bool gather) {
     MegaArgs a = h->margs;
     a.layer0 = l0; a.layer1 = l1; a.from_embed = from_embed; a.run_head = run_head; a.feedback = feedback;
-    a.gather_logits = gather && h->tp_size > 1;
+    // which ranks receive this rank's vocabulary shard: every rank (each caller of q3_forward gets the full logits), or -- when a
+    // logits root is configured -- the root only, on every launch (the ranks need not agree on who asked for logits)
+    a.gather_logits = h->tp_size > 1 ? (h->logits_root >= 0 ? (1 << h->logits_root) : (gather ? (1 << h->tp_size) - 1 : 0)) : 0;
     a.bar_base = h->bar_base;
     a.xbar_base = h->xbar_base;
     if (h->poisoned) return fail(Q3_ECOMM, "tensor-parallel handle is unusable after a timed-out wait (ranks may have diverged): destroy and re-create every rank");
@@ -1133,6 +1136,13 @@ extern "C" int q3_tp_connect(q3_handle *h, const void *blobs) {
     return Q3_OK;
 }
 
+extern "C" int q3_tp_set_logits_root(q3_handle *h, int root) {
+    if (!h) return fail(Q3_EINVAL, "null handle");
+    if (root >= h->tp_size) return fail(Q3_EINVAL, "logits root %d outside the tensor-parallel group of %d", root, h->tp_size);
+    h->logits_root = root < 0 ? -1 : root;
+    return Q3_OK;
+}
+
 extern "C" void q3_destroy(q3_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
@@ -1200,6 +1210,8 @@ extern "C" int q3_forward(q3_handle *h, int token, int pos, float *logits_host) 
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
     if ((rc = set_tok_pos(h, token, pos))) return rc;
+    if (logits_host && h->tp_size > 1 && h->logits_root >= 0 && h->logits_root != h->tp_rank)
+        return fail(Q3_EINVAL, "rank %d asked for logits but the logits root is rank %d", h->tp_rank, h->logits_root);
     if (use_mega(h)) {
         if ((rc = launch_mega(h, 0, h->cfg.n_layers, true, true, false, logits_host != nullptr))) return rc;
     } else {

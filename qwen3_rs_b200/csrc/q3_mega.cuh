@@ -1218,10 +1218,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                             } else { // lm_head (qwen3.rs:76) + greedy argmax candidate (sampler.rs:57-59)
                                 const int row = a.vocab_row0 + r;
                                 sh.logits[a.tp_rank][row] = v;
-                                if (a.gather_logits) {
+                                if (a.gather_logits) { // bit p: rank p wants the full-vocabulary logits (peer stores over NVLink)
 #pragma unroll 1
                                     for (int p = 0; p < a.tp_size; p++)
-                                        if (p != a.tp_rank) sh.logits[p][row] = v;
+                                        if (p != a.tp_rank && ((a.gather_logits >> p) & 1)) sh.logits[p][row] = v;
                                 }
                                 long long key = ((long long)total_key(v) << 32) | (unsigned)row;
                                 best = key > best ? key : best;

@@ -74,6 +74,7 @@ SHAPES: Dict[str, Shape] = {
     "tiny-untied": Shape("tiny-untied", 256, 512, 3, 8, 2, vocab_size=768, max_seq_len=128, tied=False),
     "small": Shape("small", 512, 1536, 4, 8, 4, vocab_size=4096, max_seq_len=512, tied=True),
     "micro": Shape("micro", 128, 384, 2, 2, 1, vocab_size=256, max_seq_len=64, tied=False),
+    "small8": Shape("small8", 512, 2048, 3, 16, 8, vocab_size=4096, max_seq_len=256, tied=False),  # 8 kv heads: tensor parallel up to 8
 }
 
 

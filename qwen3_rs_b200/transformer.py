@@ -62,6 +62,7 @@ ABI = {
     "q3_tp_blob_size": (_sz, []),
     "q3_tp_export": (_i, [_vp, _vp]),
     "q3_tp_connect": (_i, [_vp, _vp]),
+    "q3_tp_set_logits_root": (_i, [_vp, _i]),
     "q3_destroy": (None, [_vp]),
     "q3_get_config": (C.POINTER(_Cfg), [_vp]),
     "q3_forward": (_i, [_vp, _i, _i, _vp]),
@@ -281,6 +282,9 @@ class Transformer:
 
     def tp_connect_blobs(self, blobs: bytes) -> None:
         _check(load_library().q3_tp_connect(self._h, C.create_string_buffer(blobs, len(blobs))))
+
+    def tp_set_logits_root(self, root: int) -> None:
+        _check(load_library().q3_tp_set_logits_root(self._h, int(root)))
 
     def close(self) -> None:
         if getattr(self, "_h", None):

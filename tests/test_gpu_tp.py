@@ -1,5 +1,15 @@
-"""Tensor parallelism on real GPUs: one process per GPU (torch.distributed for the bootstrap only), the
-exchange after o_proj / down_proj fused into the persistent kernel over NVLink peer memory."""
+"""Tensor parallelism on real GPUs: one process per GPU (torch.distributed for the bootstrap only), the exchange after
+o_proj / down_proj fused into the persistent kernel over NVLink peer memory (partial rows pushed to every peer as
+(value, epoch) words, reduced once by the CTA that owns the row).
+
+Every rank is compared with the CPU ORACLE (not with a single-GPU run of this library):
+  * layer by layer, teacher-forced with the oracle's residual stream and this rank's kv heads of the oracle's cache --
+    the same yardstick as the single-GPU fast mode (tests/test_gpu_parity.py::check_layerwise): median at float round-off,
+    worst case within 3x the oracle's own re-association noise, logits from the oracle's final residual within 1e-2;
+  * free running: logits at every position within the fast-mode envelope, greedy tokens equal to the oracle's wherever the
+    oracle's top-2 margin exceeds twice the observed logit error;
+  * the ranks among themselves: bit-identical logits and tokens (the partial rows are added in rank order on every rank).
+The log of the hardware run is committed under profiles/ (r02_tp_tests_hardware.log)."""
 import os
 import socket
 
@@ -7,6 +17,7 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+NPOS = 6
 
 
 def _ngpu():
@@ -30,68 +41,103 @@ def _worker(rank, world, port, path, steps, q):
     import torch
     import torch.distributed as dist
 
-    from qwen3_rs_b200 import transformer as T
-    from qwen3_rs_b200.sampler import argmax_last
-
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         _run(rank, world, path, steps, q, dist)
     except Exception as e:  # noqa: BLE001 -- surface the failure to the parent instead of a queue timeout
-        q.put((rank, {"error": repr(e)}))
+        import traceback
+
+        q.put((rank, {"error": repr(e) + "\n" + traceback.format_exc()}))
     finally:
         dist.destroy_process_group()
 
 
 def _run(rank, world, path, steps, q, dist):
+    from oracle import binding as orc
     from qwen3_rs_b200 import transformer as T
     from qwen3_rs_b200.sampler import argmax_last
 
-    if True:
-        m = T.TransformerBuilder.new(path).with_device(rank).with_tensor_parallel(rank, world).build()
-        T.tp_connect(m, dist)
-        out = {}
-        m.reset()
-        tok, logits = 9, []
-        for pos in range(6):  # forward(): full-vocab logits gathered on every rank
-            lg = m.forward(tok, pos)
-            logits.append(lg)
-            tok = argmax_last(lg)
-        out["logits"] = np.stack(logits)
-        m.reset()
-        out["greedy"] = m.decode_greedy(9, 0, steps)
-        m.reset()
-        out["argmax"] = [m.forward_argmax(9, 0)]
-        ms = m.bench_decode(9, 1, 8)
-        out["ms_per_tok"] = ms / 8
-        q.put((rank, out))
-        dist.barrier()
-        m.close()
+    m = T.TransformerBuilder.new(path).with_device(rank).with_tensor_parallel(rank, world).build()
+    T.tp_connect(m, dist)
+    orc.set_threads(2)
+    o = orc.Model(path)
+    c = o.config
+    hd, nkv = c["head_dim"], c["n_kv_heads"]
+    kv_l = nkv // world * hd
+    out = {}
+    # ---- oracle trajectory ----
+    o.reset()
+    xd = o.dump_residuals()
+    seq, ologits, xdumps = [9], [], []
+    for pos in range(NPOS):
+        lg = o.forward(seq[pos], pos)
+        ologits.append(lg)
+        xdumps.append(xd.copy())
+        seq.append(orc.argmax(lg))
+    ko, vo = o.kv_cache()
+    # ---- layer by layer, teacher-forced (every rank runs the same launches; each holds its own kv heads) ----
+    errs, worst_lg = [], 0.0
+    for pos in range(NPOS):
+        for l in range(c["n_layers"]):
+            ks = ko[l, :pos + 1, rank * (nkv // world):(rank + 1) * (nkv // world)].reshape(pos + 1, kv_l)
+            vs = vo[l, :pos + 1, rank * (nkv // world):(rank + 1) * (nkv // world)].reshape(pos + 1, kv_l)
+            m.kv_write(l, 0, ks, vs)
+        for l in range(c["n_layers"]):
+            x = m.forward_layers(xdumps[pos][l], pos, l, l + 1)
+            errs.append(float(np.abs(x - xdumps[pos][l + 1]).max()) / max(1.0, float(np.abs(xdumps[pos][l + 1]).max())))
+        _, lg = m.forward_layers(xdumps[pos][c["n_layers"]], pos, 0, 0, run_head=True)
+        worst_lg = max(worst_lg, float(np.abs(lg - ologits[pos]).max()))
+    out["layer_errs"], out["head_err"] = np.array(errs), worst_lg
+    # ---- free running ----
+    m.reset()
+    logits = [m.forward(seq[pos], pos) for pos in range(NPOS)]  # full-vocab logits gathered on every rank
+    out["logits"] = np.stack(logits)
+    out["ologits"] = np.stack(ologits) if rank == 0 else None
+    m.reset()
+    out["greedy"] = m.decode_greedy(9, 0, steps)
+    o.reset()
+    if rank == 0:
+        out["ogreedy"], out["omargins"] = o.generate([9], steps, with_margins=True)
+    # logits root: only rank 0 receives the shards; the other ranks take the device argmax of the same step
+    m.reset()
+    m.tp_set_logits_root(0)
+    tok, rooted = 9, []
+    for pos in range(4):
+        tok = argmax_last(m.forward(tok, pos)) if rank == 0 else m.forward_argmax(tok, pos)
+        rooted.append(tok)
+    m.tp_set_logits_root(-1)
+    out["rooted"] = rooted
+    m.reset()
+    out["argmax"] = [m.forward_argmax(9, 0)]
+    # device sampler: the same seed on every rank -> the same tokens
+    m.reset()
+    m.sampler_set(0.9, 0.9, 42)
+    out["sampled"] = m.decode_sample(9, 0, 8)
+    ms = m.bench_decode(9, 1, 16)
+    out["ms_per_tok"] = ms / 16
+    q.put((rank, out))
+    dist.barrier()
+    m.close()
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("name,gs,seed,world", [("tiny-untied", 64, 1, 2), ("small", 64, 3, 2), ("small", 32, 4, 4)])
-def test_tensor_parallel_matches_single_gpu(ckpt, name, gs, seed, world):
+@pytest.mark.parametrize("name,gs,seed,world", [("tiny-untied", 64, 1, 2), ("small", 64, 3, 2), ("small", 32, 4, 4), ("small8", 64, 5, 4),
+                                                ("small8", 64, 5, 8)])
+def test_tensor_parallel_matches_oracle(ckpt, name, gs, seed, world):
     import torch.multiprocessing as mp
 
-    from qwen3_rs_b200 import transformer as T
+    from oracle import binding as orc
+    from qwen3_rs_b200.sampler import argmax_last
+    from test_gpu_parity import OracleAsModel, layerwise_errors
 
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     path = ckpt(name, gs, seed)
     steps = 24
-    ref = T.TransformerBuilder.new(path).build()
-    ref_logits, tok = [], 9
-    from qwen3_rs_b200.sampler import argmax_last
-
-    for pos in range(6):
-        lg = ref.forward(tok, pos)
-        ref_logits.append(lg)
-        tok = argmax_last(lg)
-    ref.reset()
-    ref_greedy = ref.decode_greedy(9, 0, steps)
-    ref.close()
+    # the yardstick: the oracle against itself with re-associated sums
+    ref_x, _ = layerwise_errors(OracleAsModel(orc.Model(path)), orc.Model(path), [9, 3, 5, 7], exact=False)
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -99,21 +145,40 @@ def test_tensor_parallel_matches_single_gpu(ckpt, name, gs, seed, world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, path, steps, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=150) for _ in range(world))
+    got = dict(q.get(timeout=240) for _ in range(world))
     for p in procs:
         p.join(60)
     for r in range(world):
         assert "error" not in got[r], got[r]["error"]
-    # every rank holds the same gathered logits / tokens (x is replicated bit-identically: partial sums
-    # are added in rank order on every rank)
+    # the ranks among themselves: bit-identical
     for r in range(1, world):
         assert np.array_equal(got[r]["logits"], got[0]["logits"])
         assert got[r]["greedy"] == got[0]["greedy"]
-    # vs the single-GPU run: same arithmetic up to the order of the f32 group sums (partials per rank)
-    err = np.abs(got[0]["logits"] - np.stack(ref_logits)).max(axis=1)
-    print(f"{name} tp{world}: max|dlogit| per position {np.array2string(err, precision=2)}; "
-          f"{got[0]['ms_per_tok'] * 1e3:.1f} us/token")
-    assert err[0] <= 0.05 * np.abs(ref_logits[0]).max() + 1e-2
-    assert got[0]["argmax"][0] == argmax_last(ref_logits[0])
-    agree = sum(a == b for a, b in zip(got[0]["greedy"], ref_greedy))
-    assert agree >= steps // 2  # identical unless an int8 flip moved a low-margin step
+        assert got[r]["rooted"] == got[0]["rooted"]
+        assert got[r]["sampled"] == got[0]["sampled"]
+        assert np.array_equal(got[r]["layer_errs"], got[0]["layer_errs"])
+    g = got[0]
+    ol = g["ologits"]
+    # layer by layer against the oracle
+    le = g["layer_errs"]
+    print(f"{name} gs{gs} tp{world}: layerwise |dx|/scale median {np.median(le):.2e} worst {le.max():.2e} (oracle re-association worst {ref_x.max():.2e}); "
+          f"head |dlogit| {g['head_err']:.2e}")
+    assert np.median(le) <= 1e-5
+    assert le.max() <= 3 * ref_x.max() + 1e-3
+    assert g["head_err"] <= 1e-2
+    # free running against the oracle, every position
+    err = np.abs(g["logits"] - ol).max(axis=1)
+    print(f"{name} gs{gs} tp{world}: free-running max|dlogit| per position {np.array2string(err, precision=3)}; {g['ms_per_tok'] * 1e3:.1f} us/token")
+    assert (err <= 0.05 * np.abs(ol).max() + 1e-2).all()
+    for pos in range(NPOS):
+        top2 = np.sort(ol[pos])[-2:]
+        if top2[1] - top2[0] > 2 * err[pos]:
+            assert argmax_last(g["logits"][pos]) == argmax_last(ol[pos])
+    assert g["argmax"][0] == argmax_last(g["logits"][0])
+    assert g["rooted"][0] == g["argmax"][0]
+    # greedy tokens: identical to the oracle's up to the first step whose margin is inside the fast-mode noise
+    worst = float(err.max())
+    for i, (a, b) in enumerate(zip(g["greedy"], g["ogreedy"])):
+        if a != b:
+            assert g["omargins"][i] <= max(4 * worst, 0.05), (i, a, b, float(g["omargins"][i]))
+            break
