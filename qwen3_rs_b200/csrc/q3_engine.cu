@@ -539,6 +539,21 @@ static int build_stream(q3_handle *h, MegaGemv &g, const std::vector<const DevQT
     return 0;
 }
 
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn();
+// K / V cache as a 2-D f32 tensor [n_layers * seq_len rows][KV_l]; box = MEGA_KV_ROWS rows x 128 floats (one kv head), no swizzle
+static int make_map_kv(CUtensorMap *map, const float *base, size_t rows, int KV_l) {
+    auto enc = get_encode_fn();
+    if (!enc) return fail(Q3_ECUDA, "cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)KV_l, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)KV_l * 4};
+    cuuint32_t box[2] = {(cuuint32_t)HEAD_DIM, (cuuint32_t)MEGA_KV_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(Q3_ECUDA, "cuTensorMapEncodeTiled (KV cache) failed (%d) rows %zu KV %d", (int)r, rows, KV_l);
+    return 0;
+}
+
 static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_ffn_all, const float *q_ln_all, const float *k_ln_all) {
     const q3_config &c = h->cfg;
     const int gs = c.group_size, L = c.n_layers, dim = c.dim;
@@ -549,8 +564,14 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
     if (c.vocab_size % h->tp_size) { h->mega_why = "vocab not divisible by tp"; return 0; }
     // zone-reuse safety of the flagged exchanges (q3_mega.cuh): every CTA must own a qkv row and a gate/up unit
     if (h->layers[0].qkv.rows < h->num_sms || h->H_l < h->num_sms) { h->mega_why = "fewer qkv rows / FFN units than SMs"; return 0; }
+    if (!get_encode_fn()) { h->mega_why = "cuTensorMapEncodeTiled unavailable"; return 0; }
     MegaArgs &a = h->margs;
     a = MegaArgs{};
+    {
+        int rck;
+        if ((rck = make_map_kv(&a.map_k, h->kc, (size_t)L * c.seq_len, h->KV_l))) return rck;
+        if ((rck = make_map_kv(&a.map_v, h->vc, (size_t)L * c.seq_len, h->KV_l))) return rck;
+    }
     a.dim = dim; a.n_layers = L; a.n_heads_l = h->n_heads_l; a.n_kv_l = h->n_kv_l; a.AH_l = h->AH_l; a.KV_l = h->KV_l;
     a.H_l = h->H_l; a.seq_len = c.seq_len; a.tp_rank = h->tp_rank; a.tp_size = h->tp_size;
     a.vocab_l = c.vocab_size / h->tp_size;

@@ -8,6 +8,10 @@
 // stays busy while the 16 CONSUMER warps (two groups owning alternate stages) wait on a
 // dependency or rebuild the quantised activation vector.  Consumers keep their slice of the
 // activation vector in registers and do the int8 dot products with dp4a out of shared memory.
+// The K/V cache rows an attention CTA needs travel through the SAME ring (2-D TMA tiles of 32 positions,
+// issued by the producers right behind the QKV weights): they are in shared memory before the
+// attention step starts, and at long context the cache streams at HBM rate instead of at the rate
+// register-held loads can sustain.
 //
 // Dependencies: there is NO grid barrier inside a layer.  Every datum that crosses CTAs travels as a
 // 64-bit (payload, epoch) word (see ll_store) that its consumer polls:
@@ -28,6 +32,8 @@
 // Float semantics are those of the fast multi-kernel path (q3_kernels.cuh): identical per-group
 // terms, parallel reductions.  Exact (reference-order) mode uses the multi-kernel path.
 #pragma once
+#include <cuda.h>
+
 #include "q3_kernels.cuh"
 
 namespace q3 {
@@ -84,7 +90,13 @@ struct MegaGemv {
     int tile_bytes;          // KT + 4*G rounded up to 16 B (bulk copies move 16-byte units)
 };
 
+constexpr int MEGA_KV_ROWS = 32; // cache positions per K/V stage (= MEGA_ATTN_CHUNK): 32 x 512 B of K + 32 x 512 B of V
+
 struct MegaArgs {
+    // TMA descriptors of the K and V caches seen as 2-D f32 tensors [n_layers * seq_len rows][KV_l], box = 32 rows x 128 floats:
+    // one bulk-tensor copy brings 32 consecutive positions of one kv head (16 KB) into a ring stage
+    alignas(64) CUtensorMap map_k;
+    alignas(64) CUtensorMap map_v;
     int dim, n_layers, n_heads_l, n_kv_l, AH_l, KV_l, H_l, vocab_l, vocab_row0, seq_len;
     int tp_rank, tp_size;
     MegaGemv g[5];
@@ -93,7 +105,7 @@ struct MegaArgs {
     const float *embed_s;
     const float *rope;
     float *kc, *vc;
-    float *x;                        // residual stream in / out of a teacher-forced layer range; normed x after the head prologue
+    float *x;                        // residual stream in / out of a teacher-forced layer range (read-only in a head-only launch)
     // (payload, epoch) zones, all zero-initialised; see ll_store
     unsigned long long *zq;          // [AH_l + 2 KV_l]        q | k | v rows of the current layer (raw GEMV results)
     unsigned long long *za;          // [AH_l/4 + AH_l/GS]     quantised attention output (4 int8 per word, PH_O smem order) | group scales
@@ -179,6 +191,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
             smem_u32(dst)),
         "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
 }
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(MEGA_CTHREADS) : "memory"); }
 __device__ __forceinline__ float ldcg_f(const float *p) { return __ldcg(p); }
@@ -404,7 +422,7 @@ constexpr int MEGA_MAXV = (MEGA_MAX_KT + 4 * MEGA_CTHREADS - 1) / (4 * MEGA_CTHR
 // shared memory; a thread always owns the same elements).  zone/epoch: pending GEMV rows to add (or null).
 template <int GS>
 __device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, int src, const unsigned long long *zone, unsigned epoch,
-                                              uint8_t *sxq, float *sxs, float *sred, float *sx, bool write_normed, int KT, int G, Prof &pr) {
+                                              uint8_t *sxq, float *sxs, float *sred, float *sx, int KT, int G, Prof &pr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n4 = a.dim >> 2;
     constexpr int MAXV = MEGA_MAXV;
@@ -506,7 +524,8 @@ __device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, in
             if (i4 < n4) {
                 xq_store<GS>(sxq, i4, packed, KT, G);
                 if ((i4 % (GS / 4)) == 0) sxs[i4 / (GS / 4)] = scale;
-                if (write_normed && blockIdx.x == 0) reinterpret_cast<float4 *>(a.x)[i4] = y;
+                // (the reference's final norm is in place, qwen3.rs:72, but nothing reads x after it; writing it back from one CTA
+                // would race with the other CTAs still reading a.x in a head-only launch)
             }
         }
     }
@@ -669,11 +688,22 @@ __device__ __forceinline__ void publish_head(const MegaArgs &a, int head, int la
 //   * one split: normalise + quantise + publish straight away.  Several splits: partials go to global memory, the split that
 //     arrives LAST at its kv head's counter merges them, and publishes (release: bar.sync + thread 0's fence before its
 //     atomic; acquire: fence after it).
+// ring-side state of a consumer warp (see the kernel): stage counter, parities of its group's full barriers
+struct RingPos {
+    unsigned it, fullp;
+};
+// warps that take part in the position loop: all 16 when their partials fit the scratch area, else one group
+template <int KVMUL>
+struct AttnWarps {
+    static constexpr int N = (KVMUL * MEGA_NCW * 512 + 8192 <= MEGA_SCRATCH) ? MEGA_NCW : MEGA_GW;
+};
+
 template <int GS, int KVMUL>
 __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int pos, int kvh, int split, int nsplit,
-                                               uint8_t *scratch, unsigned ep_q, unsigned ep_a, Prof &pr) {
+                                               uint8_t *scratch, unsigned ep_q, unsigned ep_a, Prof &pr, RingPos &rp, uint32_t ring_s, int slot_bytes,
+                                               uint64_t *myfull, uint64_t *empty) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NATT = (KVMUL * MEGA_NCW * 512 + 8192 <= MEGA_SCRATCH) ? MEGA_NCW : MEGA_GW; // warps in the position loop
+    constexpr int NATT = AttnWarps<KVMUL>::N; // warps in the position loop
     float4 *sq = reinterpret_cast<float4 *>(scratch);                 // [KVMUL][32]
     float4 *sk = sq + KVMUL * 32;                                     // [32]
     float4 *sv = sk + 32;                                             // [32]
@@ -726,53 +756,80 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
         l[h] = 0.0f;
         acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float *kbase = kc_l + (size_t)kvh * HEAD_DIM + lane * 4;
-    const float *vbase = vc_l + (size_t)kvh * HEAD_DIM + lane * 4;
-    // NP positions per iteration: all 2 NP K/V row loads are in flight before any is used
-    constexpr int NP = MEGA_ATTN_NP;
-    for (int t = t0 + warp; t < t1 && warp < NATT; t += NP * NATT) {
-        float4 kv[NP], vv[NP];
+    // The cache rows t0 .. t1 of this kv head arrive through the weight ring: stages of MEGA_KV_ROWS positions (K tile, then V
+    // tile, 16 KB each, [position][128] f32), issued by the producers behind the QKV weights -- normally they are already in
+    // shared memory here.  Stages alternate between the consumer groups like weight stages (all of them to group 0 when only
+    // one group's partials fit the scratch area); inside a stage warp w of the group owns positions 4w .. 4w+3.
+    // Row `pos` itself is not in the cache yet when its tile is fetched: it is taken from sk / sv.
+    constexpr int NP = 2; // positions per pass
+    const int grp = warp / MEGA_GW, wl = warp % MEGA_GW;
+    const int nst = (t1 - t0 + MEGA_KV_ROWS - 1) / MEGA_KV_ROWS;
+    for (int st = 0; st < nst; st++) {
+        const int owner = NATT == MEGA_NCW ? (st & 1) : 0;
+        if (owner == grp) {
+            const int slot = rp.it % MEGA_NSTAGE;
+            mbar_wait(&myfull[slot], (rp.fullp >> slot) & 1, a.status);
+            rp.fullp ^= 1u << slot;
+            const uint32_t kb = ring_s + slot * slot_bytes + lane * 16, vb = kb + MEGA_KV_ROWS * HEAD_DIM * 4;
+#pragma unroll 1
+            for (int half = 0; half < 4 / NP; half++) {
+                const int r0 = wl * 4 + half * NP; // row inside the stage
+                const int t = t0 + st * MEGA_KV_ROWS + r0;
+                float4 kv[NP], vv[NP];
 #pragma unroll
-        for (int j = 0; j < NP; j++) {
-            const int tj = t + j * NATT;
-            kv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            vv[j] = kv[j];
-            if (tj < t1) {
-                kv[j] = (tj == pos) ? sk[lane] : ldcg_f4(kbase + (size_t)tj * a.KV_l);
-                vv[j] = (tj == pos) ? sv[lane] : ldcg_f4(vbase + (size_t)tj * a.KV_l);
+                for (int j = 0; j < NP; j++) {
+                    const int tj = t + j;
+                    kv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    vv[j] = kv[j];
+                    if (tj < t1) {
+                        if (tj == pos) {
+                            kv[j] = sk[lane];
+                            vv[j] = sv[lane];
+                        } else {
+                            const int4 ki = lds128(kb + (r0 + j) * HEAD_DIM * 4), vi = lds128(vb + (r0 + j) * HEAD_DIM * 4);
+                            kv[j] = make_float4(__int_as_float(ki.x), __int_as_float(ki.y), __int_as_float(ki.z), __int_as_float(ki.w));
+                            vv[j] = make_float4(__int_as_float(vi.x), __int_as_float(vi.y), __int_as_float(vi.z), __int_as_float(vi.w));
+                        }
+                    }
+                }
+                if (t < t1) { // warp-uniform
+                    float sc[NP][KVMUL];
+#pragma unroll
+                    for (int j = 0; j < NP; j++)
+#pragma unroll
+                        for (int h = 0; h < KVMUL; h++) sc[j][h] = qv[h].x * kv[j].x + qv[h].y * kv[j].y + qv[h].z * kv[j].z + qv[h].w * kv[j].w;
+#pragma unroll
+                    for (int j = 0; j < NP; j++)
+#pragma unroll
+                        for (int h = 0; h < KVMUL; h++) sc[j][h] = (t + j < t1) ? __fmul_rn(warp_sum(sc[j][h]), scale) : -INFINITY;
+#pragma unroll
+                    for (int h = 0; h < KVMUL; h++) {
+                        float mn = m[h];
+#pragma unroll
+                        for (int j = 0; j < NP; j++) mn = fmaxf(mn, sc[j][h]);
+                        const float corr = expf(m[h] - mn);
+                        l[h] *= corr;
+                        acc[h].x *= corr;
+                        acc[h].y *= corr;
+                        acc[h].z *= corr;
+                        acc[h].w *= corr;
+#pragma unroll
+                        for (int j = 0; j < NP; j++) {
+                            const float pj = expf(sc[j][h] - mn); // exp(-inf) = 0 for the positions past the end
+                            l[h] += pj;
+                            acc[h].x += pj * vv[j].x;
+                            acc[h].y += pj * vv[j].y;
+                            acc[h].z += pj * vv[j].z;
+                            acc[h].w += pj * vv[j].w;
+                        }
+                        m[h] = mn;
+                    }
+                }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
         }
-        float sc[NP][KVMUL];
-#pragma unroll
-        for (int j = 0; j < NP; j++)
-#pragma unroll
-            for (int h = 0; h < KVMUL; h++) sc[j][h] = qv[h].x * kv[j].x + qv[h].y * kv[j].y + qv[h].z * kv[j].z + qv[h].w * kv[j].w;
-#pragma unroll
-        for (int j = 0; j < NP; j++)
-#pragma unroll
-            for (int h = 0; h < KVMUL; h++) sc[j][h] = (t + j * NATT < t1) ? __fmul_rn(warp_sum(sc[j][h]), scale) : -INFINITY;
-#pragma unroll
-        for (int h = 0; h < KVMUL; h++) {
-            float mn = m[h];
-#pragma unroll
-            for (int j = 0; j < NP; j++) mn = fmaxf(mn, sc[j][h]);
-            const float corr = expf(m[h] - mn);
-            l[h] *= corr;
-            acc[h].x *= corr;
-            acc[h].y *= corr;
-            acc[h].z *= corr;
-            acc[h].w *= corr;
-#pragma unroll
-            for (int j = 0; j < NP; j++) {
-                const float pj = expf(sc[j][h] - mn); // exp(-inf) = 0 for the positions past the end
-                l[h] += pj;
-                acc[h].x += pj * vv[j].x;
-                acc[h].y += pj * vv[j].y;
-                acc[h].z += pj * vv[j].z;
-                acc[h].w += pj * vv[j].w;
-            }
-            m[h] = mn;
-        }
+        rp.it++;
     }
     prof_mark(pr, 36); // position loop done
     if (warp < NATT) {
@@ -1035,6 +1092,42 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
             prof_mark(pr, 64 + slot);
             it++;
         };
+        // K/V cache tiles of this CTA's attention item (kv head, split) for `layer`: same slots, same handshake as weight stages
+        const int ppos = a.tokpos[1];
+        const int pns = mega_nsplit(ppos, a.n_kv_l, gridDim.x);
+        const bool has_item = (int)blockIdx.x < a.n_kv_l * pns;
+        const int pkvh = blockIdx.x % a.n_kv_l, psplit = blockIdx.x / a.n_kv_l;
+        const int pper = (ppos + 1 + pns - 1) / pns;
+        const int pt0 = psplit * pper, pt1 = pt0 + pper < ppos + 1 ? pt0 + pper : ppos + 1;
+        auto kvpush = [&](int layer) {
+            if (!has_item) return;
+            for (int t = pt0, si = 0; t < pt1; t += MEGA_KV_ROWS, si++) {
+                const int owner = AttnWarps<KVMUL>::N == MEGA_NCW ? (si & 1) : 0;
+                if (owner != pw) {
+                    it++;
+                    continue;
+                }
+                const int slot = it % MEGA_NSTAGE;
+                {
+                    const unsigned use = it / MEGA_NSTAGE;
+                    long long tw = clock64();
+                    while (issued[slot] != use) {
+                        if (MEGA_PSLEEP) __nanosleep(MEGA_PSLEEP);
+                        if (clock64() - tw > 4000000000LL) { atomicExch(a.status, 4); break; }
+                    }
+                }
+                mbar_wait(&empty[slot], ((it / MEGA_NSTAGE) & 1) ^ 1, a.status);
+                uint64_t *fb = &full[owner * MEGA_NSTAGE + slot];
+                uint8_t *dst = ring + (size_t)slot * slot_bytes;
+                mbar_expect_tx(fb, 2 * MEGA_KV_ROWS * HEAD_DIM * 4);
+                tma_load_2d(dst, &a.map_k, pkvh * HEAD_DIM, layer * a.seq_len + t, fb);
+                tma_load_2d(dst + MEGA_KV_ROWS * HEAD_DIM * 4, &a.map_v, pkvh * HEAD_DIM, layer * a.seq_len + t, fb);
+                __threadfence_block();
+                issued[slot] = it / MEGA_NSTAGE + 1;
+                prof_mark(pr, 64 + slot);
+                it++;
+            }
+        };
         auto plain = [&](int ph, int layer) {
             const MegaGemv &g = a.g[ph];
             PhaseGeom pg = phase_geom(a, sh, ph, layer);
@@ -1063,6 +1156,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
         };
         for (int l = L0; l < L1; l++) {
             plain(PH_QKV, l);
+            kvpush(l);
             plain(PH_O, l);
             pairs(l);
             plain(PH_DN, l);
@@ -1116,12 +1210,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
             ph = kind == 0 ? PH_QKV : kind == 3 ? PH_GU : PH_HEAD;
             // rows being consumed: o_proj of this layer (kind 3) or down of the previous / last layer
             const unsigned ep_rows = kind == 3 ? ep_prev : ll_epoch(a.ll_base, (unsigned)(MEGA_EDGES * ((kind == 0 ? l - 1 : L1 - 1) - L0) + 4));
-            prologue_norm<GS>(a, w, emb ? 0 : (pending ? 2 : 1), pending ? a.zr[kind == 3 ? 0 : 1] : nullptr, ep_rows, sxq, sxs, sred, sx, kind == 5,
+            prologue_norm<GS>(a, w, emb ? 0 : (pending ? 2 : 1), pending ? a.zr[kind == 3 ? 0 : 1] : nullptr, ep_rows, sxq, sxs, sred, sx,
                               a.g[ph].KT, a.g[ph].G, pr);
         } else if (kind == 1) {
             // QK-norm + RoPE + attention (layers.rs:339-343) + quantize (qwen3.rs:152) on the CTAs that own a (kv head, split) item
-            if ((int)blockIdx.x < a.n_kv_l * nsplit)
-                attention_item<GS, KVMUL>(a, l, pos, blockIdx.x % a.n_kv_l, blockIdx.x / a.n_kv_l, nsplit, scratch, ep_prev, ep_step, pr);
+            if ((int)blockIdx.x < a.n_kv_l * nsplit) {
+                RingPos rp{it, fullp};
+                attention_item<GS, KVMUL>(a, l, pos, blockIdx.x % a.n_kv_l, blockIdx.x / a.n_kv_l, nsplit, scratch, ep_prev, ep_step, pr, rp,
+                                          smem_u32(ring), slot_bytes, myfull, empty);
+                it = rp.it;
+                fullp = rp.fullp;
+            }
         } else if (kind == 2) {
             prologue_attn_poll<GS>(a, ep_prev, sxq, sxs);
             ph = PH_O;

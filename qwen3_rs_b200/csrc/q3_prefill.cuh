@@ -45,12 +45,6 @@ struct PrefillGemmArgs {
     int AH, KV, pos0;
 };
 
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-                 : "memory");
-}
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
     // K-major, SWIZZLE_128B: 8-row atoms of 128 B, atoms 1024 B apart (SBO), LBO unused (=1), version 1
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ULL << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46) | (2ULL << 61);
