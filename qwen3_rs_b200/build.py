@@ -37,11 +37,17 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     target = out or LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, *["-D" + d for d in defines], "-o", target, *[os.path.join(CSRC, s) for s in SOURCES]]
+    tmp = target + f".tmp{os.getpid()}"  # link next to the target, then rename: a reader never sees a half-written library
+    cmd = [_nvcc(), *NVCC_FLAGS, *["-D" + d for d in defines], "-o", tmp, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)
-    subprocess.check_call(cmd)
+    try:
+        subprocess.check_call(cmd)
+        os.replace(tmp, target)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return target
 
 

@@ -123,6 +123,7 @@ struct q3_handle {
     // batched prefill (tcgen05 GEMM) state
     bool pf_ok = false;
     std::string pf_why;
+    bool pf_attn_f32 = false; // Q3_PF_ATTN_F32=1: the CUDA-core f32 attention instead of the tensor-core one (comparison)
     int pf_cap = 0;          // token capacity of the buffers below (multiple of 128)
     float *pf_x = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_hb = nullptr, *pf_xsT = nullptr, *pf_hsT = nullptr;
     int8_t *pf_xq = nullptr, *pf_hq = nullptr;
@@ -770,21 +771,30 @@ static int make_map_i8(CUtensorMap *map, const void *base, int rows, int K) {
     return 0;
 }
 
-template <int GS, int EPI>
+template <int GS, int EPI, int MODE>
 static int launch_gemm_q8_t(const CUtensorMap &mx, const CUtensorMap &mw, const PrefillGemmArgs &a, cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
-        CK(cudaFuncSetAttribute(k_gemm_q8<GS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+        CK(cudaFuncSetAttribute(k_gemm_q8<GS, EPI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
         attr = true;
     }
     dim3 grid(a.N / PF_BN, a.Tpad / PF_BM);
-    k_gemm_q8<GS, EPI><<<grid, PF_THREADS, PF_SMEM, s>>>(mx, mw, a);
+    k_gemm_q8<GS, EPI, MODE><<<grid, PF_THREADS, PF_SMEM, s>>>(mx, mw, a);
     return 0;
 }
+// mode 0: the fast drain (what q3_prefill runs); 1: reference-order f32 fold (bit-identical to matmul); 2: dense ceiling
+// (timing experiment: no group structure, one drain per tile) -- the int32 group dots are the same in modes 0 and 1
 template <int EPI>
-static int launch_gemm_q8(int gs, const CUtensorMap &mx, const CUtensorMap &mw, const PrefillGemmArgs &a, cudaStream_t s) {
+static int launch_gemm_q8(int gs, const CUtensorMap &mx, const CUtensorMap &mw, const PrefillGemmArgs &a, cudaStream_t s, int mode = 0) {
     int rc = 0;
-    GS_DISPATCH(gs, (rc = launch_gemm_q8_t<GS, EPI>(mx, mw, a, s)));
+    if (mode == 1) {
+        GS_DISPATCH(gs, (rc = launch_gemm_q8_t<GS, EPI, 1>(mx, mw, a, s)));
+    } else if (mode == 2) {
+        if (EPI != PF_EPI_STORE) return fail(Q3_EINVAL, "dense ceiling mode only with the plain store epilogue");
+        GS_DISPATCH(gs, (rc = launch_gemm_q8_t<GS, PF_EPI_STORE, 2>(mx, mw, a, s)));
+    } else {
+        GS_DISPATCH(gs, (rc = launch_gemm_q8_t<GS, EPI, 0>(mx, mw, a, s)));
+    }
     return rc;
 }
 
@@ -811,10 +821,15 @@ static int prefill_init(q3_handle *h) {
         return 0;
     }
     if (!get_encode_fn()) { h->pf_why = "cuTensorMapEncodeTiled unavailable"; return 0; }
+    h->pf_attn_f32 = getenv("Q3_PF_ATTN_F32") != nullptr;
     CK(cudaFuncSetAttribute(k_pf_attention<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFA_SMEM));
     CK(cudaFuncSetAttribute(k_pf_attention<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFA_SMEM));
     CK(cudaFuncSetAttribute(k_pf_attention<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFA_SMEM));
     CK(cudaFuncSetAttribute(k_pf_attention<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFA_SMEM));
+    CK(cudaFuncSetAttribute(k_pf_attention_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFT_SMEM));
+    CK(cudaFuncSetAttribute(k_pf_attention_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFT_SMEM));
+    CK(cudaFuncSetAttribute(k_pf_attention_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFT_SMEM));
+    CK(cudaFuncSetAttribute(k_pf_attention_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFT_SMEM));
     int rc;
     for (auto &W : h->layers) {
         if ((rc = prefill_prepare_tensor(h, W.qkv))) return rc;
@@ -892,7 +907,7 @@ static int prefill_run(q3_handle *h, const int *tokens_host, int T, int pos0) {
         if ((rc = launch_gemm_q8<PF_EPI_QKV>(gs, mx_dim, W.qkv.map, g, s))) return rc;
         dim3 rg((h->n_heads_l + h->n_kv_l + 3) / 4, T);
         k_pf_qknorm_rope<<<rg, 128, 0, s>>>(h->pf_q, kc_l, W.q_ln, W.k_ln, h->rope, pos0, h->n_heads_l, h->n_kv_l, AH, KV);
-        {
+        if (h->pf_attn_f32) { // f32 on the CUDA cores (kept for comparison: Q3_PF_ATTN_F32=1)
             const int bq = PFA_R / h->kv_mul;
             dim3 ag(h->n_kv_l, (T + bq - 1) / bq);
             switch (h->kv_mul) {
@@ -900,6 +915,15 @@ static int prefill_run(q3_handle *h, const int *tokens_host, int T, int pos0) {
             case 2: k_pf_attention<2><<<ag, 256, PFA_SMEM, s>>>(h->pf_q, kc_l, vc_l, h->pf_att, T, pos0, AH, KV); break;
             case 4: k_pf_attention<4><<<ag, 256, PFA_SMEM, s>>>(h->pf_q, kc_l, vc_l, h->pf_att, T, pos0, AH, KV); break;
             case 8: k_pf_attention<8><<<ag, 256, PFA_SMEM, s>>>(h->pf_q, kc_l, vc_l, h->pf_att, T, pos0, AH, KV); break;
+            }
+        } else { // tensor cores (3xTF32)
+            const int bq = PFT_R / h->kv_mul;
+            dim3 ag(h->n_kv_l, (T + bq - 1) / bq);
+            switch (h->kv_mul) {
+            case 1: k_pf_attention_tc<1><<<ag, 128, PFT_SMEM, s>>>(h->pf_q, kc_l, vc_l, h->pf_att, T, pos0, AH, KV); break;
+            case 2: k_pf_attention_tc<2><<<ag, 128, PFT_SMEM, s>>>(h->pf_q, kc_l, vc_l, h->pf_att, T, pos0, AH, KV); break;
+            case 4: k_pf_attention_tc<4><<<ag, 128, PFT_SMEM, s>>>(h->pf_q, kc_l, vc_l, h->pf_att, T, pos0, AH, KV); break;
+            case 8: k_pf_attention_tc<8><<<ag, 128, PFT_SMEM, s>>>(h->pf_q, kc_l, vc_l, h->pf_att, T, pos0, AH, KV); break;
             }
         }
         GS_DISPATCH(gs, (k_pf_quantize<GS><<<T, 256, 0, s>>>(h->pf_att, h->pf_xq, h->pf_xsT, AH, Tpad)));
@@ -1690,7 +1714,7 @@ extern "C" int q3_op_matmul(int device, const int8_t *xq, const float *xs, const
 }
 
 extern "C" int q3_op_gemm_q8(int device, const int8_t *xq, const float *xs, const int8_t *wq, const float *ws, int T, int N,
-                             int K, int gs, float *out) {
+                             int K, int gs, int exact, float *out) {
     int rc = op_prologue(device, gs);
     if (rc) return rc;
     if (T <= 0 || N % 128 || K % 128 || K % gs) return fail(Q3_EINVAL, "need N %% 128 == 0, K %% 128 == 0");
@@ -1713,7 +1737,7 @@ extern "C" int q3_op_gemm_q8(int device, const int8_t *xq, const float *xs, cons
     if ((rc = make_map_i8(&mx, dxq.p, Tpad, K)) || (rc = make_map_i8(&mw, dwq.p, N, K))) return rc;
     PrefillGemmArgs a{};
     a.T = T; a.Tpad = Tpad; a.N = N; a.K = K; a.wsT = dwsT.as<float>(); a.xsT = dxsT.as<float>(); a.out = dout.as<float>(); a.ld_out = N;
-    if ((rc = launch_gemm_q8<PF_EPI_STORE>(gs, mx, mw, a, 0))) return rc;
+    if ((rc = launch_gemm_q8<PF_EPI_STORE>(gs, mx, mw, a, 0, exact))) return rc;
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out, dout.p, (size_t)T * N * 4, cudaMemcpyDeviceToHost));
@@ -1740,6 +1764,57 @@ extern "C" int q3_op_sample(int device, const float *logits, int n, float temper
     CK(cudaGetLastError());
     CK(cudaMemcpy(rng_state, dr.p, 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(token_out, dt.p, 4, cudaMemcpyDeviceToHost));
+    return Q3_OK;
+}
+
+// Timing helper: the tcgen05 GEMM alone on device-resident random operands, CUDA events; mode as in q3_op_gemm_q8
+// (0 fast drain, 1 exact drain, 2 dense int8 ceiling of the same tiling).  ms_out = milliseconds per launch (best of reps).
+__global__ void k_fill_i8(int8_t *p, size_t n, unsigned seed) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned h = (unsigned)i * 2654435761u + seed;
+        h ^= h >> 15;
+        p[i] = (int8_t)((h * 2246822519u >> 24) - 128);
+    }
+}
+__global__ void k_fill_f32(float *p, size_t n, float v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+extern "C" int q3_bench_gemm_q8(int device, int T, int N, int K, int gs, int mode, int reps, float *ms_out) {
+    int rc = op_prologue(device, gs);
+    if (rc) return rc;
+    if (T <= 0 || N % 128 || K % 128 || K % gs || reps < 1 || mode < 0 || mode > 2) return fail(Q3_EINVAL, "bad gemm bench arguments");
+    const int Tpad = (T + 127) / 128 * 128, ng = K / gs;
+    DevBuf dxq, dxsT, dwq, dwsT, dout;
+    if ((rc = dxq.alloc((size_t)Tpad * K)) || (rc = dxsT.alloc((size_t)ng * Tpad * 4)) || (rc = dwq.alloc((size_t)N * K)) ||
+        (rc = dwsT.alloc((size_t)N * ng * 4)) || (rc = dout.alloc((size_t)T * N * 4)))
+        return rc;
+    k_fill_i8<<<592, 256>>>(dxq.as<int8_t>(), (size_t)Tpad * K, 1);
+    k_fill_i8<<<592, 256>>>(dwq.as<int8_t>(), (size_t)N * K, 2);
+    k_fill_f32<<<592, 256>>>(dxsT.as<float>(), (size_t)ng * Tpad, 0.01f);
+    k_fill_f32<<<592, 256>>>(dwsT.as<float>(), (size_t)N * ng, 0.02f);
+    CUtensorMap mx, mw;
+    if ((rc = make_map_i8(&mx, dxq.p, Tpad, K)) || (rc = make_map_i8(&mw, dwq.p, N, K))) return rc;
+    PrefillGemmArgs a{};
+    a.T = T; a.Tpad = Tpad; a.N = N; a.K = K; a.wsT = dwsT.as<float>(); a.xsT = dxsT.as<float>(); a.out = dout.as<float>(); a.ld_out = N;
+    if ((rc = launch_gemm_q8<PF_EPI_STORE>(gs, mx, mw, a, 0, mode))) return rc; // warm-up
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int r = 0; r < reps; r++) {
+        CK(cudaEventRecord(e0, 0));
+        if ((rc = launch_gemm_q8<PF_EPI_STORE>(gs, mx, mw, a, 0, mode))) return rc;
+        CK(cudaEventRecord(e1, 0));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = ms < best ? ms : best;
+    }
+    CK(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_out) *ms_out = best;
     return Q3_OK;
 }
 

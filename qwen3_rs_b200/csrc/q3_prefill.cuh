@@ -29,7 +29,7 @@ constexpr int PF_NACC = 4; // TMEM accumulator buffers (128 columns each)
 constexpr int PF_EPI_WARPS = 16;                   // 4 TMEM lane quadrants x 4 column quarters
 constexpr int PF_THREADS = (2 + PF_EPI_WARPS) * 32;
 constexpr int PF_COLS = PF_BN / (PF_EPI_WARPS / 4); // accumulator columns per epilogue thread (32)
-constexpr int PF_SMEM = PF_STAGES * (PF_BM * PF_BK + PF_BN * PF_BK) + 1024 + 256;
+constexpr int PF_SMEM = PF_STAGES * (PF_BM * PF_BK + PF_BN * PF_BK) + 8 * 1024 /* scale-row ring */ + 1024 + 512;
 
 enum { PF_EPI_STORE = 0, PF_EPI_QKV = 1, PF_EPI_RESID = 2, PF_EPI_SWIGLU = 3 };
 
@@ -66,18 +66,31 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity) {
     }
 }
 
-template <int GS, int EPI>
+// EXACT: every output is the reference's left fold of unfused (dot * ws) * xs terms -- bit-identical to `matmul` (the
+// operator-level proof).  !EXACT (what q3_prefill runs): the same exact int32 group dots, drained with
+// acc = fma(f32(dot) * ws, xs, acc) in packed f32x2 form, the scale rows of a group (128 weight scales + 128 token scales)
+// brought into a small shared-memory ring by the TMA warp instead of 32 global loads per thread and group, and the TMEM
+// read of the second half of a thread's columns in flight while the first half is being scaled.
+constexpr int PF_SRING = 8; // scale-row slots (one quantisation group each: 512 B of weight scales + 512 B of token scales)
+
+// MODE: 0 = fast drain, 1 = EXACT, 2 = dense ceiling (timing experiment only: the group structure is ignored, all of K is
+// accumulated in ONE TMEM buffer and drained once -- what this tiling / pipeline reaches as a plain int8 GEMM; the output
+// is the raw integer dot converted to f32)
+template <int GS, int EPI, int MODE>
 __global__ void __launch_bounds__(PF_THREADS, 1)
     k_gemm_q8(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const PrefillGemmArgs a) {
     extern __shared__ __align__(1024) uint8_t pf_smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(pf_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;                                  // [STAGES][128 rows][128 B]
     uint8_t *sB = smem + PF_STAGES * PF_BM * PF_BK;      // [STAGES][128 rows][128 B]
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + PF_STAGES * (PF_BM + PF_BN) * PF_BK);
+    float *sscale = reinterpret_cast<float *>(smem + PF_STAGES * (PF_BM + PF_BN) * PF_BK); // [PF_SRING][ws 128 | xs 128]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + PF_STAGES * (PF_BM + PF_BN) * PF_BK + PF_SRING * 1024);
     uint64_t *empty = full + PF_STAGES;
     uint64_t *tfull = empty + PF_STAGES;
     uint64_t *tempty = tfull + PF_NACC;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + PF_NACC);
+    uint64_t *sfull = tempty + PF_NACC;
+    uint64_t *sempty = sfull + PF_SRING;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sempty + PF_SRING);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * PF_BN, m0 = blockIdx.y * PF_BM;
@@ -85,6 +98,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1)
     constexpr int GPS = PF_BK / GS; // groups per stage
     constexpr int KPG = GS / 32;    // MMA K-steps per group
     const int ng = a.K / GS;
+    constexpr bool EXACT = MODE == 1, DENSE = MODE == 2;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < PF_STAGES; s++) {
@@ -94,6 +108,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1)
         for (int b = 0; b < PF_NACC; b++) {
             mbar_init(&tfull[b], 1);
             mbar_init(&tempty[b], PF_EPI_WARPS); // one arrive per epilogue warp
+        }
+        for (int b = 0; b < PF_SRING; b++) {
+            mbar_init(&sfull[b], 1);
+            mbar_init(&sempty[b], PF_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -111,12 +129,24 @@ __global__ void __launch_bounds__(PF_THREADS, 1)
     if (warp == 0) {
         // ------------------------------- TMA producer -------------------------------
         if (lane == 0) {
+            uint64_t policy;
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+            int gi = 0;
             for (int kb = 0; kb < nkb; kb++) {
                 const int s = kb % PF_STAGES;
                 mbar_wait_spin(&empty[s], ((kb / PF_STAGES) & 1) ^ 1);
                 mbar_expect_tx(&full[s], (PF_BM + PF_BN) * PF_BK);
                 tma_load_2d(sA + (size_t)s * PF_BM * PF_BK, &map_x, kb * PF_BK, m0, &full[s]);
                 tma_load_2d(sB + (size_t)s * PF_BN * PF_BK, &map_w, kb * PF_BK, n0, &full[s]);
+                if (MODE == 0) { // the scale rows of this stage's groups
+                    for (int gg = 0; gg < GPS; gg++, gi++) {
+                        const int sl = gi % PF_SRING;
+                        mbar_wait_spin(&sempty[sl], ((gi / PF_SRING) & 1) ^ 1);
+                        mbar_expect_tx(&sfull[sl], 1024);
+                        bulk_g2s(sscale + sl * 256, a.wsT + (size_t)gi * a.N + n0, 512, &sfull[sl], policy);
+                        bulk_g2s(sscale + sl * 256 + 128, a.xsT + (size_t)gi * a.Tpad + m0, 512, &sfull[sl], policy);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -133,15 +163,17 @@ __global__ void __launch_bounds__(PF_THREADS, 1)
                 const uint32_t b_s = smem_u32(sB + (size_t)s * PF_BN * PF_BK);
 #pragma unroll
                 for (int gg = 0; gg < GPS; gg++, gi++) {
-                    const int buf = gi % PF_NACC;
-                    mbar_wait_spin(&tempty[buf], ((gi / PF_NACC) & 1) ^ 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const int buf = DENSE ? 0 : gi % PF_NACC;
+                    if (!DENSE) {
+                        mbar_wait_spin(&tempty[buf], ((gi / PF_NACC) & 1) ^ 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
 #pragma unroll
                     for (int kk = 0; kk < KPG; kk++) {
                         const uint32_t koff = gg * GS + kk * 32; // bytes along K inside the 128 B swizzle span
-                        umma_i8(tmem_base + buf * PF_BN, umma_desc_k_sw128(a_s + koff), umma_desc_k_sw128(b_s + koff), IDESC, kk > 0);
+                        umma_i8(tmem_base + buf * PF_BN, umma_desc_k_sw128(a_s + koff), umma_desc_k_sw128(b_s + koff), IDESC, kk > 0 || (DENSE && gi > 0));
                     }
-                    umma_commit(&tfull[buf]); // accumulator of group gi complete -> epilogue
+                    if (!DENSE || gi == ng - 1) umma_commit(&tfull[buf]); // accumulator of group gi complete -> epilogue
                 }
                 umma_commit(&empty[s]); // all MMAs reading this stage retired -> TMA may refill it
             }
@@ -156,35 +188,78 @@ __global__ void __launch_bounds__(PF_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < PF_COLS; j++) acc[j] = 0.0f;
         const float *ws_col = a.wsT + n0 + part * PF_COLS;
-        for (int gi = 0; gi < ng; gi++) {
-            const int buf = gi % PF_NACC;
-            const float xs = a.xsT[(size_t)gi * a.Tpad + t];
-            mbar_wait_spin(&tfull[buf], (gi / PF_NACC) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t d[PF_COLS];
+        for (int gi = DENSE ? ng - 1 : 0; gi < ng; gi++) {
+            const int buf = DENSE ? 0 : gi % PF_NACC;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * PF_BN + part * PF_COLS;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]),
-                  "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]), "=r"(d[16]), "=r"(d[17]), "=r"(d[18]),
-                  "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]), "=r"(d[23]), "=r"(d[24]), "=r"(d[25]), "=r"(d[26]), "=r"(d[27]),
-                  "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
-                : "r"(taddr)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[buf]); // buffer drained into registers: MMA may reuse it
-            const float4 *wsg = reinterpret_cast<const float4 *>(ws_col + (size_t)gi * a.N);
+            if (EXACT || DENSE) {
+                const float xs = DENSE ? 1.0f : a.xsT[(size_t)gi * a.Tpad + t];
+                mbar_wait_spin(&tfull[buf], DENSE ? 0 : (gi / PF_NACC) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t d[PF_COLS];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]),
+                      "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]), "=r"(d[16]), "=r"(d[17]), "=r"(d[18]),
+                      "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]), "=r"(d[23]), "=r"(d[24]), "=r"(d[25]), "=r"(d[26]), "=r"(d[27]),
+                      "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]); // buffer drained into registers: MMA may reuse it
+                const float4 *wsg = reinterpret_cast<const float4 *>(ws_col + (size_t)gi * a.N);
 #pragma unroll
-            for (int j4 = 0; j4 < PF_COLS / 4; j4++) {
-                const float4 w = __ldg(wsg + j4);
-                // (dot as f32 * weight_scale) * input_scale, then the left-fold add (tensor.rs:59-61)
-                acc[4 * j4 + 0] = __fadd_rn(acc[4 * j4 + 0], __fmul_rn(__fmul_rn((float)(int)d[4 * j4 + 0], w.x), xs));
-                acc[4 * j4 + 1] = __fadd_rn(acc[4 * j4 + 1], __fmul_rn(__fmul_rn((float)(int)d[4 * j4 + 1], w.y), xs));
-                acc[4 * j4 + 2] = __fadd_rn(acc[4 * j4 + 2], __fmul_rn(__fmul_rn((float)(int)d[4 * j4 + 2], w.z), xs));
-                acc[4 * j4 + 3] = __fadd_rn(acc[4 * j4 + 3], __fmul_rn(__fmul_rn((float)(int)d[4 * j4 + 3], w.w), xs));
+                for (int j4 = 0; j4 < PF_COLS / 4; j4++) {
+                    const float4 w = DENSE ? make_float4(1.f, 1.f, 1.f, 1.f) : __ldg(wsg + j4);
+                    // (dot as f32 * weight_scale) * input_scale, then the left-fold add (tensor.rs:59-61)
+                    acc[4 * j4 + 0] = __fadd_rn(acc[4 * j4 + 0], __fmul_rn(__fmul_rn((float)(int)d[4 * j4 + 0], w.x), xs));
+                    acc[4 * j4 + 1] = __fadd_rn(acc[4 * j4 + 1], __fmul_rn(__fmul_rn((float)(int)d[4 * j4 + 1], w.y), xs));
+                    acc[4 * j4 + 2] = __fadd_rn(acc[4 * j4 + 2], __fmul_rn(__fmul_rn((float)(int)d[4 * j4 + 2], w.z), xs));
+                    acc[4 * j4 + 3] = __fadd_rn(acc[4 * j4 + 3], __fmul_rn(__fmul_rn((float)(int)d[4 * j4 + 3], w.w), xs));
+                }
+            } else {
+                const int sl = gi % PF_SRING;
+                const float *sw = sscale + sl * 256 + part * PF_COLS;
+                mbar_wait_spin(&tfull[buf], (gi / PF_NACC) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t d[PF_COLS];
+                // first half of this thread's columns, then the second half in flight while the first is being scaled
+#define PF_LD16(off, base)                                                                                                             \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"              \
+                 : "=r"(d[base + 0]), "=r"(d[base + 1]), "=r"(d[base + 2]), "=r"(d[base + 3]), "=r"(d[base + 4]), "=r"(d[base + 5]),     \
+                   "=r"(d[base + 6]), "=r"(d[base + 7]), "=r"(d[base + 8]), "=r"(d[base + 9]), "=r"(d[base + 10]), "=r"(d[base + 11]),   \
+                   "=r"(d[base + 12]), "=r"(d[base + 13]), "=r"(d[base + 14]), "=r"(d[base + 15])                                       \
+                 : "r"(taddr + off)                                                                                                    \
+                 : "memory")
+                PF_LD16(0, 0);
+                mbar_wait_spin(&sfull[sl], (gi / PF_SRING) & 1); // scale rows of this group landed
+                const float xs1 = sscale[sl * 256 + 128 + m];
+                const float2 xs = make_float2(xs1, xs1);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                PF_LD16(16, 16);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) {
+                    const float4 w = *reinterpret_cast<const float4 *>(sw + 4 * j4);
+                    float2 *ac = reinterpret_cast<float2 *>(acc + 4 * j4);
+                    ac[0] = __ffma2_rn(__fmul2_rn(make_float2((float)(int)d[4 * j4 + 0], (float)(int)d[4 * j4 + 1]), make_float2(w.x, w.y)), xs, ac[0]);
+                    ac[1] = __ffma2_rn(__fmul2_rn(make_float2((float)(int)d[4 * j4 + 2], (float)(int)d[4 * j4 + 3]), make_float2(w.z, w.w)), xs, ac[1]);
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]); // buffer drained into registers: MMA may reuse it
+#pragma unroll
+                for (int j4 = 4; j4 < 8; j4++) {
+                    const float4 w = *reinterpret_cast<const float4 *>(sw + 4 * j4);
+                    float2 *ac = reinterpret_cast<float2 *>(acc + 4 * j4);
+                    ac[0] = __ffma2_rn(__fmul2_rn(make_float2((float)(int)d[4 * j4 + 0], (float)(int)d[4 * j4 + 1]), make_float2(w.x, w.y)), xs, ac[0]);
+                    ac[1] = __ffma2_rn(__fmul2_rn(make_float2((float)(int)d[4 * j4 + 2], (float)(int)d[4 * j4 + 3]), make_float2(w.z, w.w)), xs, ac[1]);
+                }
+#undef PF_LD16
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sempty[sl]); // scale rows consumed
             }
         }
         // ---- write the PF_COLS outputs of this token row ----
@@ -456,6 +531,170 @@ __global__ void __launch_bounds__(256, 2) k_pf_attention(const float *__restrict
             reinterpret_cast<float4 *>(dst)[0] = make_float4(__fmul_rn(acc[i][0], inv), __fmul_rn(acc[i][1], inv), __fmul_rn(acc[i][2], inv), __fmul_rn(acc[i][3], inv));
             reinterpret_cast<float4 *>(dst)[1] = make_float4(__fmul_rn(acc[i][4], inv), __fmul_rn(acc[i][5], inv), __fmul_rn(acc[i][6], inv), __fmul_rn(acc[i][7], inv));
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Causal attention on the tensor cores: mma.sync m16n8k8 TF32 with the 3xTF32 split (x = hi + lo, hi = tf32(x),
+// lo = tf32(x - hi); a*b ~ hi*hi + hi*lo + lo*hi), which keeps the products at f32-class accuracy (relative error ~2^-21
+// instead of TF32's 2^-11: the attention output is re-quantised to int8 right after, and a coarser score would flip far
+// more int8 values than the f32 path does).  Same tiling idea as k_pf_attention: one CTA = one kv head x 64 query rows
+// (64 / KVMUL tokens x the KVMUL heads that share the K / V stream), 4 warps x 16 rows, key tiles of 32 positions whose
+// K and V rows are split into hi / lo once when they are staged in shared memory.
+//   S = Q K^T : A = Q fragment (split on the fly), B = K tile (key-major = "col" operand), 4 n-tiles x 16 k-steps
+//   O += P V  : the accumulator fragment of S doubles as the A fragment of P when the 8 keys of a k-step are taken in the
+//               order (0,2,4,6,1,3,5,7) -- the same permutation is applied to the rows of V in the B fragment, no shuffles.
+// ------------------------------------------------------------------------------------------
+constexpr int PFT_R = 64, PFT_BK = 32, PFT_LD = HEAD_DIM + 4;
+constexpr int PFT_SMEM = (PFT_R * PFT_LD + 4 * PFT_BK * PFT_LD) * 4;
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = __fsub_rn(x, __uint_as_float(hi));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+template <int KVMUL>
+__global__ void __launch_bounds__(128, 2) k_pf_attention_tc(const float *__restrict__ q, const float *__restrict__ kc,
+                                                            const float *__restrict__ vc, float *out, int T, int pos0, int AH, int KV) {
+    extern __shared__ __align__(16) float pft_smem[];
+    float *Qs = pft_smem;                   // [64][132] f32
+    float *Kh = Qs + PFT_R * PFT_LD;        // [32][132] tf32 hi
+    float *Kl = Kh + PFT_BK * PFT_LD;       // [32][132] tf32 lo
+    float *Vh = Kl + PFT_BK * PFT_LD;
+    float *Vl = Vh + PFT_BK * PFT_LD;
+    constexpr int BQ = PFT_R / KVMUL;
+    const int kvh = blockIdx.x, q0 = blockIdx.y * BQ;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const float scale = __fdiv_rn(1.0f, sqrtf((float)HEAD_DIM));
+    // Q tile: row r <-> (token q0 + r / KVMUL, head kvh*KVMUL + r % KVMUL)
+    for (int i = tid; i < PFT_R * 32; i += 128) {
+        const int r = i >> 5, c4 = i & 31;
+        const int tq = q0 + r / KVMUL;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tq < T) v = reinterpret_cast<const float4 *>(q + (size_t)tq * AH + (size_t)(kvh * KVMUL + r % KVMUL) * HEAD_DIM)[c4];
+        *reinterpret_cast<float4 *>(Qs + r * PFT_LD + c4 * 4) = v;
+    }
+    const int r0 = warp * 16 + g, r1 = r0 + 8;             // this thread's two rows of the tile
+    const int qp0 = pos0 + q0 + r0 / KVMUL, qp1 = pos0 + q0 + r1 / KVMUL; // their absolute positions
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+    float o[16][4];
+#pragma unroll
+    for (int j = 0; j < 16; j++) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.0f;
+    int last_q = q0 + BQ - 1;
+    if (last_q > T - 1) last_q = T - 1;
+    const int nkeys = pos0 + last_q + 1; // causal horizon of the last query in the tile
+    const float *kb = kc + (size_t)kvh * HEAD_DIM, *vb = vc + (size_t)kvh * HEAD_DIM;
+    for (int k0 = 0; k0 < nkeys; k0 += PFT_BK) {
+        __syncthreads(); // previous tile fully consumed (also orders the Q tile stores on the first pass)
+        for (int i = tid; i < PFT_BK * 32; i += 128) {
+            const int p = i >> 5, c4 = i & 31;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (k0 + p < nkeys) {
+                kv = reinterpret_cast<const float4 *>(kb + (size_t)(k0 + p) * KV)[c4];
+                vv = reinterpret_cast<const float4 *>(vb + (size_t)(k0 + p) * KV)[c4];
+            }
+            uint32_t h[4], lo[4];
+            split_tf32(kv.x, h[0], lo[0]); split_tf32(kv.y, h[1], lo[1]); split_tf32(kv.z, h[2], lo[2]); split_tf32(kv.w, h[3], lo[3]);
+            *reinterpret_cast<uint4 *>(Kh + p * PFT_LD + c4 * 4) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4 *>(Kl + p * PFT_LD + c4 * 4) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            split_tf32(vv.x, h[0], lo[0]); split_tf32(vv.y, h[1], lo[1]); split_tf32(vv.z, h[2], lo[2]); split_tf32(vv.w, h[3], lo[3]);
+            *reinterpret_cast<uint4 *>(Vh + p * PFT_LD + c4 * 4) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4 *>(Vl + p * PFT_LD + c4 * 4) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        __syncthreads();
+        // ---- S = Q K^T (16 rows x 32 keys per warp) ----
+        float s[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
+#pragma unroll 4
+        for (int ks = 0; ks < 16; ks++) {
+            const int d0 = ks * 8 + t;
+            uint32_t ah[4], al[4];
+            split_tf32(Qs[r0 * PFT_LD + d0], ah[0], al[0]);
+            split_tf32(Qs[r1 * PFT_LD + d0], ah[1], al[1]);
+            split_tf32(Qs[r0 * PFT_LD + d0 + 4], ah[2], al[2]);
+            split_tf32(Qs[r1 * PFT_LD + d0 + 4], ah[3], al[3]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int krow = (8 * j + g) * PFT_LD + d0;
+                const uint32_t bh0 = __float_as_uint(Kh[krow]), bh1 = __float_as_uint(Kh[krow + 4]);
+                const uint32_t bl0 = __float_as_uint(Kl[krow]), bl1 = __float_as_uint(Kl[krow + 4]);
+                mma_tf32(s[j], al, bh0, bh1);
+                mma_tf32(s[j], ah, bl0, bl1);
+                mma_tf32(s[j], ah, bh0, bh1);
+            }
+        }
+        // ---- online softmax: thread holds keys k0 + 8j + {2t, 2t+1} of rows r0 (s[j][0..1]) and r1 (s[j][2..3]) ----
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int key = k0 + 8 * j + 2 * t;
+            s[j][0] = (key <= qp0) ? __fmul_rn(s[j][0], scale) : -INFINITY;
+            s[j][1] = (key + 1 <= qp0) ? __fmul_rn(s[j][1], scale) : -INFINITY;
+            s[j][2] = (key <= qp1) ? __fmul_rn(s[j][2], scale) : -INFINITY;
+            s[j][3] = (key + 1 <= qp1) ? __fmul_rn(s[j][3], scale) : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float c0 = (mn0 == -INFINITY) ? 1.0f : expf(m0 - mn0), c1 = (mn1 == -INFINITY) ? 1.0f : expf(m1 - mn1);
+        m0 = mn0;
+        m1 = mn1;
+        l0 *= c0;
+        l1 *= c1;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            o[j][0] *= c0;
+            o[j][1] *= c0;
+            o[j][2] *= c1;
+            o[j][3] *= c1;
+        }
+        // ---- O += P V: k-step j = keys 8j .. 8j+7 in the order (0,2,4,6,1,3,5,7) ----
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float p00 = (s[j][0] == -INFINITY) ? 0.0f : expf(s[j][0] - mn0), p01 = (s[j][1] == -INFINITY) ? 0.0f : expf(s[j][1] - mn0);
+            const float p10 = (s[j][2] == -INFINITY) ? 0.0f : expf(s[j][2] - mn1), p11 = (s[j][3] == -INFINITY) ? 0.0f : expf(s[j][3] - mn1);
+            l0 += p00 + p01;
+            l1 += p10 + p11;
+            uint32_t ah[4], al[4]; // a0 (r0, k = t) = P[r0][2t], a1 (r1, t) = P[r1][2t], a2 (r0, t+4) = P[r0][2t+1], a3 (r1, t+4) = P[r1][2t+1]
+            split_tf32(p00, ah[0], al[0]);
+            split_tf32(p10, ah[1], al[1]);
+            split_tf32(p01, ah[2], al[2]);
+            split_tf32(p11, ah[3], al[3]);
+            const int vrow0 = (8 * j + 2 * t) * PFT_LD + g, vrow1 = vrow0 + PFT_LD;
+#pragma unroll
+            for (int n = 0; n < 16; n++) {
+                const uint32_t bh0 = __float_as_uint(Vh[vrow0 + 8 * n]), bh1 = __float_as_uint(Vh[vrow1 + 8 * n]);
+                const uint32_t bl0 = __float_as_uint(Vl[vrow0 + 8 * n]), bl1 = __float_as_uint(Vl[vrow1 + 8 * n]);
+                mma_tf32(o[n], al, bh0, bh1);
+                mma_tf32(o[n], ah, bl0, bl1);
+                mma_tf32(o[n], ah, bh0, bh1);
+            }
+        }
+    }
+    // row sums live spread over the quad
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = __fdiv_rn(1.0f, l0), i1 = __fdiv_rn(1.0f, l1);
+    const int tq0 = q0 + r0 / KVMUL, tq1 = q0 + r1 / KVMUL;
+    float *d0 = out + (size_t)tq0 * AH + (size_t)(kvh * KVMUL + r0 % KVMUL) * HEAD_DIM + 2 * t;
+    float *d1 = out + (size_t)tq1 * AH + (size_t)(kvh * KVMUL + r1 % KVMUL) * HEAD_DIM + 2 * t;
+#pragma unroll
+    for (int n = 0; n < 16; n++) {
+        if (tq0 < T) *reinterpret_cast<float2 *>(d0 + 8 * n) = make_float2(__fmul_rn(o[n][0], i0), __fmul_rn(o[n][1], i0));
+        if (tq1 < T) *reinterpret_cast<float2 *>(d1 + 8 * n) = make_float2(__fmul_rn(o[n][2], i1), __fmul_rn(o[n][3], i1));
     }
 }
 

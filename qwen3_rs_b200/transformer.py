@@ -92,8 +92,9 @@ ABI = {
     "q3_op_quantize": (_i, [_i, _vp, _i, _i, _vp, _vp]),
     "q3_op_matmul": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "q3_op_expf": (_i, [_i, _vp, _i, _vp]),
-    "q3_op_gemm_q8": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "q3_op_gemm_q8": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "q3_op_sample": (_i, [_i, _vp, _i, _f, _f, C.POINTER(C.c_ulonglong), C.POINTER(_i)]),
+    "q3_bench_gemm_q8": (_i, [_i, _i, _i, _i, _i, _i, _i, C.POINTER(_f)]),
     "q3_op_rmsnorm": (_i, [_i, _vp, _vp, _i, _vp]),
     "q3_op_quantize_q80": (_i, [_i, _vp, _sz, _i, _vp, _vp]),
     "q3_op_quantize_q80_dev": (_i, [_i, _vp, _sz, _i, _vp, _vp]),
@@ -382,13 +383,13 @@ def op_matmul(xq, xs, wq, ws, n: int, d: int, gs: int, want_dots: bool = False, 
     return (out, dots) if want_dots else out
 
 
-def op_gemm_q8(xq, xs, wq, ws, T: int, N: int, K: int, gs: int, device: int = 0):
+def op_gemm_q8(xq, xs, wq, ws, T: int, N: int, K: int, gs: int, exact: bool = False, device: int = 0):
     xq = np.ascontiguousarray(xq, np.int8)
     xs = np.ascontiguousarray(xs, np.float32)
     wq = np.ascontiguousarray(wq, np.int8)
     ws = np.ascontiguousarray(ws, np.float32)
     out = np.empty((T, N), np.float32)
-    _check(load_library().q3_op_gemm_q8(device, _ptr(xq), _ptr(xs), _ptr(wq), _ptr(ws), T, N, K, gs, _ptr(out)))
+    _check(load_library().q3_op_gemm_q8(device, _ptr(xq), _ptr(xs), _ptr(wq), _ptr(ws), T, N, K, gs, int(exact), _ptr(out)))
     return out
 
 
@@ -398,6 +399,13 @@ def op_sample(logits, temperature: float, topp: float, rng_state: int, device: i
     st, tok = C.c_ulonglong(int(rng_state) & 0xFFFFFFFFFFFFFFFF), C.c_int(0)
     _check(load_library().q3_op_sample(device, _ptr(a), a.size, float(temperature), float(topp), C.byref(st), C.byref(tok)))
     return tok.value, st.value
+
+
+def bench_gemm_q8(T: int, N: int, K: int, gs: int = 64, mode: int = 0, reps: int = 5, device: int = 0) -> float:
+    """Milliseconds per launch of the tcgen05 GEMM alone (mode 0 fast drain, 1 exact drain, 2 dense int8 ceiling)."""
+    ms = C.c_float(0)
+    _check(load_library().q3_bench_gemm_q8(device, T, N, K, gs, mode, reps, C.byref(ms)))
+    return ms.value
 
 
 def op_rmsnorm(x, w, device: int = 0):

@@ -52,6 +52,7 @@ xq = rng.integers(-127, 128, (130, 256), dtype=np.int8)
 xs = rng.random((130, 4)).astype(np.float32)
 wq = rng.integers(-127, 128, 128 * 256, dtype=np.int8)
 ws = rng.random(128 * 4).astype(np.float32)
-out = T.op_gemm_q8(xq, xs, wq, ws, 130, 128, 256, 64)
-print("gemm_q8 ok %.3f" % float(np.abs(out).max()))
+for ex in (True, False):
+    out = T.op_gemm_q8(xq, xs, wq, ws, 130, 128, 256, 64, exact=ex)
+    print("gemm_q8 exact=%d ok %.3f" % (ex, float(np.abs(out).max())))
 print("SANITIZE_TARGET_DONE")

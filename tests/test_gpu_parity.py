@@ -518,9 +518,13 @@ def test_tensor_core_gemm_bit_identical_to_reference_matmul(T, N, K, gs):
         xq[t], xs[t] = orc.quantize(rng.standard_normal(K).astype(np.float32) * (1 + t % 3), gs)
     xq[0, :] = 127  # extreme row
     wq[:K] = -127
-    out = T_mod.op_gemm_q8(xq, xs, wq, ws, T, N, K, gs)
+    out = T_mod.op_gemm_q8(xq, xs, wq, ws, T, N, K, gs, exact=True)
     ref = np.stack([orc.matmul(xq[t], xs[t], wq, ws, K, N, gs) for t in range(T)])
     assert np.array_equal(out, ref), float(np.abs(out - ref).max())
+    # the drain q3_prefill runs: same int32 group dots and group order, fused multiply-adds -> float round-off of the fold only
+    fast = T_mod.op_gemm_q8(xq, xs, wq, ws, T, N, K, gs)
+    scale = np.abs(ref).max() + 1e-30
+    assert np.abs(fast - ref).max() <= 2e-6 * scale * np.sqrt(K / gs)
 
 
 @pytest.mark.parametrize("name,gs,seed,T", [("tiny-untied", 64, 1, 37), ("small", 128, 2, 130), ("tiny", 64, 0, 5)])
@@ -619,3 +623,35 @@ def test_exact_mask_switches_one_reduction_at_a_time(models, golden):
                 assert err <= 0.05 * float(np.abs(lg).max()) + LOGIT_TOL
     finally:
         m.set_exact(False)
+
+
+@pytest.mark.parametrize("name,gs,seed,T", [("tiny-untied", 64, 1, 37), ("small", 128, 2, 130), ("small", 64, 3, 200)])
+def test_prefill_matches_oracle(models, ckpt, name, gs, seed, T):
+    """q3_prefill (tcgen05 GEMMs + tensor-core attention) against the ORACLE's T sequential forwards: K / V cache rows of
+    every layer and the logits of the last token.  Layer 0 depends only on embedding -> norm -> QKV GEMM -> QK-norm / RoPE
+    (nothing can cascade): 1e-4.  Deeper layers see the attention output re-quantised to int8: most rows agree to float
+    round-off (median), a flipped int8 moves a row by a quantisation step, bounded by the fast-mode envelope."""
+    m, o = models(name, gs, seed), orc.Model(ckpt(name, gs, seed))
+    c = o.config
+    rng = np.random.default_rng(T + 1)
+    toks = rng.integers(0, c["vocab_size"], T).tolist()
+    o.reset()
+    for p, t in enumerate(toks):
+        lo = o.forward(t, p)
+    ko, vo = o.kv_cache()
+    m.reset()
+    lg = m.prefill(toks, 0)
+    kvd = c["n_kv_heads"] * c["head_dim"]
+    for l in range(c["n_layers"]):
+        k, v = m.kv_read(l, 0, T)
+        kr, vr = ko[l, :T].reshape(T, kvd), vo[l, :T].reshape(T, kvd)
+        ek, ev = np.abs(k - kr), np.abs(v - vr)
+        if l == 0:
+            assert ek.max() <= 1e-4 and ev.max() <= 1e-4
+        assert np.median(ev) <= 1e-5 * max(1.0, float(np.abs(vr).max())), (l, float(np.median(ev)))
+        assert ev.max() <= 0.05 * np.abs(vr).max() + 1e-2 and ek.max() <= 0.05 * np.abs(kr).max() + 1e-2
+        k1, v1 = m.kv_read(l, T, 1)
+        assert not k1.any() and not v1.any()
+    err = float(np.abs(lg - lo).max())
+    print(f"{name} gs{gs} prefill T={T} vs oracle: max|dlogit| {err:.2e} (|logit| max {np.abs(lo).max():.1f})")
+    assert err <= 0.05 * float(np.abs(lo).max()) + LOGIT_TOL
