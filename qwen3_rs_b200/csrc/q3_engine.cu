@@ -106,7 +106,7 @@ struct q3_handle {
     unsigned long long bar_base = 0, xbar_base = 0;
     int *d_status = nullptr;  // device abort flag raised by a timed-out wait inside the kernel
     unsigned long long *part_buf[2] = {nullptr, nullptr};            // TP landing zones [tp][dim] (inside xchg: peers write them)
-    unsigned long long *zq = nullptr, *za = nullptr, *zh = nullptr, *zr[2] = {nullptr, nullptr}; // local (payload, epoch) zones
+    unsigned long long *zq = nullptr, *za = nullptr, *zh = nullptr, *zp = nullptr, *zr[2] = {nullptr, nullptr}; // local (payload, epoch) zones
     int logits_root = -1;     // TP: >= 0 = only this rank receives the other ranks' vocabulary shards (q3_tp_set_logits_root)
     bool poisoned = false;    // a wait timed out under tensor parallelism: the ranks' epoch / barrier sequences may have diverged
     unsigned long long *d_best = nullptr, *d_bar = nullptr;
@@ -609,6 +609,7 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
             {&h->zq, (size_t)h->AH_l + 2 * (size_t)h->KV_l},
             {&h->za, (size_t)h->AH_l / 4 + (size_t)h->AH_l / gs},
             {&h->zh, (size_t)h->H_l},
+            {&h->zp, (size_t)h->n_heads_l * MEGA_MAX_SPLITS * ATTN_PART_STRIDE},
             {&h->zr[0], (size_t)dim},
             {&h->zr[1], (size_t)dim}};
         for (auto &z : zones) {
@@ -624,7 +625,7 @@ static int build_mega(q3_handle *h, const float *rms_att_all, const float *rms_f
     CK(cudaMemset(h->d_status, 0, 64));
     int *d_status = h->d_status;
     a.x = h->x;
-    a.zq = h->zq; a.za = h->za; a.zh = h->zh; a.zr[0] = h->zr[0]; a.zr[1] = h->zr[1];
+    a.zq = h->zq; a.za = h->za; a.zh = h->zh; a.zp = h->zp; a.zr[0] = h->zr[0]; a.zr[1] = h->zr[1];
     a.attn_part = h->attn_part; a.att_cnt = h->att_cnt;
     a.dbg = getenv("Q3_MEGA_DBG") ? atoi(getenv("Q3_MEGA_DBG")) : 0;
     a.bar = h->d_bar; a.status = d_status; a.tokpos = h->d_tokpos; a.history = h->d_history;
@@ -1764,6 +1765,49 @@ extern "C" int q3_op_sample(int device, const float *logits, int n, float temper
     CK(cudaGetLastError());
     CK(cudaMemcpy(rng_state, dr.p, 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(token_out, dt.p, 4, cudaMemcpyDeviceToHost));
+    return Q3_OK;
+}
+
+// Causal prefill attention alone (layers.rs:374-419 for T query tokens at positions pos0 .. pos0+T-1 over a cache of pos0+T rows):
+// q [T][n_heads*128] (already normalised + rotated), k / v [pos0+T][n_kv*128], out [T][n_heads*128].
+// f32_cuda_cores != 0: the CUDA-core f32 kernel; 0: the tensor-core (3xTF32) kernel q3_prefill runs.
+extern "C" int q3_op_prefill_attention(int device, const float *q, const float *k, const float *v, int T, int pos0, int n_heads, int n_kv,
+                                       int f32_cuda_cores, float *out) {
+    CK(cudaSetDevice(device));
+    if (!q || !k || !v || !out || T <= 0 || pos0 < 0 || n_kv <= 0 || n_heads % n_kv) return fail(Q3_EINVAL, "bad attention arguments");
+    const int kv_mul = n_heads / n_kv;
+    if (kv_mul != 1 && kv_mul != 2 && kv_mul != 4 && kv_mul != 8) return fail(Q3_EUNSUPPORTED, "GQA factor %d unsupported", kv_mul);
+    const int AH = n_heads * HEAD_DIM, KV = n_kv * HEAD_DIM, nk = pos0 + T;
+    DevBuf dq, dk, dv, dout;
+    int rc;
+    if ((rc = dq.alloc((size_t)T * AH * 4)) || (rc = dk.alloc((size_t)nk * KV * 4)) || (rc = dv.alloc((size_t)nk * KV * 4)) ||
+        (rc = dout.alloc((size_t)T * AH * 4)))
+        return rc;
+    CK(cudaMemcpy(dq.p, q, (size_t)T * AH * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dk.p, k, (size_t)nk * KV * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dv.p, v, (size_t)nk * KV * 4, cudaMemcpyHostToDevice));
+#define PFA_CASE(KM)                                                                                                                        \
+    case KM:                                                                                                                                \
+        if (f32_cuda_cores) {                                                                                                               \
+            CK(cudaFuncSetAttribute(k_pf_attention<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFA_SMEM));                            \
+            k_pf_attention<KM><<<dim3(n_kv, (T + PFA_R / KM - 1) / (PFA_R / KM)), 256, PFA_SMEM>>>(dq.as<float>(), dk.as<float>(), dv.as<float>(), \
+                                                                                                 dout.as<float>(), T, pos0, AH, KV);         \
+        } else {                                                                                                                            \
+            CK(cudaFuncSetAttribute(k_pf_attention_tc<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFT_SMEM));                         \
+            k_pf_attention_tc<KM><<<dim3(n_kv, (T + PFT_R / KM - 1) / (PFT_R / KM)), 128, PFT_SMEM>>>(dq.as<float>(), dk.as<float>(), dv.as<float>(), \
+                                                                                                    dout.as<float>(), T, pos0, AH, KV);      \
+        }                                                                                                                                   \
+        break;
+    switch (kv_mul) {
+        PFA_CASE(1)
+        PFA_CASE(2)
+        PFA_CASE(4)
+        PFA_CASE(8)
+    }
+#undef PFA_CASE
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, dout.p, (size_t)T * AH * 4, cudaMemcpyDeviceToHost));
     return Q3_OK;
 }
 

@@ -76,6 +76,9 @@ constexpr int MEGA_EDGES = 6;                       // epochs per layer: one per
 #ifndef MEGA_POLL_SLEEP
 #define MEGA_POLL_SLEEP 0   // ns between two polls of a word that has not arrived yet (measured: 0 best, 64: -1.4 %, 200: -1.9 %)
 #endif
+#ifndef MEGA_LLPART
+#define MEGA_LLPART 0       // 1: attention split partials as (value, epoch) words, head h merged by split h % nsplit (measured: +7.8 % us/token -- rejected)
+#endif
 #ifndef MEGA_EARLY_W
 #define MEGA_EARLY_W 1      // issue the norm-weight loads BEFORE polling for the activation (one loaded round trip instead of two)
 #endif
@@ -112,7 +115,8 @@ struct MegaArgs {
     unsigned long long *zh;          // [H_l]                  SwiGLU outputs
     unsigned long long *zr[2];       // [dim]                  o_proj / down rows, reduced over the TP ranks (this rank's copy)
     unsigned long long *part[2][MEGA_MAX_TP]; // TP only: [o|down][rank] -> that rank's landing zone [tp][dim] (peer memory)
-    float *attn_part;                // [n_heads_l][MEGA_MAX_SPLITS][ATTN_PART_STRIDE] split partials (nsplit > 1)
+    float *attn_part;                // [n_heads_l][MEGA_MAX_SPLITS][ATTN_PART_STRIDE] split partials (nsplit > 1, MEGA_LLPART == 0)
+    unsigned long long *zp;          // the same as (value, epoch) words (MEGA_LLPART): [n_heads_l][MEGA_MAX_SPLITS][ATTN_PART_STRIDE]
     unsigned *att_cnt;               // [n_layers][n_kv_l] arrivals of the splits of a kv head (returns to 0 within the launch)
     float *logits[MEGA_MAX_TP];      // full-vocab logits buffer of every rank
     unsigned long long *best[MEGA_MAX_TP]; // [tp][grid] argmax candidates of every rank
@@ -866,6 +870,70 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
         if (warp < KVMUL) publish_head<GS>(a, kvh * KVMUL + warp, lane, A, L, ep_a);
         return;
     }
+#if MEGA_LLPART
+    // Several splits: every split publishes its partial (acc[128], m, l per query head) as (value, epoch) words; query head h of
+    // the group is merged by the split h % nsplit -- no fence, no counter: the merger polls the nsplit partials of its head.
+    if (warp < KVMUL) {
+        unsigned long long *dst = a.zp + ((size_t)(kvh * KVMUL + warp) * MEGA_MAX_SPLITS + split) * ATTN_PART_STRIDE;
+        ll_store(dst + lane * 4 + 0, A.x, ep_a);
+        ll_store(dst + lane * 4 + 1, A.y, ep_a);
+        ll_store(dst + lane * 4 + 2, A.z, ep_a);
+        ll_store(dst + lane * 4 + 3, A.w, ep_a);
+        if (lane == 0) {
+            ll_store(dst + HEAD_DIM, M, ep_a);
+            ll_store(dst + HEAD_DIM + 1, L, ep_a);
+        }
+    }
+    prof_mark(pr, 37); // split partial published
+    if (warp < KVMUL && (warp % nsplit) == split) {
+        const int head = kvh * KVMUL + warp;
+        const unsigned long long *pb = a.zp + (size_t)head * MEGA_MAX_SPLITS * ATTN_PART_STRIDE;
+        unsigned spins = 0;
+        // lane s: statistics of split s (one round trip for all splits once they are there)
+        float ms = -INFINITY, ls = 0.0f;
+        if (lane < nsplit) {
+            unsigned long long x, y;
+            while (true) {
+                ll_load2(pb + (size_t)lane * ATTN_PART_STRIDE + HEAD_DIM, x, y);
+                if ((ll_ok(x, ep_a) && ll_ok(y, ep_a)) || ll_give_up(a, spins, 12)) break;
+            }
+            ms = __uint_as_float((unsigned)x);
+            ls = __uint_as_float((unsigned)y);
+        }
+        const float Mx = warp_max(ms);
+        const float cs = lane < nsplit ? expf(ms - Mx) : 0.0f;
+        const float Ls = warp_sum(ls * cs);
+        float4 As = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int s0 = 0; s0 < nsplit; s0 += 4) { // accumulators four splits at a time, all eight loads in flight together
+            unsigned long long w[4][4];
+            while (true) {
+                bool ok = true;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (s0 + j < nsplit) {
+                        const unsigned long long *src = pb + (size_t)(s0 + j) * ATTN_PART_STRIDE + lane * 4;
+                        ll_load2(src, w[j][0], w[j][1]);
+                        ll_load2(src + 2, w[j][2], w[j][3]);
+                        ok = ok && ll_ok(w[j][0], ep_a) && ll_ok(w[j][1], ep_a) && ll_ok(w[j][2], ep_a) && ll_ok(w[j][3], ep_a);
+                    }
+                }
+                if (ok || ll_give_up(a, spins, 12)) break;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float c = __shfl_sync(0xffffffffu, cs, (s0 + j) & 31);
+                if (s0 + j < nsplit) {
+                    As.x += __uint_as_float((unsigned)w[j][0]) * c;
+                    As.y += __uint_as_float((unsigned)w[j][1]) * c;
+                    As.z += __uint_as_float((unsigned)w[j][2]) * c;
+                    As.w += __uint_as_float((unsigned)w[j][3]) * c;
+                }
+            }
+        }
+        publish_head<GS>(a, head, lane, As, Ls, ep_a);
+    }
+#else
     if (warp < KVMUL) {
         float *dst = a.attn_part + ((size_t)(kvh * KVMUL + warp) * MEGA_MAX_SPLITS + split) * ATTN_PART_STRIDE;
         reinterpret_cast<float4 *>(dst)[lane] = A;
@@ -915,6 +983,7 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
         }
         publish_head<GS>(a, head, lane, As, Ls, ep_a);
     }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

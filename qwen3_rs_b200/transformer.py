@@ -95,6 +95,7 @@ ABI = {
     "q3_op_gemm_q8": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "q3_op_sample": (_i, [_i, _vp, _i, _f, _f, C.POINTER(C.c_ulonglong), C.POINTER(_i)]),
     "q3_bench_gemm_q8": (_i, [_i, _i, _i, _i, _i, _i, _i, C.POINTER(_f)]),
+    "q3_op_prefill_attention": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "q3_op_rmsnorm": (_i, [_i, _vp, _vp, _i, _vp]),
     "q3_op_quantize_q80": (_i, [_i, _vp, _sz, _i, _vp, _vp]),
     "q3_op_quantize_q80_dev": (_i, [_i, _vp, _sz, _i, _vp, _vp]),
@@ -399,6 +400,16 @@ def op_sample(logits, temperature: float, topp: float, rng_state: int, device: i
     st, tok = C.c_ulonglong(int(rng_state) & 0xFFFFFFFFFFFFFFFF), C.c_int(0)
     _check(load_library().q3_op_sample(device, _ptr(a), a.size, float(temperature), float(topp), C.byref(st), C.byref(tok)))
     return tok.value, st.value
+
+
+def op_prefill_attention(q, k, v, pos0: int, n_heads: int, n_kv: int, f32_cuda_cores: bool = False, device: int = 0):
+    """Causal attention of T = q.shape[0] query tokens at positions pos0.. over k / v rows [pos0 + T][n_kv * 128]."""
+    q = np.ascontiguousarray(q, np.float32)
+    k = np.ascontiguousarray(k, np.float32)
+    v = np.ascontiguousarray(v, np.float32)
+    out = np.empty_like(q)
+    _check(load_library().q3_op_prefill_attention(device, _ptr(q), _ptr(k), _ptr(v), q.shape[0], pos0, n_heads, n_kv, int(f32_cuda_cores), _ptr(out)))
+    return out
 
 
 def bench_gemm_q8(T: int, N: int, K: int, gs: int = 64, mode: int = 0, reps: int = 5, device: int = 0) -> float:

@@ -6,6 +6,7 @@ from qwen3_rs_b200 import transformer as T
 model = sys.argv[1] if len(sys.argv) > 1 else "qwen3-8b"
 path_id = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 6
-m = T.TransformerBuilder.new(bench.bench_checkpoint(model, 64)).with_ctx_length(256).build()
+pos0 = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+m = T.TransformerBuilder.new(bench.bench_checkpoint(model, 64)).with_ctx_length(max(256, pos0 + steps + 8)).build()
 m.set_decode_path(path_id)
-print(m.decode_greedy(1, 0, steps))
+print(m.decode_greedy(1, pos0, steps))

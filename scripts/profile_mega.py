@@ -17,7 +17,8 @@ else:
     m = T.TransformerBuilder.new(path).with_ctx_length(max(256, pos + 8)).build()
     m.bench_decode(1, 0, 4)
     raw = m.debug_profile(1, pos)
-    np.save("gpurun_out/mega_profile_%s_pos%d.npy" % (model, pos), raw)
+    if os.environ.get("Q3_SAVE_PROFILE_NPY"):
+        np.save("gpurun_out/mega_profile_%s_pos%d.npy" % (model, pos), raw)
 
 KINDS = ["qkv", "att", "o", "gu", "dn", "head"]
 MAIN = ["pro", "gemv", "sync"]  # prologue (poll + rebuild) / GEMV / wait for this CTA's last warp (head: grid barrier)
