@@ -779,8 +779,14 @@ static int launch_gemm_q8_t(const CUtensorMap &mx, const CUtensorMap &mw, const 
         CK(cudaFuncSetAttribute(k_gemm_q8<GS, EPI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
         attr = true;
     }
-    dim3 grid(a.N / PF_BN, a.Tpad / PF_BM);
-    k_gemm_q8<GS, EPI, MODE><<<grid, PF_THREADS, PF_SMEM, s>>>(mx, mw, a);
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int tiles = (a.N / PF_BN) * (a.Tpad / PF_BM); // persistent: one CTA per SM walks the tiles
+    k_gemm_q8<GS, EPI, MODE><<<tiles < num_sms ? tiles : num_sms, PF_THREADS, PF_SMEM, s>>>(mx, mw, a);
     return 0;
 }
 // mode 0: the fast drain (what q3_prefill runs); 1: reference-order f32 fold (bit-identical to matmul); 2: dense ceiling
@@ -790,9 +796,12 @@ static int launch_gemm_q8(int gs, const CUtensorMap &mx, const CUtensorMap &mw, 
     int rc = 0;
     if (mode == 1) {
         GS_DISPATCH(gs, (rc = launch_gemm_q8_t<GS, EPI, 1>(mx, mw, a, s)));
-    } else if (mode == 2) {
-        if (EPI != PF_EPI_STORE) return fail(Q3_EINVAL, "dense ceiling mode only with the plain store epilogue");
-        GS_DISPATCH(gs, (rc = launch_gemm_q8_t<GS, PF_EPI_STORE, 2>(mx, mw, a, s)));
+    } else if (mode >= 2 && mode <= 5) {
+        if (EPI != PF_EPI_STORE) return fail(Q3_EINVAL, "timing-experiment modes only with the plain store epilogue");
+        if (mode == 2) GS_DISPATCH(gs, (rc = launch_gemm_q8_t<GS, PF_EPI_STORE, 2>(mx, mw, a, s)));
+        if (mode == 3) GS_DISPATCH(gs, (rc = launch_gemm_q8_t<GS, PF_EPI_STORE, 3>(mx, mw, a, s)));
+        if (mode == 4) GS_DISPATCH(gs, (rc = launch_gemm_q8_t<GS, PF_EPI_STORE, 4>(mx, mw, a, s)));
+        if (mode == 5) GS_DISPATCH(gs, (rc = launch_gemm_q8_t<GS, PF_EPI_STORE, 5>(mx, mw, a, s)));
     } else {
         GS_DISPATCH(gs, (rc = launch_gemm_q8_t<GS, EPI, 0>(mx, mw, a, s)));
     }
@@ -1826,7 +1835,7 @@ __global__ void k_fill_f32(float *p, size_t n, float v) {
 extern "C" int q3_bench_gemm_q8(int device, int T, int N, int K, int gs, int mode, int reps, float *ms_out) {
     int rc = op_prologue(device, gs);
     if (rc) return rc;
-    if (T <= 0 || N % 128 || K % 128 || K % gs || reps < 1 || mode < 0 || mode > 2) return fail(Q3_EINVAL, "bad gemm bench arguments");
+    if (T <= 0 || N % 128 || K % 128 || K % gs || reps < 1 || mode < 0 || mode > 5) return fail(Q3_EINVAL, "bad gemm bench arguments");
     const int Tpad = (T + 127) / 128 * 128, ng = K / gs;
     DevBuf dxq, dxsT, dwq, dwsT, dout;
     if ((rc = dxq.alloc((size_t)Tpad * K)) || (rc = dxsT.alloc((size_t)ng * Tpad * 4)) || (rc = dwq.alloc((size_t)N * K)) ||
@@ -1842,6 +1851,22 @@ extern "C" int q3_bench_gemm_q8(int device, int T, int N, int K, int gs, int mod
     a.T = T; a.Tpad = Tpad; a.N = N; a.K = K; a.wsT = dwsT.as<float>(); a.xsT = dxsT.as<float>(); a.out = dout.as<float>(); a.ld_out = N;
     if ((rc = launch_gemm_q8<PF_EPI_STORE>(gs, mx, mw, a, 0, mode))) return rc; // warm-up
     CK(cudaDeviceSynchronize());
+    if (getenv("Q3_PF_TRACE")) { // one extra launch with the in-kernel stamps of CTA 0 switched on; dumped to stderr (cycles, relative)
+        DevBuf dtr;
+        if ((rc = dtr.alloc((size_t)4 * PF_TRACE_N * 8))) return rc;
+        CK(cudaMemset(dtr.p, 0, (size_t)4 * PF_TRACE_N * 8));
+        PrefillGemmArgs at = a;
+        at.trace = dtr.as<long long>();
+        if ((rc = launch_gemm_q8<PF_EPI_STORE>(gs, mx, mw, at, 0, mode))) return rc;
+        CK(cudaDeviceSynchronize());
+        std::vector<long long> tr((size_t)4 * PF_TRACE_N);
+        CK(cudaMemcpy(tr.data(), dtr.p, tr.size() * 8, cudaMemcpyDeviceToHost));
+        const long long t0 = tr[PF_TRACE_N]; // first commit
+        fprintf(stderr, "pair  mma:slot_free  mma:committed  epi:complete_seen  epi:released   (cycles after the first commit; T %d N %d K %d mode %d)\n", T, N, K, mode);
+        for (int i = 0; i < 48; i++)
+            fprintf(stderr, "%4d %14lld %14lld %18lld %14lld\n", i, tr[i] ? tr[i] - t0 : -1, tr[PF_TRACE_N + i] - t0, tr[2 * PF_TRACE_N + i] ? tr[2 * PF_TRACE_N + i] - t0 : -1,
+                    tr[3 * PF_TRACE_N + i] - t0);
+    }
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));

@@ -79,6 +79,10 @@ constexpr int MEGA_EDGES = 6;                       // epochs per layer: one per
 #ifndef MEGA_LLPART
 #define MEGA_LLPART 0       // 1: attention split partials as (value, epoch) words, head h merged by split h % nsplit (measured: +7.8 % us/token -- rejected)
 #endif
+#ifndef MEGA_LAZY_SYNC
+#define MEGA_LAZY_SYNC 0    // 1: no CTA-wide sync at the end of the o_proj / gate-up / down steps (the next prologue syncs before it rewrites the
+                            // activation; down_proj's activation lives in a second buffer so that gate/up stragglers may still read the first)
+#endif
 #ifndef MEGA_EARLY_W
 #define MEGA_EARLY_W 1      // issue the norm-weight loads BEFORE polling for the activation (one loaded round trip instead of two)
 #endif
@@ -1081,6 +1085,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
     uint8_t *sxq = scratch;                                          // up to 16384 B
     float *sxs = reinterpret_cast<float *>(scratch + 16384);         // up to 512 groups
     float *sred = reinterpret_cast<float *>(scratch + 16384 + 2048); // 16 floats (+ argmax scratch at +32)
+    // down_proj's activation: its own buffer under MEGA_LAZY_SYNC (written while gate/up stragglers may still be reading sxq)
+    uint8_t *sxq_dn = MEGA_LAZY_SYNC ? scratch + 20480 : sxq;
+    float *sxs_dn = MEGA_LAZY_SYNC ? reinterpret_cast<float *>(scratch + 20480 + 16384) : sxs;
+    static_assert(20480 + 16384 + 2048 <= MEGA_SCRATCH, "second activation buffer");
     // full barriers are per (consumer group, slot): a waiter can only tell adjacent mbarrier phases
     // apart, and with ownership alternating between the groups a group would otherwise skip the
     // other group's use of a slot and mistake the phase before it for its own.
@@ -1294,7 +1302,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
             prologue_attn_poll<GS>(a, ep_prev, sxq, sxs);
             ph = PH_O;
         } else {
-            prologue_quant_ll<GS>(a, a.zh, ep_prev, a.H_l, sxq, sxs, a.g[PH_DN].KT, a.g[PH_DN].G); // quantize(hb), layers.rs:478
+            prologue_quant_ll<GS>(a, a.zh, ep_prev, a.H_l, sxq_dn, sxs_dn, a.g[PH_DN].KT, a.g[PH_DN].G); // quantize(hb), layers.rs:478
             ph = PH_DN;
         }
         prof_mark(pr, 1 + 3 * kind);
@@ -1339,12 +1347,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
                 // row phases: batches of 32 rows x n_kt K tiles x up to 4 stages of 8 rows
                 const unsigned ep_out = ep_step;
                 const bool x_once = MEGA_X_ONCE && g.n_kt == 1; // the whole activation fits the registers: load it once per phase
-                if (x_once) load_x<GS>(xr, sxq, sxs, 0, g.KT, g.G, lane);
+                if (x_once) load_x<GS>(xr, kind == 4 ? sxq_dn : sxq, kind == 4 ? sxs_dn : sxs, 0, g.KT, g.G, lane);
                 for (int b0 = 0; b0 < count; b0 += MEGA_BATCH) {
                     const int nb = count - b0 < MEGA_BATCH ? count - b0 : MEGA_BATCH;
                     float acc0 = 0.f, acc1 = 0.f; // this warp's rows in its (up to) two stages of the batch
                     for (int kt = 0; kt < g.n_kt; kt++) {
-                        if (!x_once) load_x<GS>(xr, sxq, sxs, kt, g.KT, g.G, lane);
+                        if (!x_once) load_x<GS>(xr, kind == 4 ? sxq_dn : sxq, kind == 4 ? sxs_dn : sxs, kt, g.KT, g.G, lane);
                         prof_mark(pr, 58);
                         for (int sidx = 0; MEGA_GW * sidx < nb; sidx++) {
                             if ((sidx & 1) == grp) { // stages alternate between the two consumer groups
@@ -1450,7 +1458,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
         }
         // results carry their own flags: the only thing to wait for is this CTA's own warps (sxq / scratch are about to be rewritten)
         if (kind == 5) grid_barrier(a, bs, true, pr);
-        else csync();
+        else if (!(MEGA_LAZY_SYNC && kind >= 2)) csync();
         prof_mark(pr, 3 + 3 * kind);
     }
 

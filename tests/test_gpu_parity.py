@@ -646,10 +646,13 @@ def test_prefill_matches_oracle(models, ckpt, name, gs, seed, T):
         k, v = m.kv_read(l, 0, T)
         kr, vr = ko[l, :T].reshape(T, kvd), vo[l, :T].reshape(T, kvd)
         ek, ev = np.abs(k - kr), np.abs(v - vr)
-        if l == 0:  # embedding -> norm -> quantise -> QKV GEMM -> QK-norm / RoPE: exact up to float round-off, except in the rare token
-            # whose RMSNorm sum lands one ulp off the oracle's and flips an int8 activation (a row then moves by ~1e-3 .. 1e-2)
+        if l == 0:  # embedding -> norm -> quantise -> QKV GEMM -> QK-norm / RoPE: exact up to float round-off, except in the token
+            # whose RMSNorm sum lands an ulp off the oracle's and flips an int8 activation (a row then moves by ~1e-3 .. 1e-2).
+            # Layer 0 of the SYNTHETIC checkpoints is the worst case for that: the input is int8 x scale (the embedding row) times a
+            # bf16-rounded norm weight, so x / scale lands on exact .5 ties far more often than real activations do -- up to 18 % of
+            # the rows here (24 / 130 on small gs128; the sequential decode path flips the very same rows: scripts/diag/prefill_rows.py).
             rows_off = float(np.mean(ek.max(axis=1) > 1e-4))
-            assert np.median(ek) <= 1e-6 and np.median(ev) <= 1e-6 and rows_off <= 0.15 and ek.max() <= 2e-2, (rows_off, float(ek.max()))
+            assert np.median(ek) <= 1e-6 and np.median(ev) <= 1e-6 and rows_off <= 0.25 and ek.max() <= 2e-2, (rows_off, float(ek.max()))
         # deeper layers: an upstream flip perturbs every later element a little (and, through attention, later tokens), so only the
         # noise level is checked here -- the attention kernel itself is compared with float64 in test_prefill_attention_kernels_...
         assert np.median(ev) <= 1e-2 * max(1.0, float(np.abs(vr).max())), (l, float(np.median(ev)))
