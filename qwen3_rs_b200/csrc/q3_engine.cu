@@ -772,6 +772,21 @@ static int make_map_i8(CUtensorMap *map, const void *base, int rows, int K) {
     return 0;
 }
 
+// group-major scale matrix [groups][cols] f32 (row pitch cols * 4 bytes), box = 2 groups x 128 columns: the scale rows of one
+// accumulator pair arrive with ONE tensor copy
+static int make_map_scales(CUtensorMap *map, const float *base, int groups, int cols) {
+    auto enc = get_encode_fn();
+    if (!enc) return fail(Q3_ECUDA, "cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)groups};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {128, 2};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(Q3_ECUDA, "cuTensorMapEncodeTiled (scales) failed (%d) groups %d cols %d", (int)r, groups, cols);
+    return 0;
+}
+
 template <int GS, int EPI, int MODE>
 static int launch_gemm_q8_t(const CUtensorMap &mx, const CUtensorMap &mw, const PrefillGemmArgs &a, cudaStream_t s) {
     static bool attr = false;
@@ -785,8 +800,11 @@ static int launch_gemm_q8_t(const CUtensorMap &mx, const CUtensorMap &mw, const 
         CK(cudaGetDevice(&dev));
         CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
+    CUtensorMap mxs, mws;
+    int rc;
+    if ((rc = make_map_scales(&mxs, a.xsT, a.K / GS, a.Tpad)) || (rc = make_map_scales(&mws, a.wsT, a.K / GS, a.N))) return rc;
     const int tiles = (a.N / PF_BN) * (a.Tpad / PF_BM); // persistent: one CTA per SM walks the tiles
-    k_gemm_q8<GS, EPI, MODE><<<tiles < num_sms ? tiles : num_sms, PF_THREADS, PF_SMEM, s>>>(mx, mw, a);
+    k_gemm_q8<GS, EPI, MODE><<<tiles < num_sms ? tiles : num_sms, PF_THREADS, PF_SMEM, s>>>(mx, mw, mxs, mws, a);
     return 0;
 }
 // mode 0: the fast drain (what q3_prefill runs); 1: reference-order f32 fold (bit-identical to matmul); 2: dense ceiling
@@ -828,6 +846,10 @@ static int prefill_init(q3_handle *h) {
     if (h->tp_size != 1) { h->pf_why = "batched prefill is single-GPU for now"; return 0; }
     if (c.dim % 128 || h->AH_l % 128 || h->H_l % 128 || h->layers[0].qkv.rows % 128 || (2 * h->H_l) % 128) {
         h->pf_why = "matrix dimensions must be multiples of 128";
+        return 0;
+    }
+    if ((c.dim / c.group_size) % 2 || (h->AH_l / c.group_size) % 2 || (h->H_l / c.group_size) % 2) {
+        h->pf_why = "the tensor-core GEMM hands accumulators over in pairs: rows need an even number of quantisation groups";
         return 0;
     }
     if (!get_encode_fn()) { h->pf_why = "cuTensorMapEncodeTiled unavailable"; return 0; }
@@ -1727,7 +1749,7 @@ extern "C" int q3_op_gemm_q8(int device, const int8_t *xq, const float *xs, cons
                              int K, int gs, int exact, float *out) {
     int rc = op_prologue(device, gs);
     if (rc) return rc;
-    if (T <= 0 || N % 128 || K % 128 || K % gs) return fail(Q3_EINVAL, "need N %% 128 == 0, K %% 128 == 0");
+    if (T <= 0 || N % 128 || K % 128 || K % gs || (K / gs) % 2) return fail(Q3_EINVAL, "need N %% 128 == 0, K %% 128 == 0 and an even number of groups per row");
     const int Tpad = (T + 127) / 128 * 128, ng = K / gs;
     DevBuf dxq, dxsT, dwq, dws, dwsT, dout;
     if ((rc = dxq.alloc((size_t)Tpad * K)) || (rc = dxsT.alloc((size_t)ng * Tpad * 4)) || (rc = dwq.alloc((size_t)N * K)) ||
@@ -1835,7 +1857,7 @@ __global__ void k_fill_f32(float *p, size_t n, float v) {
 extern "C" int q3_bench_gemm_q8(int device, int T, int N, int K, int gs, int mode, int reps, float *ms_out) {
     int rc = op_prologue(device, gs);
     if (rc) return rc;
-    if (T <= 0 || N % 128 || K % 128 || K % gs || reps < 1 || mode < 0 || mode > 5) return fail(Q3_EINVAL, "bad gemm bench arguments");
+    if (T <= 0 || N % 128 || K % 128 || K % gs || (K / gs) % 2 || reps < 1 || mode < 0 || mode > 5) return fail(Q3_EINVAL, "bad gemm bench arguments");
     const int Tpad = (T + 127) / 128 * 128, ng = K / gs;
     DevBuf dxq, dxsT, dwq, dwsT, dout;
     if ((rc = dxq.alloc((size_t)Tpad * K)) || (rc = dxsT.alloc((size_t)ng * Tpad * 4)) || (rc = dwq.alloc((size_t)N * K)) ||

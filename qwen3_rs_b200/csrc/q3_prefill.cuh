@@ -10,9 +10,9 @@
 // adds its groups in order g = 0..ng-1 with unfused multiplies, i.e. exactly the reference's
 // left fold: the GEMM result is bit-identical to `matmul` applied token by token.
 //
-// Warp roles (576 threads): warps 0..15 = epilogue (TMEM lane quadrant = warp % 4, column quarter = warp / 4: 32 accumulator
+// Warp roles (608 threads): warps 0..15 = epilogue (TMEM lane quadrant = warp % 4, column quarter = warp / 4: 32 accumulator
 // columns per thread keep the register count low enough for 4 epilogue warps per scheduler), warp 16 = TMEM allocator + MMA
-// issuer, warp 17 = TMA producer.  The two single-thread roles sit in the HIGHEST warp ids on purpose: the warp scheduler
+// issuer, warp 17 = tile producer (TMA), warp 18 = scale-row producer (TMA).  The single-thread roles sit in the HIGHEST warp ids on purpose: the warp scheduler
 // favours the higher warp id among ready warps, and with the roles in warps 0 / 1 the MMA issuer was starved of issue slots
 // whenever the four epilogue warps of its scheduler were busy scaling -- the drain arithmetic then did not overlap with the
 // tensor pipe at all (measured: time = pipeline-only time + arithmetic time; profiles/r02_gemm_q8_ceilings.txt).
@@ -29,12 +29,11 @@ constexpr int PF_BM = 128, PF_BN = 128, PF_BK = 128; // tile: tokens x weight ro
 constexpr int PF_STAGES = 4;
 constexpr int PF_NACC = 4;                          // TMEM accumulator buffers (128 columns each), handed over in PAIRS
 constexpr int PF_EPI_WARPS = 16;                   // 4 TMEM lane quadrants x 4 column quarters
-constexpr int PF_THREADS = (2 + PF_EPI_WARPS) * 32;
-constexpr int PF_MMA_WARP = PF_EPI_WARPS, PF_TMA_WARP = PF_EPI_WARPS + 1; // highest warp ids: scheduling priority (see above)
+constexpr int PF_THREADS = (3 + PF_EPI_WARPS) * 32;
+constexpr int PF_MMA_WARP = PF_EPI_WARPS, PF_TMA_WARP = PF_EPI_WARPS + 1, PF_SCALE_WARP = PF_EPI_WARPS + 2; // highest warp ids: scheduling priority (see above)
 constexpr int PF_COLS = PF_BN / (PF_EPI_WARPS / 4); // accumulator columns per epilogue thread (32)
-constexpr int PF_SG = 4;                            // quantisation groups per scale-ring slot (even: accumulator pairs never straddle slots)
-constexpr int PF_SRING = 4;                         // scale-ring slots: PF_SG x (128 weight scales | 128 token scales) each
-constexpr int PF_SLA = 1;                           // scale rows are requested this many chunks ahead of their stage
+constexpr int PF_SG = 2;                            // quantisation groups per scale-ring slot: one accumulator pair (even: accumulator pairs never straddle slots)
+constexpr int PF_SRING = 8;                         // scale-ring slots: PF_SG x (128 weight scales | 128 token scales) each
 constexpr int PF_PATCH_LD = 36;                     // floats per row of a warp's 32 x 32 output patch
 constexpr int PF_SMEM = PF_STAGES * (PF_BM * PF_BK + PF_BN * PF_BK) + PF_SRING * PF_SG * 1024 + 1024 /* barriers */ +
                         PF_EPI_WARPS * 32 * PF_PATCH_LD * 4 + 1024 /* alignment slack */;
@@ -52,14 +51,21 @@ struct PrefillGemmArgs {
     float *q;          // [T][AH]
     float *kc, *vc;    // layer base of the caches [seq][KV]
     int AH, KV, pos0;
-    long long *trace;  // optional (Q3_PF_TRACE): [4][PF_TRACE_N] clock64 stamps of CTA 0 -- MMA thread: pair may be reused / pair committed;
+    long long *trace;  // optional (Q3_PF_TRACE): [20][PF_TRACE_N] clock64 stamps of CTA 0 -- MMA thread: pair may be reused / pair committed;
                        // epilogue warp 0: pair complete seen / pair released
 };
 constexpr int PF_TRACE_N = 512;
+#ifndef PF_TRACE
+#define PF_TRACE 0 // 1: build with the in-kernel pipeline stamps (a variant library for scripts/diag/gemm_trace.py; costs registers in the drain loop)
+#endif
+#if PF_TRACE
 #define PF_STAMP(row, idx)                                                                                  \
     do {                                                                                                    \
         if (a.trace && blockIdx.x == 0 && (idx) < PF_TRACE_N) a.trace[(row) * PF_TRACE_N + (idx)] = clock64(); \
     } while (0)
+#else
+#define PF_STAMP(row, idx) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
     // K-major, SWIZZLE_128B: 8-row atoms of 128 B, atoms 1024 B apart (SBO), LBO unused (=1), version 1
@@ -95,6 +101,24 @@ __device__ __forceinline__ void pf_wait(uint32_t bar, uint32_t parity) {
         if (ok) break;
         if (++n > (1u << 22)) __trap(); // never hang the GPU
     }
+}
+// One try, result consumed later: the ~100-250 clk a try_wait takes even on a completed barrier then overlap with whatever is
+// scheduled between the try and the use of its result.
+__device__ __forceinline__ uint32_t pf_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok;
+}
+// one lane of a CONVERGED warp (always the same one): the single-thread tcgen05 / TMA instructions are issued under this predicate
+// while the loop around them stays warp-uniform -- inside a divergent `if (lane == 0)` every operand of a uniform-datapath
+// instruction (UTCIMMA, UTCBAR, UTMALDG) has to be re-broadcast through an ELECT / R2UR / BRA.U.ANY loop (~8 instructions each)
+__device__ __forceinline__ bool pf_elect() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void pf_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ float4 lds128f(uint32_t saddr) {
@@ -142,71 +166,75 @@ __device__ __forceinline__ void pf_scale16(float *acc, const uint32_t (&d)[16], 
     }
 }
 
-// Drain one accumulator PAIR (N2 = 2 groups, or 1 at an odd tail) of this thread's 32 columns, as a stream of 16-column chunks
-// through two register buffers: the TMEM read of the next chunk is always in flight while the current one is being scaled.
-// The stream does not stop at the pair boundary: the first chunk of this pair (d0) was issued by the caller or by the previous
-// pair, and before the last chunk is scaled the first chunk of the NEXT pair (nxt_taddr, possibly of the next tile) is
-// requested -- so neither the wait for the MMA warp nor a TMEM read latency sits exposed between two pairs.  The pair is handed
-// back to the MMA warp as soon as its last read has landed in registers.  srow: shared address of the first group's scale row
-// (ws[128] | xs[128]; the next group's row follows 1 KB later).
-template <int VAR, int N2>
-__device__ __forceinline__ void pf_drain_pair(float (&acc)[PF_COLS], uint32_t (&d0)[16], uint32_t (&d1)[16], uint32_t taddr, uint32_t srow, int part,
-                                              int m, uint32_t tempty_bar, int lane, bool has_next, uint32_t nxt_taddr, uint32_t nxt_bar,
-                                              uint32_t nxt_parity, long long *trace, int pt) {
-    const bool stamp = trace && pt + 1 < PF_TRACE_N && blockIdx.x == 0 && threadIdx.x == 0;
-    const uint32_t ws0 = srow + part * (PF_COLS * 4), xsa = srow + 512 + m * 4;
-    if (VAR == 4) { // timing experiment: the hand-shake alone (no TMEM read, no arithmetic)
+// Shared-memory layout of k_gemm_q8 as byte offsets from the 1 KB-aligned base: every address the hot loops use is base + constant
+constexpr uint32_t PF_OFF_A = 0;                                                 // [STAGES][128 rows][128 B] activation tiles
+constexpr uint32_t PF_OFF_B = PF_STAGES * PF_BM * PF_BK;                         // [STAGES][128 rows][128 B] weight tiles
+constexpr uint32_t PF_OFF_SCALE = PF_STAGES * (PF_BM + PF_BN) * PF_BK;           // [PF_SRING][ws g0 | ws g1 | xs g0 | xs g1] x 128 f32
+constexpr uint32_t PF_OFF_BAR = PF_OFF_SCALE + PF_SRING * PF_SG * 1024;          // mbarriers (8 B each), then the TMEM base slot
+constexpr uint32_t PF_BAR_FULL = PF_OFF_BAR, PF_BAR_EMPTY = PF_BAR_FULL + 8 * PF_STAGES, PF_BAR_TFULL = PF_BAR_EMPTY + 8 * PF_STAGES,
+                   PF_BAR_TEMPTY = PF_BAR_TFULL + 16 /* [2 pair slots][2 groups] */, PF_BAR_SFULL = PF_BAR_TEMPTY + 32,
+                   PF_BAR_SEMPTY = PF_BAR_SFULL + 8 * PF_SRING, PF_OFF_TMEM = PF_BAR_SEMPTY + 8 * PF_SRING;
+constexpr uint32_t PF_OFF_PATCH = PF_OFF_BAR + 1024;                             // [16 warps][32 rows][PF_PATCH_LD] f32 output patches
+static_assert(PF_OFF_TMEM + 4 <= PF_OFF_PATCH, "barrier block");
+static_assert(PF_OFF_PATCH + PF_EPI_WARPS * 32 * PF_PATCH_LD * 4 + 1024 <= PF_SMEM, "shared memory budget");
+
+__device__ __forceinline__ void sts128f(uint32_t saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Drain one accumulator PAIR (two quantisation groups) of this thread's 32 columns, as a stream of 16-column chunks through
+// two register buffers: the TMEM read of the next chunk is always in flight while the current one is being scaled.  The
+// stream does not stop at the pair boundary -- the first chunk of this pair (d0) was requested while the previous pair was
+// being finished, and before the last chunk is scaled the first chunk of the NEXT pair (nxt_taddr, possibly of the next tile)
+// is requested; whether that pair is complete is asked (try_wait) one scaling block earlier and looked at only then, so
+// neither the barrier latency nor a TMEM read latency sits exposed between two pairs.  Each group accumulator goes back to the
+// MMA warp as soon as its second chunk has landed in registers (group 0 two scaling blocks before group 1).
+// ws0 / xsa: shared addresses of this thread's 32 weight scales / its token scale for the pair's first group (the second group's
+// follow 512 B later).  tempty_bar: the slot's two "drained" barriers (group 0, group 1).
+template <int VAR>
+__device__ __forceinline__ void pf_drain_pair(float (&acc)[PF_COLS], uint32_t (&d0)[16], uint32_t (&d1)[16], uint32_t taddr, uint32_t ws0, uint32_t xsa,
+                                              uint32_t tempty_bar, int lane, uint32_t nxt_taddr, uint32_t nxt_bar, uint32_t nxt_parity) {
+    if (VAR >= 4) { // timing experiments: 4 = the hand-shake alone; 5 = the arithmetic on whatever the chunk registers hold (no TMEM read)
+        if (VAR == 5) {
+            const float xs = lds_f32(xsa), xsb = lds_f32(xsa + 512);
+            pf_scale16<0>(acc, d0, ws0, xs);
+            pf_scale16<0>(acc + 16, d1, ws0 + 64, xs);
+            pf_scale16<0>(acc, d0, ws0 + 512, xsb);
+            pf_scale16<0>(acc + 16, d1, ws0 + 512 + 64, xsb);
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) pf_arrive(tempty_bar);
-        if (has_next) pf_wait(nxt_bar, nxt_parity);
+        if (lane == 0) {
+            pf_arrive(tempty_bar);
+            pf_arrive(tempty_bar + 8);
+        }
+        pf_wait(nxt_bar, nxt_parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         return;
     }
     const float xs = lds_f32(xsa);
-    if (VAR == 5) { // timing experiment: the arithmetic alone, on whatever the chunk registers hold (no TMEM read)
-        pf_scale16<0>(acc, d0, ws0, xs);
-        pf_scale16<0>(acc + 16, d1, ws0 + 64, xs);
-        if (N2 == 2) {
-            const float xsb = lds_f32(xsa + 1024);
-            pf_scale16<0>(acc, d0, ws0 + 1024, xsb);
-            pf_scale16<0>(acc + 16, d1, ws0 + 1024 + 64, xsb);
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) pf_arrive(tempty_bar);
-        if (has_next) pf_wait(nxt_bar, nxt_parity);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        return;
-    }
     pf_wait_ld(); // d0 = group 0, columns 0..15
     PF_LD16(d1, taddr + 16);
     pf_scale16<VAR>(acc, d0, ws0, xs);
     pf_wait_ld();
-    float xl = xs;
-    uint32_t wl = ws0 + 64; // scale row / token scale of the LAST chunk (in d1)
-    if (N2 == 2) {
-        PF_LD16(d0, taddr + PF_BN);
-        const float xsb = lds_f32(xsa + 1024);
-        pf_scale16<VAR>(acc + 16, d1, ws0 + 64, xs);
-        pf_wait_ld();
-        PF_LD16(d1, taddr + PF_BN + 16);
-        pf_scale16<VAR>(acc, d0, ws0 + 1024, xsb);
-        pf_wait_ld();
-        xl = xsb;
-        wl = ws0 + 1024 + 64;
-    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
-    if (lane == 0) pf_arrive(tempty_bar); // pair drained into registers: the MMA warp may reuse it
-    if (stamp) trace[3 * PF_TRACE_N + pt] = clock64();
-    if (has_next) { // first chunk of the next pair: in flight while the last chunk of this one is scaled
-        pf_wait(nxt_bar, nxt_parity);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (stamp) trace[2 * PF_TRACE_N + pt + 1] = clock64();
-        PF_LD16(d0, nxt_taddr);
-    }
-    pf_scale16<VAR>(acc + 16, d1, wl, xl);
+    if (lane == 0) pf_arrive(tempty_bar); // group 0 of the pair is in registers: its accumulator may be refilled already
+    PF_LD16(d0, taddr + PF_BN);
+    const float xsb = lds_f32(xsa + 512);
+    pf_scale16<VAR>(acc + 16, d1, ws0 + 64, xs);
+    pf_wait_ld();
+    PF_LD16(d1, taddr + PF_BN + 16);
+    const uint32_t nxt_ok = pf_try(nxt_bar, nxt_parity); // asked now, looked at after the scaling block below
+    pf_scale16<VAR>(acc, d0, ws0 + 512, xsb);
+    pf_wait_ld();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) pf_arrive(tempty_bar + 8); // group 1 drained into registers
+    if (!nxt_ok) pf_wait(nxt_bar, nxt_parity);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    PF_LD16(d0, nxt_taddr); // first chunk of the next pair: in flight while the last chunk of this one is scaled
+    pf_scale16<VAR>(acc + 16, d1, ws0 + 512 + 64, xsb);
 }
 
 // MODE: 0 = fast drain (what q3_prefill runs): the same exact int32 group dots, folded with packed f32x2 FMAs.
@@ -215,138 +243,131 @@ __device__ __forceinline__ void pf_drain_pair(float (&acc)[PF_COLS], uint32_t (&
 //       2 = dense ceiling (timing experiment only: the group structure is ignored, all of K is accumulated in ONE TMEM
 //           buffer and drained once per tile -- what this tiling / pipeline reaches as a plain int8 GEMM; the output is the raw
 //           integer dot converted to f32).
-//       3 / 4 = timing experiments on the grouped pipeline (outputs are garbage): 3 = every group accumulator is read out of
-//           TMEM but not scaled; 4 = the accumulator hand-shake alone, no TMEM read; 5 = the scaling arithmetic without TMEM reads.
+//       3 / 4 / 5 = timing experiments on the grouped pipeline (outputs are garbage): 3 = every group accumulator is read out
+//           of TMEM but not scaled; 4 = the accumulator hand-shake alone, no TMEM read; 5 = the scaling arithmetic without TMEM reads.
+// K / GS must be even (checked by the host): the unit of hand-over between the MMA warp and the epilogue is a PAIR of group
+// accumulators (2 x 128 TMEM columns; two pair slots fill the 512 columns), and a scale-ring slot holds the rows of one pair.
 // PERSISTENT: grid = min(tiles, SMs); a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (token tile fastest, so the
 // CTAs running together share weight tiles in L2).  The TMA and MMA warps run straight on into the next tile (stage ring,
 // accumulator pairs and scale ring keep their running indices), so a tile's output store and the pipeline refill overlap
 // and TMEM is allocated once per SM instead of once per tile.
 template <int GS, int EPI, int MODE>
-__global__ void __launch_bounds__(PF_THREADS, 1) // 96 registers: two schedulers host 5 warps (16384 / (5 x 32) = 102; 112 does not launch)
-    k_gemm_q8(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const PrefillGemmArgs a) {
+__global__ void __launch_bounds__(PF_THREADS, 1) // 96 registers: three schedulers host 5 warps (16384 / (5 x 32) = 102; 112 does not launch)
+    k_gemm_q8(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_xs,
+              const __grid_constant__ CUtensorMap map_ws, const PrefillGemmArgs a) {
     extern __shared__ __align__(1024) uint8_t pf_smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(pf_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *sA = smem;                                  // [STAGES][128 rows][128 B]
-    uint8_t *sB = smem + PF_STAGES * PF_BM * PF_BK;      // [STAGES][128 rows][128 B]
-    float *sscale = reinterpret_cast<float *>(smem + PF_STAGES * (PF_BM + PF_BN) * PF_BK); // [PF_SRING][PF_SG][ws 128 | xs 128]
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + PF_STAGES * (PF_BM + PF_BN) * PF_BK + PF_SRING * PF_SG * 1024);
-    uint64_t *empty = full + PF_STAGES;
-    uint64_t *tfull = empty + PF_STAGES;   // [2] accumulator pair complete
-    uint64_t *tempty = tfull + 2;          // [2] accumulator pair drained
-    uint64_t *sfull = tempty + 2;          // [PF_SRING]
-    uint64_t *sempty = sfull + PF_SRING;   // [PF_SRING]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sempty + PF_SRING);
-    float *sstage = reinterpret_cast<float *>(smem + PF_STAGES * (PF_BM + PF_BN) * PF_BK + PF_SRING * PF_SG * 1024 + 1024); // [16 warps][32][36]
-
+    const uint32_t sb = smem_u32(smem); // every shared address below is sb + a constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = a.Tpad / PF_BM, ntile = mt * (a.N / PF_BN);
     const int nkb = a.K / PF_BK;
     constexpr int GPS = PF_BK / GS; // groups per stage
     constexpr int KPG = GS / 32;    // MMA K-steps per group
-    const int ng = a.K / GS;
-    constexpr bool EXACT = MODE == 1, DENSE = MODE == 2;
-    static_assert(PF_SG % 2 == 0 && PF_NACC == 4, "accumulator pairs");
+    const int ng = a.K / GS, npair = ng >> 1;
+    constexpr bool DENSE = MODE == 2;
+    static_assert(PF_NACC == 4 && PF_SG == 2 && (PF_SRING & (PF_SRING - 1)) == 0, "pairs");
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < PF_STAGES; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(reinterpret_cast<uint64_t *>(smem + PF_BAR_FULL) + s, 1);
+            mbar_init(reinterpret_cast<uint64_t *>(smem + PF_BAR_EMPTY) + s, 1);
         }
-        for (int b = 0; b < 2; b++) {
-            mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], PF_EPI_WARPS); // one arrive per epilogue warp
-        }
+        for (int b = 0; b < 2; b++) mbar_init(reinterpret_cast<uint64_t *>(smem + PF_BAR_TFULL) + b, 1);
+        for (int b = 0; b < 4; b++) mbar_init(reinterpret_cast<uint64_t *>(smem + PF_BAR_TEMPTY) + b, PF_EPI_WARPS); // one arrive per epilogue warp
         for (int b = 0; b < PF_SRING; b++) {
-            mbar_init(&sfull[b], 1);
-            mbar_init(&sempty[b], PF_EPI_WARPS);
+            mbar_init(reinterpret_cast<uint64_t *>(smem + PF_BAR_SFULL) + b, 1);
+            mbar_init(reinterpret_cast<uint64_t *>(smem + PF_BAR_SEMPTY) + b, PF_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xs) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ws) : "memory");
     }
     if (warp == PF_MMA_WARP) { // TMEM: all 512 columns = 2 pairs of 128 x 128 int32 accumulators
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sb + PF_OFF_TMEM), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = *reinterpret_cast<uint32_t *>(smem + PF_OFF_TMEM);
 
     if (warp == PF_TMA_WARP) {
-        // ------------------------------- TMA producer -------------------------------
-        if (lane == 0) {
-            uint64_t policy;
-            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-            // The scale rows travel PF_SLA chunks (of PF_SG groups) AHEAD of the stage that carries their first group -- also across
-            // tile boundaries: a 512-byte bulk copy queues behind the tile traffic for a microsecond or two, and issued together with
-            // its stage the rows arrived ~500 clk after the accumulators they belong to (in-kernel trace: every first pair of a chunk
-            // took 1 500 clk instead of 980).  Waiting for a free slot cannot deadlock: it only depends on chunks whose stages are out.
-            const int nchunk = (ng + PF_SG - 1) / PF_SG;
-            const int my_tiles = ((int)blockIdx.x < ntile) ? (ntile - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-            const int total_chunks = DENSE ? 0 : my_tiles * nchunk;
-            int kbt = 0, sc = 0; // running stage uses across tiles; scale chunks issued
-            auto issue_scale = [&](int G) {
-                const int ti = G / nchunk, c = G - ti * nchunk, tile = blockIdx.x + ti * gridDim.x;
-                const int m0 = (tile % mt) * PF_BM, n0 = (tile / mt) * PF_BN;
-                const int g0 = c * PF_SG, n = ng - g0 < PF_SG ? ng - g0 : PF_SG;
-                const int sl = G % PF_SRING;
-                mbar_wait_spin(&sempty[sl], ((G / PF_SRING) & 1) ^ 1);
-                mbar_expect_tx(&sfull[sl], n * 1024);
-                for (int j = 0; j < n; j++) {
-                    float *row = sscale + (sl * PF_SG + j) * 256;
-                    bulk_g2s(row, a.wsT + (size_t)(g0 + j) * a.N + n0, 512, &sfull[sl], policy);
-                    bulk_g2s(row + 128, a.xsT + (size_t)(g0 + j) * a.Tpad + m0, 512, &sfull[sl], policy);
+        // ------------------------------- tile producer (whole warp runs the loop, one elected lane issues) -------------------------------
+        int kbt = 0; // running stage uses across tiles
+        for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+            const int m0 = (tile % mt) * PF_BM, n0 = (tile / mt) * PF_BN;
+            for (int kb = 0; kb < nkb; kb++, kbt++) {
+                const int s = kbt % PF_STAGES;
+                pf_wait(sb + PF_BAR_EMPTY + 8 * s, ((kbt / PF_STAGES) & 1) ^ 1);
+                if (pf_elect()) {
+                    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + PF_BAR_FULL) + s;
+                    mbar_expect_tx(bar, (PF_BM + PF_BN) * PF_BK);
+                    tma_load_2d(smem + PF_OFF_A + (size_t)s * PF_BM * PF_BK, &map_x, kb * PF_BK, m0, bar);
+                    tma_load_2d(smem + PF_OFF_B + (size_t)s * PF_BN * PF_BK, &map_w, kb * PF_BK, n0, bar);
                 }
-            };
-            int ti = 0;
-            for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x, ti++) {
+                __syncwarp();
+            }
+        }
+    } else if (warp == PF_SCALE_WARP) {
+        // ------------------------------- scale-row producer -------------------------------
+        // The scale rows of an accumulator pair (2 groups x 128 weight scales, 2 groups x 128 token scales: two tensor copies) go
+        // through their own ring, fed by their own warp: it runs as far ahead of the epilogue as the ring is deep (PF_SRING pairs,
+        // across tile boundaries), independent of the tile producer.  History: as eight 512-byte bulk copies per stage issued by the
+        // tile producer from a divergent single-lane branch, the scale traffic -- not the tensor pipe, not the epilogue -- set the
+        // pace of the whole kernel (8B gate/up: 650 us; the same kernel with the scale traffic switched off: 457 us).
+#ifndef PF_DBG_NOSCALE // (timing experiment: no scale-row traffic at all, the epilogue scales with stale shared memory)
+        if (!DENSE) {
+            int sc = 0; // running pair count
+            for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
                 const int m0 = (tile % mt) * PF_BM, n0 = (tile / mt) * PF_BN;
-                for (int kb = 0; kb < nkb; kb++, kbt++) {
-                    const int Gs = ti * nchunk + (kb * GPS) / PF_SG; // chunk this stage's first group belongs to
-                    while (sc <= Gs + PF_SLA && sc < total_chunks) issue_scale(sc++);
-                    const int s = kbt % PF_STAGES;
-                    mbar_wait_spin(&empty[s], ((kbt / PF_STAGES) & 1) ^ 1);
-                    mbar_expect_tx(&full[s], (PF_BM + PF_BN) * PF_BK);
-                    tma_load_2d(sA + (size_t)s * PF_BM * PF_BK, &map_x, kb * PF_BK, m0, &full[s]);
-                    tma_load_2d(sB + (size_t)s * PF_BN * PF_BK, &map_w, kb * PF_BK, n0, &full[s]);
+                for (int c = 0; c < npair; c++, sc++) {
+                    const int sl = sc & (PF_SRING - 1);
+                    pf_wait(sb + PF_BAR_SEMPTY + 8 * sl, ((sc / PF_SRING) & 1) ^ 1);
+                    if (pf_elect()) {
+                        uint64_t *bar = reinterpret_cast<uint64_t *>(smem + PF_BAR_SFULL) + sl;
+                        mbar_expect_tx(bar, 2048);
+                        tma_load_2d(smem + PF_OFF_SCALE + sl * 2048, &map_ws, n0, 2 * c, bar);
+                        tma_load_2d(smem + PF_OFF_SCALE + sl * 2048 + 1024, &map_xs, m0, 2 * c, bar);
+                    }
+                    __syncwarp();
                 }
             }
         }
+#endif
     } else if (warp == PF_MMA_WARP) {
-        // ------------------------------- MMA issuer -------------------------------
-        if (lane == 0) {
-            // instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 128, M = 128
-            constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((PF_BN >> 3) << 17) | ((PF_BM >> 4) << 24);
-            int kbt = 0, pt = 0, titer = 0; // running stage uses, accumulator-pair uses, tiles
-            const uint32_t b_full = smem_u32(full), b_tempty = smem_u32(tempty);
-            const uint64_t desc_a0 = umma_desc_k_sw128(smem_u32(sA)), desc_b0 = umma_desc_k_sw128(smem_u32(sB));
-            for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x, titer++) {
-                int gi = 0;
-                for (int kb = 0; kb < nkb; kb++, kbt++) {
-                    const int s = kbt % PF_STAGES;
-                    pf_wait(b_full + 8 * s, (kbt / PF_STAGES) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    // descriptors of this stage: the start-address field counts 16-byte units (stages are 16 KB apart, K-steps 32 B)
-                    const uint64_t da = desc_a0 + (uint64_t)(s * (PF_BM * PF_BK / 16)), db = desc_b0 + (uint64_t)(s * (PF_BN * PF_BK / 16));
+        // ------------------------------- MMA issuer (whole warp runs the loop, one elected lane issues) -------------------------------
+        // instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 128, M = 128
+        constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((PF_BN >> 3) << 17) | ((PF_BM >> 4) << 24);
+        uint64_t *tfull = reinterpret_cast<uint64_t *>(smem + PF_BAR_TFULL), *empty = reinterpret_cast<uint64_t *>(smem + PF_BAR_EMPTY);
+        int kbt = 0, pt = 0, titer = 0; // running stage uses, accumulator-pair uses, tiles
+        const uint64_t desc_a0 = umma_desc_k_sw128(sb + PF_OFF_A), desc_b0 = umma_desc_k_sw128(sb + PF_OFF_B);
+        for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x, titer++) {
+            int gi = 0;
+            for (int kb = 0; kb < nkb; kb++, kbt++) {
+                const int s = kbt % PF_STAGES;
+                pf_wait(sb + PF_BAR_FULL + 8 * s, (kbt / PF_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // descriptors of this stage: the start-address field counts 16-byte units (stages are 16 KB apart, K-steps 32 B)
+                const uint64_t da = desc_a0 + (uint64_t)(s * (PF_BM * PF_BK / 16)), db = desc_b0 + (uint64_t)(s * (PF_BN * PF_BK / 16));
 #pragma unroll
-                    for (int gg = 0; gg < GPS; gg++, gi++) {
-                        const int ps = pt & 1;
-                        uint32_t col;
-                        if (DENSE) {
-                            col = 0;
-                            if (gi == 0) { // the previous tile's accumulator has been read out
-                                pf_wait(b_tempty, (titer & 1) ^ 1);
-                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            }
-                        } else {
-                            col = ps * 2 * PF_BN + (gi & 1) * PF_BN;
-                            if ((gi & 1) == 0) { // first group of a pair: the pair has been drained
-                                pf_wait(b_tempty + 8 * ps, ((pt >> 1) & 1) ^ 1);
-                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                                PF_STAMP(0, pt);
-                            }
+                for (int gg = 0; gg < GPS; gg++, gi++) {
+                    const int ps = pt & 1;
+                    uint32_t col;
+                    if (DENSE) {
+                        col = 0;
+                        if (gi == 0) { // the previous tile's accumulator has been read out
+                            pf_wait(sb + PF_BAR_TEMPTY, (titer & 1) ^ 1);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         }
+                    } else { // each group accumulator of a pair is handed back on its own: the first one two scaling blocks earlier
+                        col = ps * 2 * PF_BN + (gi & 1) * PF_BN;
+                        pf_wait(sb + PF_BAR_TEMPTY + 8 * (2 * ps + (gi & 1)), ((pt >> 1) & 1) ^ 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (lane == 0 && (gi & 1) == 0) PF_STAMP(0, pt);
+                    }
+                    if (pf_elect()) {
 #pragma unroll
                         for (int kk = 0; kk < KPG; kk++) {
                             const uint32_t koff = (gg * GS + kk * 32) >> 4; // along K inside the 128 B swizzle span, in 16-byte units
@@ -354,85 +375,74 @@ __global__ void __launch_bounds__(PF_THREADS, 1) // 96 registers: two schedulers
                         }
                         if (DENSE) {
                             if (gi == ng - 1) umma_commit(&tfull[0]);
-                        } else if ((gi & 1) || gi == ng - 1) { // pair (or odd tail) complete -> epilogue
+                        } else if (gi & 1) { // pair complete -> epilogue
                             umma_commit(&tfull[ps]);
-                            PF_STAMP(1, pt);
-                            pt++;
                         }
                     }
-                    umma_commit(&empty[s]); // all MMAs reading this stage retired -> TMA may refill it
+                    __syncwarp();
+                    if (!DENSE && (gi & 1)) {
+                        if (lane == 0) PF_STAMP(1, pt);
+                        pt++;
+                    }
                 }
+                if (pf_elect()) umma_commit(&empty[s]); // all MMAs reading this stage retired -> TMA may refill it
+                __syncwarp();
             }
         }
-    } else {
+        if (!DENSE) { // one empty pair: the epilogue's last look-ahead waits for it (and reads an accumulator nobody uses)
+            if (pf_elect()) umma_commit(&tfull[pt & 1]);
+            __syncwarp();
+        }
+    } else if (warp < PF_EPI_WARPS) {
         // ------------------------------- epilogue -------------------------------
-        const int quad = warp & 3;          // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
-        const int part = warp >> 2;         // which PF_COLS accumulator columns
-        const int m = quad * 32 + lane;     // row of the tile = token
+        const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
+        const int part = warp >> 2; // which PF_COLS accumulator columns
         const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16) + part * PF_COLS;
-        const uint32_t s_scale = smem_u32(sscale), b_tfull = smem_u32(tfull), b_tempty = smem_u32(tempty), b_sfull = smem_u32(sfull),
-                       b_sempty = smem_u32(sempty);
-        int pt = 0, ct = 0, titer = 0;
-        bool primed = false;     // d0 already holds (or is receiving) the first chunk of the pair about to be drained
-        uint32_t d0[16], d1[16]; // the two chunk buffers of the TMEM read stream (live across pairs and tiles)
+        const uint32_t wsx = sb + PF_OFF_SCALE + part * (PF_COLS * 4);                 // this thread's weight scales in scale slot 0, row 0
+        const uint32_t xsx = sb + PF_OFF_SCALE + 1024 + (quad * 32 + lane) * 4;        // its token scale (slot: ws g0 | ws g1 | xs g0 | xs g1)
+        int pt = 0, titer = 0;      // running pair count (pair slot = pt & 1, scale slot = pt & (PF_SRING - 1)), tiles
+        uint32_t d0[16], d1[16];    // the two chunk buffers of the TMEM read stream (live across pairs and tiles)
         if (MODE == 5) {
 #pragma unroll
             for (int j = 0; j < 16; j++) d0[j] = d1[j] = threadIdx.x + j;
         }
+        uint32_t s_ok = 0;          // the scale rows of the pair about to start are known to have landed (asked ahead of time)
+        if (!DENSE) {               // the very first pair of this CTA: nobody has requested its first chunk yet
+            pf_wait(sb + PF_BAR_TFULL, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (MODE < 4) PF_LD16(d0, tq);
+        }
         for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x, titer++) {
-            const int m0 = (tile % mt) * PF_BM, n0 = (tile / mt) * PF_BN;
-            const int t = m0 + m;
             float acc[PF_COLS];
 #pragma unroll
             for (int j = 0; j < PF_COLS; j++) acc[j] = 0.0f;
             if (DENSE) {
-                pf_wait(b_tfull, titer & 1);
+                pf_wait(sb + PF_BAR_TFULL, titer & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 PF_LD16(d0, tq);
                 PF_LD16(d1, tq + 16);
                 pf_wait_ld();
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) pf_arrive(b_tempty);
+                if (lane == 0) pf_arrive(sb + PF_BAR_TEMPTY);
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     acc[j] = (float)(int)d0[j];
                     acc[16 + j] = (float)(int)d1[j];
                 }
             } else {
-                const bool last_tile = tile + (int)gridDim.x >= ntile;
-                if (!primed) { // the very first pair of this CTA: nobody has requested its first chunk yet
-                    pf_wait(b_tfull + 8 * (pt & 1), (pt >> 1) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (MODE < 4) PF_LD16(d0, tq + (pt & 1) * 2 * PF_BN);
-                    primed = true;
-                }
-                for (int g0 = 0; g0 < ng; g0 += PF_SG, ct++) {
-                    const int sl = ct % PF_SRING;
-                    pf_wait(b_sfull + 8 * sl, (ct / PF_SRING) & 1); // scale rows of these PF_SG groups landed
-                    const uint32_t srow = s_scale + sl * (PF_SG * 1024);
-                    if (ng - g0 >= PF_SG) {
-#pragma unroll
-                        for (int j = 0; j < PF_SG; j += 2, pt++) {
-                            const int ps = pt & 1, nps = ps ^ 1;
-                            const bool has_next = !(last_tile && g0 + j + 2 >= ng);
-                            pf_drain_pair<MODE, 2>(acc, d0, d1, tq + ps * 2 * PF_BN, srow + j * 1024, part, m, b_tempty + 8 * ps, lane, has_next,
-                                                   tq + nps * 2 * PF_BN, b_tfull + 8 * nps, ((pt + 1) >> 1) & 1, a.trace, pt);
-                        }
-                    } else {
-                        for (int j = 0; j < ng - g0; j += 2, pt++) {
-                            const int ps = pt & 1, nps = ps ^ 1;
-                            const bool has_next = !(last_tile && g0 + j + 2 >= ng);
-                            if (ng - g0 - j >= 2)
-                                pf_drain_pair<MODE, 2>(acc, d0, d1, tq + ps * 2 * PF_BN, srow + j * 1024, part, m, b_tempty + 8 * ps, lane, has_next,
-                                                       tq + nps * 2 * PF_BN, b_tfull + 8 * nps, ((pt + 1) >> 1) & 1, a.trace, pt);
-                            else
-                                pf_drain_pair<MODE, 1>(acc, d0, d1, tq + ps * 2 * PF_BN, srow + j * 1024, part, m, b_tempty + 8 * ps, lane, has_next,
-                                                       tq + nps * 2 * PF_BN, b_tfull + 8 * nps, ((pt + 1) >> 1) & 1, a.trace, pt);
-                        }
-                    }
+#pragma unroll 1
+                for (int c = 0; c < npair; c++, pt++) {
+                    const uint32_t ps = pt & 1, sl = pt & (PF_SRING - 1);
+#ifndef PF_DBG_NOSCALE
+                    if (!s_ok) pf_wait(sb + PF_BAR_SFULL + 8 * sl, (pt / PF_SRING) & 1); // the pair's scale rows landed
+                    // the next pair's scale rows: asked for here, looked at when they are needed (never, after the very last pair)
+                    s_ok = pf_try(sb + PF_BAR_SFULL + 8 * ((pt + 1) & (PF_SRING - 1)), ((pt + 1) / PF_SRING) & 1);
+#endif
+                    pf_drain_pair<MODE>(acc, d0, d1, tq + ps * (2 * PF_BN), wsx + sl * 2048, xsx + sl * 2048, sb + PF_BAR_TEMPTY + 16 * ps, lane,
+                                        tq + (ps ^ 1) * (2 * PF_BN), sb + PF_BAR_TFULL + 8 * (ps ^ 1), ((pt + 1) >> 1) & 1);
                     __syncwarp();
-                    if (lane == 0) pf_arrive(b_sempty + 8 * sl); // scale rows consumed
+                    if (lane == 0) pf_arrive(sb + PF_BAR_SEMPTY + 8 * sl); // scale rows consumed
                 }
             }
             // ---- write the tile out ----
@@ -441,10 +451,11 @@ __global__ void __launch_bounds__(PF_THREADS, 1) // 96 registers: two schedulers
             // therefore turns its 32 x 32 block through a private shared-memory patch (pitch 36 floats: conflict-free for the
             // 128-bit stores and loads) and writes 4 full 128-byte row segments per instruction.
             {
-                float *patch = sstage + warp * (32 * PF_PATCH_LD);
+                const int m0 = (tile % mt) * PF_BM, n0 = (tile / mt) * PF_BN;
+                const uint32_t patch = sb + PF_OFF_PATCH + warp * (32 * PF_PATCH_LD * 4);
 #pragma unroll
                 for (int j4 = 0; j4 < PF_COLS / 4; j4++)
-                    *reinterpret_cast<float4 *>(patch + lane * PF_PATCH_LD + 4 * j4) = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
+                    sts128f(patch + (lane * PF_PATCH_LD + 4 * j4) * 4, make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]));
                 __syncwarp();
                 const int r4 = lane >> 3, c4 = lane & 7;
                 const int c0 = n0 + part * PF_COLS; // first column of the warp's block
@@ -458,7 +469,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) // 96 registers: two schedulers
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const int row = 4 * k + r4, tr = m0 + quad * 32 + row;
-                    const float4 v = *reinterpret_cast<const float4 *>(patch + row * PF_PATCH_LD + 4 * c4);
+                    const float4 v = lds128f(patch + (row * PF_PATCH_LD + 4 * c4) * 4);
                     if (tr < a.T) {
                         if (EPI == PF_EPI_SWIGLU) { // rows interleaved (gate_j, up_j): layers.rs:472-475
                             const float s0 = __fmul_rn(v.x, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v.x))));
@@ -478,6 +489,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) // 96 registers: two schedulers
                 __syncwarp(); // the patch is rewritten at the end of the next tile
             }
         }
+        pf_wait_ld(); // the stream's last look-ahead read
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
