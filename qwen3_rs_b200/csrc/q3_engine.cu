@@ -123,7 +123,9 @@ struct q3_handle {
     // batched prefill (tcgen05 GEMM) state
     bool pf_ok = false;
     std::string pf_why;
-    bool pf_attn_f32 = false; // Q3_PF_ATTN_F32=1: the CUDA-core f32 attention instead of the tensor-core one (comparison)
+    int pf_attn_kind = 0;     // 0: tensor cores, FP16 hi/lo split (default); 1: Q3_PF_ATTN_F32=1, f32 on the CUDA cores; 2: Q3_PF_ATTN_TF32=1, 3xTF32
+    __half *pf_kvh = nullptr; // [4][pf_kvh_rows][KV_l] halves: this layer's K / V rows split into hi / lo (k_pf_split_kv)
+    size_t pf_kvh_rows = 0;
     int pf_cap = 0;          // token capacity of the buffers below (multiple of 128)
     float *pf_x = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_hb = nullptr, *pf_xsT = nullptr, *pf_hsT = nullptr;
     int8_t *pf_xq = nullptr, *pf_hq = nullptr;
@@ -853,7 +855,11 @@ static int prefill_init(q3_handle *h) {
         return 0;
     }
     if (!get_encode_fn()) { h->pf_why = "cuTensorMapEncodeTiled unavailable"; return 0; }
-    h->pf_attn_f32 = getenv("Q3_PF_ATTN_F32") != nullptr;
+    h->pf_attn_kind = getenv("Q3_PF_ATTN_F32") ? 1 : getenv("Q3_PF_ATTN_TF32") ? 2 : 0;
+    CK(cudaFuncSetAttribute(k_pf_attention_h<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFH_SMEM));
+    CK(cudaFuncSetAttribute(k_pf_attention_h<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFH_SMEM));
+    CK(cudaFuncSetAttribute(k_pf_attention_h<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFH_SMEM));
+    CK(cudaFuncSetAttribute(k_pf_attention_h<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFH_SMEM));
     CK(cudaFuncSetAttribute(k_pf_attention<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFA_SMEM));
     CK(cudaFuncSetAttribute(k_pf_attention<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFA_SMEM));
     CK(cudaFuncSetAttribute(k_pf_attention<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFA_SMEM));
@@ -875,6 +881,9 @@ static int prefill_init(q3_handle *h) {
 }
 
 static void prefill_release(q3_handle *h) {
+    if (h->pf_kvh) cudaFree(h->pf_kvh);
+    h->pf_kvh = nullptr;
+    h->pf_kvh_rows = 0;
     void **ps[] = {(void **)&h->pf_x, (void **)&h->pf_q, (void **)&h->pf_att, (void **)&h->pf_hb, (void **)&h->pf_xsT, (void **)&h->pf_hsT,
                    (void **)&h->pf_xq, (void **)&h->pf_hq, (void **)&h->pf_tokens};
     for (void **p : ps) {
@@ -919,6 +928,19 @@ static int prefill_run(q3_handle *h, const int *tokens_host, int T, int pos0) {
     const int gs = c.group_size, dim = c.dim, AH = h->AH_l, KV = h->KV_l, H = h->H_l;
     int rc;
     if ((rc = prefill_reserve(h, T))) return rc;
+    if (h->pf_attn_kind == 0 && (size_t)pos0 + T > h->pf_kvh_rows) { // hi / lo copy of one layer's K / V rows (grow-only)
+        if (h->pf_kvh) cudaFree(h->pf_kvh);
+        h->pf_kvh = nullptr;
+        h->pf_kvh_rows = 0;
+        const size_t rows = ((size_t)pos0 + T + 127) / 128 * 128;
+        cudaError_t e = cudaMalloc((void **)&h->pf_kvh, 4 * rows * KV * sizeof(__half));
+        if (e != cudaSuccess) {
+            h->pf_kvh = nullptr;
+            cudaGetLastError();
+            return fail(Q3_ECUDA, "prefill K/V split buffer for %zu rows: %s", rows, cudaGetErrorString(e));
+        }
+        h->pf_kvh_rows = rows;
+    }
     const int Tpad = (T + 127) / 128 * 128;
     cudaStream_t s = h->stream;
     CK(cudaMemcpyAsync(h->pf_tokens, tokens_host, (size_t)T * 4, cudaMemcpyHostToDevice, s));
@@ -939,7 +961,18 @@ static int prefill_run(q3_handle *h, const int *tokens_host, int T, int pos0) {
         if ((rc = launch_gemm_q8<PF_EPI_QKV>(gs, mx_dim, W.qkv.map, g, s))) return rc;
         dim3 rg((h->n_heads_l + h->n_kv_l + 3) / 4, T);
         k_pf_qknorm_rope<<<rg, 128, 0, s>>>(h->pf_q, kc_l, W.q_ln, W.k_ln, h->rope, pos0, h->n_heads_l, h->n_kv_l, AH, KV);
-        if (h->pf_attn_f32) { // f32 on the CUDA cores (kept for comparison: Q3_PF_ATTN_F32=1)
+        if (h->pf_attn_kind == 0) { // tensor cores, FP16 hi / lo split: K / V rows 0 .. pos0+T-1 of this layer split once, then streamed
+            const size_t rows = (size_t)pos0 + T, plane = h->pf_kvh_rows * KV;
+            k_pf_split_kv<<<h->num_sms * 4, 256, 0, s>>>(kc_l, vc_l, h->pf_kvh, rows * KV / 4, plane);
+            const int bq = PFH_R / h->kv_mul;
+            dim3 ag(h->n_kv_l, (T + bq - 1) / bq);
+            switch (h->kv_mul) {
+            case 1: k_pf_attention_h<1><<<ag, 128, PFH_SMEM, s>>>(h->pf_q, h->pf_kvh, plane, h->pf_att, T, pos0, AH, KV); break;
+            case 2: k_pf_attention_h<2><<<ag, 128, PFH_SMEM, s>>>(h->pf_q, h->pf_kvh, plane, h->pf_att, T, pos0, AH, KV); break;
+            case 4: k_pf_attention_h<4><<<ag, 128, PFH_SMEM, s>>>(h->pf_q, h->pf_kvh, plane, h->pf_att, T, pos0, AH, KV); break;
+            case 8: k_pf_attention_h<8><<<ag, 128, PFH_SMEM, s>>>(h->pf_q, h->pf_kvh, plane, h->pf_att, T, pos0, AH, KV); break;
+            }
+        } else if (h->pf_attn_kind == 1) { // f32 on the CUDA cores (kept for comparison: Q3_PF_ATTN_F32=1)
             const int bq = PFA_R / h->kv_mul;
             dim3 ag(h->n_kv_l, (T + bq - 1) / bq);
             switch (h->kv_mul) {
@@ -948,7 +981,7 @@ static int prefill_run(q3_handle *h, const int *tokens_host, int T, int pos0) {
             case 4: k_pf_attention<4><<<ag, 256, PFA_SMEM, s>>>(h->pf_q, kc_l, vc_l, h->pf_att, T, pos0, AH, KV); break;
             case 8: k_pf_attention<8><<<ag, 256, PFA_SMEM, s>>>(h->pf_q, kc_l, vc_l, h->pf_att, T, pos0, AH, KV); break;
             }
-        } else { // tensor cores (3xTF32)
+        } else { // tensor cores, 3xTF32 (the first tensor-core version, kept for comparison: Q3_PF_ATTN_TF32=1)
             const int bq = PFT_R / h->kv_mul;
             dim3 ag(h->n_kv_l, (T + bq - 1) / bq);
             switch (h->kv_mul) {
@@ -1809,20 +1842,25 @@ extern "C" int q3_op_prefill_attention(int device, const float *q, const float *
     const int kv_mul = n_heads / n_kv;
     if (kv_mul != 1 && kv_mul != 2 && kv_mul != 4 && kv_mul != 8) return fail(Q3_EUNSUPPORTED, "GQA factor %d unsupported", kv_mul);
     const int AH = n_heads * HEAD_DIM, KV = n_kv * HEAD_DIM, nk = pos0 + T;
-    DevBuf dq, dk, dv, dout;
+    DevBuf dq, dk, dv, dout, dkvh;
     int rc;
     if ((rc = dq.alloc((size_t)T * AH * 4)) || (rc = dk.alloc((size_t)nk * KV * 4)) || (rc = dv.alloc((size_t)nk * KV * 4)) ||
-        (rc = dout.alloc((size_t)T * AH * 4)))
+        (rc = dout.alloc((size_t)T * AH * 4)) || (rc = dkvh.alloc((size_t)4 * nk * KV * 2)))
         return rc;
     CK(cudaMemcpy(dq.p, q, (size_t)T * AH * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dk.p, k, (size_t)nk * KV * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dv.p, v, (size_t)nk * KV * 4, cudaMemcpyHostToDevice));
 #define PFA_CASE(KM)                                                                                                                        \
     case KM:                                                                                                                                \
-        if (f32_cuda_cores) {                                                                                                               \
+        if (f32_cuda_cores == 1) {                                                                                                          \
             CK(cudaFuncSetAttribute(k_pf_attention<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFA_SMEM));                            \
             k_pf_attention<KM><<<dim3(n_kv, (T + PFA_R / KM - 1) / (PFA_R / KM)), 256, PFA_SMEM>>>(dq.as<float>(), dk.as<float>(), dv.as<float>(), \
                                                                                                  dout.as<float>(), T, pos0, AH, KV);         \
+        } else if (f32_cuda_cores == 0) {                                                                                                   \
+            CK(cudaFuncSetAttribute(k_pf_attention_h<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFH_SMEM));                          \
+            k_pf_split_kv<<<296, 256>>>(dk.as<float>(), dv.as<float>(), dkvh.as<__half>(), (size_t)nk * KV / 4, (size_t)nk * KV);            \
+            k_pf_attention_h<KM><<<dim3(n_kv, (T + PFH_R / KM - 1) / (PFH_R / KM)), 128, PFH_SMEM>>>(dq.as<float>(), dkvh.as<__half>(),      \
+                                                                                                   (size_t)nk * KV, dout.as<float>(), T, pos0, AH, KV); \
         } else {                                                                                                                            \
             CK(cudaFuncSetAttribute(k_pf_attention_tc<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFT_SMEM));                         \
             k_pf_attention_tc<KM><<<dim3(n_kv, (T + PFT_R / KM - 1) / (PFT_R / KM)), 128, PFT_SMEM>>>(dq.as<float>(), dk.as<float>(), dv.as<float>(), \

@@ -18,6 +18,7 @@
 // tensor pipe at all (measured: time = pipeline-only time + arithmetic time; profiles/r02_gemm_q8_ceilings.txt).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -883,6 +884,231 @@ __global__ void __launch_bounds__(128, 2) k_pf_attention_tc(const float *__restr
     const int tq0 = q0 + r0 / KVMUL, tq1 = q0 + r1 / KVMUL;
     float *d0 = out + (size_t)tq0 * AH + (size_t)(kvh * KVMUL + r0 % KVMUL) * HEAD_DIM + 2 * t;
     float *d1 = out + (size_t)tq1 * AH + (size_t)(kvh * KVMUL + r1 % KVMUL) * HEAD_DIM + 2 * t;
+#pragma unroll
+    for (int n = 0; n < 16; n++) {
+        if (tq0 < T) *reinterpret_cast<float2 *>(d0 + 8 * n) = make_float2(__fmul_rn(o[n][0], i0), __fmul_rn(o[n][1], i0));
+        if (tq1 < T) *reinterpret_cast<float2 *>(d1 + 8 * n) = make_float2(__fmul_rn(o[n][2], i1), __fmul_rn(o[n][3], i1));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Causal attention on the tensor cores, second version: mma.sync m16n8k16 on an FP16 hi / lo split with f32 accumulation.
+//   x = hi + lo, hi = fp16(x), lo = fp16(x - hi);  a*b ~ hi*hi + hi*lo + lo*hi   (relative error ~2^-21, as the 3xTF32 form)
+// Against the TF32 kernel above: a k16 MMA covers twice the depth of a k8 one (half the MMA count), the operands are half as
+// wide in shared memory, fragments come in with ldmatrix (4 8x8 tiles per instruction instead of 32-bit loads), and K / V are
+// split ONCE per layer by k_pf_split_kv instead of by every CTA that streams them -- the tiles then arrive with cp.async,
+// double-buffered, no ALU work on the way.
+//   FP16 range: hi overflows beyond 65504 (K is QK-normalised, P <= 1; V / Q of that size do not occur), and a lo part below
+//   6.1e-5 is subnormal -- an absolute error of <= 3e-8 per element, far below the f32 round-off of the sums it enters.
+// One CTA = one kv head x 64 query rows (64 / KVMUL tokens x the KVMUL heads that share the K / V stream), 4 warps x 16 rows,
+// key tiles of 32 positions.  Shared memory rows are 128 halfs = 256 B = 16 chunks of 16 B; chunk c of row r sits at chunk
+// c ^ (r & 7), which makes every ldmatrix phase (8 rows, same logical chunk) conflict-free.
+//   S = Q K^T : A = Q (ldmatrix), B = K rows as stored (ldmatrix, non-transposed: a K row IS a column of K^T)
+//   O += P V  : A = P straight from the S accumulators (two adjacent 8-key tiles form one k16 fragment), B = V (ldmatrix.trans)
+// ------------------------------------------------------------------------------------------
+constexpr int PFH_R = 64, PFH_BK = 32;
+constexpr int PFH_SMEM = 2 * PFH_R * HEAD_DIM * 2 + 2 * 4 * PFH_BK * HEAD_DIM * 2; // Q hi/lo + 2 stages x (K hi, K lo, V hi, V lo) = 96 KB
+
+// rows [0, rows) of one layer's K and V cache (f32 [rows][KV]) -> hi / lo halves, four arrays [rows][KV]: Kh | Kl | Vh | Vl
+__global__ void __launch_bounds__(256) k_pf_split_kv(const float *__restrict__ kc, const float *__restrict__ vc, __half *out, size_t n4, size_t plane) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n4; i += (size_t)gridDim.x * blockDim.x) {
+        const bool isv = i >= n4;
+        const size_t j = isv ? i - n4 : i;
+        const float4 x = reinterpret_cast<const float4 *>(isv ? vc : kc)[j];
+        const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(__fsub_rn(x.x, f0.x), __fsub_rn(x.y, f0.y)), l1 = __floats2half2_rn(__fsub_rn(x.z, f1.x), __fsub_rn(x.w, f1.y));
+        __half *dst = out + (isv ? 2 * plane : 0) + 4 * j;
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+        *reinterpret_cast<uint2 *>(dst + plane) = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+    }
+}
+
+__device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void pfh_split2(float x, float y, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(__fsub_rn(x, f.x), __fsub_rn(y, f.y));
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+// kvh: [4][rows_alloc][KV] halves from k_pf_split_kv (plane = rows_alloc * KV)
+template <int KVMUL>
+__global__ void __launch_bounds__(128, 2) k_pf_attention_h(const float *__restrict__ q, const __half *__restrict__ kvh, size_t plane, float *out, int T,
+                                                           int pos0, int AH, int KV) {
+    extern __shared__ __align__(1024) uint8_t pfh_smem[];
+    const uint32_t sQ = smem_u32(pfh_smem);                      // Qh [64][128] | Ql [64][128]
+    const uint32_t sKV = sQ + 2 * PFH_R * HEAD_DIM * 2;          // [2 stages][Kh | Kl | Vh | Vl][32][128]
+    constexpr uint32_t QL = PFH_R * HEAD_DIM * 2, ARR = PFH_BK * HEAD_DIM * 2, STAGE = 4 * ARR;
+    constexpr int BQ = PFH_R / KVMUL;
+    const int kvhd = blockIdx.x, q0 = blockIdx.y * BQ;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const float scale = __fdiv_rn(1.0f, sqrtf((float)HEAD_DIM));
+    int last_q = q0 + BQ - 1;
+    if (last_q > T - 1) last_q = T - 1;
+    const int nkeys = pos0 + last_q + 1; // causal horizon of the last query in the tile
+    const int ntiles = (nkeys + PFH_BK - 1) / PFH_BK;
+
+    // stage loader: 4 arrays x 32 rows x 16 chunks = 2048 16-byte copies, 16 per thread; rows past the horizon are zero-filled
+    auto load_stage = [&](int tile, int st) {
+        const int k0 = tile * PFH_BK;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int idx = tid + i * 128, arr = idx >> 9, p = (idx >> 4) & 31, c = idx & 15;
+            const int key = k0 + p;
+            const bool ok = key < nkeys;
+            const __half *src = kvh + (size_t)arr * plane + (size_t)(ok ? key : 0) * KV + (size_t)kvhd * HEAD_DIM + c * 8;
+            const uint32_t dst = sKV + st * STAGE + arr * ARR + p * 256 + ((c ^ (p & 7)) << 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    load_stage(0, 0);
+    // Q tile: row r <-> (token q0 + r / KVMUL, head kvhd*KVMUL + r % KVMUL), split once
+    for (int i = tid; i < PFH_R * 16; i += 128) {
+        const int r = i >> 4, c = i & 15;
+        const int tq = q0 + r / KVMUL;
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (tq < T) {
+            const float4 *src = reinterpret_cast<const float4 *>(q + (size_t)tq * AH + (size_t)(kvhd * KVMUL + r % KVMUL) * HEAD_DIM + c * 8);
+            v0 = src[0];
+            v1 = src[1];
+        }
+        uint32_t h[4], l[4];
+        pfh_split2(v0.x, v0.y, h[0], l[0]);
+        pfh_split2(v0.z, v0.w, h[1], l[1]);
+        pfh_split2(v1.x, v1.y, h[2], l[2]);
+        pfh_split2(v1.z, v1.w, h[3], l[3]);
+        const uint32_t off = r * 256 + ((c ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sQ + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sQ + QL + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+    }
+    const int r0 = warp * 16 + g, r1 = r0 + 8;                                   // this thread's two rows of the tile
+    const int qp0 = pos0 + q0 + r0 / KVMUL, qp1 = pos0 + q0 + r1 / KVMUL;          // their absolute positions
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+    float o[16][4];
+#pragma unroll
+    for (int j = 0; j < 16; j++) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.0f;
+    // ldmatrix lane roles
+    const int a_row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, a_cg = (lane >> 4) & 1;      // A (Q): row, which 8-column half of the k16 step
+    const int b_key = (lane & 7) + ((lane >> 4) & 1) * 8, b_cg = (lane >> 3) & 1;                  // B (K): key within a 16-key group, 8-dim half
+    const int v_key = (lane & 7) + ((lane >> 3) & 1) * 8, v_cg = (lane >> 4) & 1;                  // B (V, transposed): key within the k16 step, 8-dim half
+
+    for (int tile = 0; tile < ntiles; tile++) {
+        const int st = tile & 1, k0 = tile * PFH_BK;
+        if (tile + 1 < ntiles) {
+            load_stage(tile + 1, st ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads(); // tile `tile` (and, first time round, the Q tile) visible to every warp
+        const uint32_t sKh = sKV + st * STAGE, sKl = sKh + ARR, sVh = sKh + 2 * ARR, sVl = sKh + 3 * ARR;
+        // ---- S = Q K^T (16 rows x 32 keys per warp) ----
+        float s[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+            uint32_t ah[4], al[4];
+            const uint32_t aoff = a_row * 256 + (((2 * ks + a_cg) ^ (a_row & 7)) << 4);
+            ldsm4(ah, sQ + aoff);
+            ldsm4(al, sQ + QL + aoff);
+#pragma unroll
+            for (int jj = 0; jj < 2; jj++) { // 16 keys per ldmatrix.x4: n-tiles 2jj, 2jj+1
+                const int key = 16 * jj + b_key;
+                const uint32_t boff = key * 256 + (((2 * ks + b_cg) ^ (key & 7)) << 4);
+                uint32_t bh[4], bl[4];
+                ldsm4(bh, sKh + boff);
+                ldsm4(bl, sKl + boff);
+                mma_f16(s[2 * jj], al[0], al[1], al[2], al[3], bh[0], bh[1]);
+                mma_f16(s[2 * jj], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+                mma_f16(s[2 * jj], ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+                mma_f16(s[2 * jj + 1], al[0], al[1], al[2], al[3], bh[2], bh[3]);
+                mma_f16(s[2 * jj + 1], ah[0], ah[1], ah[2], ah[3], bl[2], bl[3]);
+                mma_f16(s[2 * jj + 1], ah[0], ah[1], ah[2], ah[3], bh[2], bh[3]);
+            }
+        }
+        // ---- online softmax: thread holds keys k0 + 8j + {2t, 2t+1} of rows r0 (s[j][0..1]) and r1 (s[j][2..3]) ----
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int key = k0 + 8 * j + 2 * t;
+            s[j][0] = (key <= qp0) ? __fmul_rn(s[j][0], scale) : -INFINITY;
+            s[j][1] = (key + 1 <= qp0) ? __fmul_rn(s[j][1], scale) : -INFINITY;
+            s[j][2] = (key <= qp1) ? __fmul_rn(s[j][2], scale) : -INFINITY;
+            s[j][3] = (key + 1 <= qp1) ? __fmul_rn(s[j][3], scale) : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float c0 = (mn0 == -INFINITY) ? 1.0f : expf(m0 - mn0), c1 = (mn1 == -INFINITY) ? 1.0f : expf(m1 - mn1);
+        m0 = mn0;
+        m1 = mn1;
+        l0 *= c0;
+        l1 *= c1;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            o[j][0] *= c0;
+            o[j][1] *= c0;
+            o[j][2] *= c1;
+            o[j][3] *= c1;
+        }
+        // ---- O += P V: k16 step kk = keys 16kk .. 16kk+15 = S tiles 2kk, 2kk+1 ----
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++) {
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; h2++) {
+                const float *sj = s[2 * kk + h2];
+                const float p00 = (sj[0] == -INFINITY) ? 0.0f : expf(sj[0] - mn0), p01 = (sj[1] == -INFINITY) ? 0.0f : expf(sj[1] - mn0);
+                const float p10 = (sj[2] == -INFINITY) ? 0.0f : expf(sj[2] - mn1), p11 = (sj[3] == -INFINITY) ? 0.0f : expf(sj[3] - mn1);
+                l0 += p00 + p01;
+                l1 += p10 + p11;
+                pfh_split2(p00, p01, ph[2 * h2], pl[2 * h2]);         // a0a1 / a4a5: row g
+                pfh_split2(p10, p11, ph[2 * h2 + 1], pl[2 * h2 + 1]); // a2a3 / a6a7: row g+8
+            }
+            const int key = 16 * kk + v_key;
+#pragma unroll
+            for (int nn = 0; nn < 8; nn++) { // 16 dims per ldmatrix.x4.trans: n-tiles 2nn, 2nn+1
+                const uint32_t voff = key * 256 + (((2 * nn + v_cg) ^ (key & 7)) << 4);
+                uint32_t vh[4], vl[4];
+                ldsm4t(vh, sVh + voff);
+                ldsm4t(vl, sVl + voff);
+                mma_f16(o[2 * nn], pl[0], pl[1], pl[2], pl[3], vh[0], vh[1]);
+                mma_f16(o[2 * nn], ph[0], ph[1], ph[2], ph[3], vl[0], vl[1]);
+                mma_f16(o[2 * nn], ph[0], ph[1], ph[2], ph[3], vh[0], vh[1]);
+                mma_f16(o[2 * nn + 1], pl[0], pl[1], pl[2], pl[3], vh[2], vh[3]);
+                mma_f16(o[2 * nn + 1], ph[0], ph[1], ph[2], ph[3], vl[2], vl[3]);
+                mma_f16(o[2 * nn + 1], ph[0], ph[1], ph[2], ph[3], vh[2], vh[3]);
+            }
+        }
+        __syncthreads(); // everybody is done with stage `st` before the next iteration's loads overwrite it
+    }
+    // row sums live spread over the quad
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = __fdiv_rn(1.0f, l0), i1 = __fdiv_rn(1.0f, l1);
+    const int tq0 = q0 + r0 / KVMUL, tq1 = q0 + r1 / KVMUL;
+    float *d0 = out + (size_t)tq0 * AH + (size_t)(kvhd * KVMUL + r0 % KVMUL) * HEAD_DIM + 2 * t;
+    float *d1 = out + (size_t)tq1 * AH + (size_t)(kvhd * KVMUL + r1 % KVMUL) * HEAD_DIM + 2 * t;
 #pragma unroll
     for (int n = 0; n < 16; n++) {
         if (tq0 < T) *reinterpret_cast<float2 *>(d0 + 8 * n) = make_float2(__fmul_rn(o[n][0], i0), __fmul_rn(o[n][1], i0));

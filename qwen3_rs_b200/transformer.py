@@ -402,8 +402,9 @@ def op_sample(logits, temperature: float, topp: float, rng_state: int, device: i
     return tok.value, st.value
 
 
-def op_prefill_attention(q, k, v, pos0: int, n_heads: int, n_kv: int, f32_cuda_cores: bool = False, device: int = 0):
-    """Causal attention of T = q.shape[0] query tokens at positions pos0.. over k / v rows [pos0 + T][n_kv * 128]."""
+def op_prefill_attention(q, k, v, pos0: int, n_heads: int, n_kv: int, f32_cuda_cores=0, device: int = 0):
+    """Causal attention of T = q.shape[0] query tokens at positions pos0.. over k / v rows [pos0 + T][n_kv * 128].
+    f32_cuda_cores: 0 = the tensor-core kernel q3_prefill runs (FP16 hi / lo split), 1 / True = f32 on the CUDA cores, 2 = 3xTF32."""
     q = np.ascontiguousarray(q, np.float32)
     k = np.ascontiguousarray(k, np.float32)
     v = np.ascontiguousarray(v, np.float32)

@@ -1,11 +1,11 @@
-"""Layer-0 K/V rows of q3_prefill against the oracle (small gs128 seed 2, T=130): how many rows are off, by how much (Q3_LIB picks the library)."""
+"""Layer-0 K/V rows of q3_prefill against the oracle (default: small gs128 seed 2, T=130; or: name gs seed T): how many rows are off, by how much (Q3_LIB picks the library)."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import binding as orc
 from qwen3_rs_b200 import synth, transformer as T
-name, gs, seed, Tn = "small", 128, 2, 130
+name, gs, seed, Tn = (sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else ("small", 128, 2, 130)
 path = f"/tmp/diag_{name}_{gs}_{seed}.bin"
 if not os.path.exists(path):
     synth.export_synthetic(synth.SHAPES[name], path, gs, seed=seed)

@@ -650,9 +650,11 @@ def test_prefill_matches_oracle(models, ckpt, name, gs, seed, T):
             # whose RMSNorm sum lands an ulp off the oracle's and flips an int8 activation (a row then moves by ~1e-3 .. 1e-2).
             # Layer 0 of the SYNTHETIC checkpoints is the worst case for that: the input is int8 x scale (the embedding row) times a
             # bf16-rounded norm weight, so x / scale lands on exact .5 ties far more often than real activations do -- up to 18 % of
-            # the rows here (24 / 130 on small gs128; the sequential decode path flips the very same rows: scripts/diag/prefill_rows.py).
+            # the rows here (24 / 130 on small gs128, 60 / 200 on small gs64; the sequential decode path flips the very same rows:
+            # scripts/diag/prefill_rows.py).  On the CPU alone (scripts/diag/layer0_ties.py, tests/test_oracle.py): 57 % of these
+            # rows hold an element within 1e-6 of a tie, and moving the normalisation factor by ONE ulp changes 23 % of them.
             rows_off = float(np.mean(ek.max(axis=1) > 1e-4))
-            assert np.median(ek) <= 1e-6 and np.median(ev) <= 1e-6 and rows_off <= 0.25 and ek.max() <= 2e-2, (rows_off, float(ek.max()))
+            assert np.median(ek) <= 1e-6 and np.median(ev) <= 1e-6 and rows_off <= 0.4 and ek.max() <= 2e-2, (rows_off, float(ek.max()))
         # deeper layers: an upstream flip perturbs every later element a little (and, through attention, later tokens), so only the
         # noise level is checked here -- the attention kernel itself is compared with float64 in test_prefill_attention_kernels_...
         assert np.median(ev) <= 1e-2 * max(1.0, float(np.abs(vr).max())), (l, float(np.median(ev)))
@@ -666,9 +668,9 @@ def test_prefill_matches_oracle(models, ckpt, name, gs, seed, T):
 
 @pytest.mark.parametrize("T,pos0,n_heads,n_kv", [(70, 0, 8, 2), (33, 45, 4, 4), (129, 3, 16, 2), (200, 0, 2, 1)])
 def test_prefill_attention_kernels_against_float64(T, pos0, n_heads, n_kv):
-    """The batched causal attention alone (tensor-core 3xTF32 kernel and the f32 CUDA-core kernel) against a float64
-    softmax attention: f32-class accuracy (1e-5 of the value scale), i.e. the TF32 split loses nothing that matters
-    to the int8 re-quantisation behind it."""
+    """The batched causal attention alone (the tensor-core kernel q3_prefill runs -- FP16 hi / lo split --, the f32 CUDA-core
+    kernel and the first tensor-core version, 3xTF32) against a float64 softmax attention: f32-class accuracy (1e-5 of the
+    value scale), i.e. the operand split loses nothing that matters to the int8 re-quantisation behind it."""
     rng = np.random.default_rng(T + pos0)
     hd, nk = 128, pos0 + T
     q = rng.standard_normal((T, n_heads * hd)).astype(np.float32)
@@ -684,8 +686,8 @@ def test_prefill_attention_kernels_against_float64(T, pos0, n_heads, n_kv):
         s[mask] = -np.inf
         p = np.exp(s - s.max(axis=1, keepdims=True))
         ref[:, h * hd:(h + 1) * hd] = (p / p.sum(axis=1, keepdims=True)) @ vh
-    for f32 in (False, True):
-        out = T_mod.op_prefill_attention(q, k, v, pos0, n_heads, n_kv, f32_cuda_cores=f32)
+    for kind, label in ((0, "fp16 hi/lo"), (1, "f32"), (2, "3xTF32")):
+        out = T_mod.op_prefill_attention(q, k, v, pos0, n_heads, n_kv, f32_cuda_cores=kind)
         err = float(np.abs(out - ref).max())
-        print(f"prefill attention T={T} pos0={pos0} heads {n_heads}/{n_kv} {'f32' if f32 else '3xTF32'}: max err {err:.2e}")
+        print(f"prefill attention T={T} pos0={pos0} heads {n_heads}/{n_kv} {label}: max err {err:.2e}")
         assert err <= 2e-5 * max(1.0, float(np.abs(ref).max()))
