@@ -925,7 +925,7 @@ __global__ void __launch_bounds__(256) k_pf_split_kv(const float *__restrict__ k
 }
 
 __device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
@@ -952,7 +952,8 @@ __global__ void __launch_bounds__(128, 2) k_pf_attention_h(const float *__restri
     const uint32_t sKV = sQ + 2 * PFH_R * HEAD_DIM * 2;          // [2 stages][Kh | Kl | Vh | Vl][32][128]
     constexpr uint32_t QL = PFH_R * HEAD_DIM * 2, ARR = PFH_BK * HEAD_DIM * 2, STAGE = 4 * ARR;
     constexpr int BQ = PFH_R / KVMUL;
-    const int kvhd = blockIdx.x, q0 = blockIdx.y * BQ;
+    // the query tiles with the longest causal horizon are launched first (a late tile does up to T / 64 times the work of the first)
+    const int kvhd = blockIdx.x, q0 = ((int)gridDim.y - 1 - (int)blockIdx.y) * BQ;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const float scale = __fdiv_rn(1.0f, sqrtf((float)HEAD_DIM));
     int last_q = q0 + BQ - 1;
@@ -1025,20 +1026,21 @@ __global__ void __launch_bounds__(128, 2) k_pf_attention_h(const float *__restri
             const uint32_t aoff = a_row * 256 + (((2 * ks + a_cg) ^ (a_row & 7)) << 4);
             ldsm4(ah, sQ + aoff);
             ldsm4(al, sQ + QL + aoff);
+            // the three product terms go round the four key tiles: consecutive MMAs never touch the same accumulator
+            uint32_t bh[2][4], bl[2][4];
 #pragma unroll
             for (int jj = 0; jj < 2; jj++) { // 16 keys per ldmatrix.x4: n-tiles 2jj, 2jj+1
                 const int key = 16 * jj + b_key;
                 const uint32_t boff = key * 256 + (((2 * ks + b_cg) ^ (key & 7)) << 4);
-                uint32_t bh[4], bl[4];
-                ldsm4(bh, sKh + boff);
-                ldsm4(bl, sKl + boff);
-                mma_f16(s[2 * jj], al[0], al[1], al[2], al[3], bh[0], bh[1]);
-                mma_f16(s[2 * jj], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
-                mma_f16(s[2 * jj], ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
-                mma_f16(s[2 * jj + 1], al[0], al[1], al[2], al[3], bh[2], bh[3]);
-                mma_f16(s[2 * jj + 1], ah[0], ah[1], ah[2], ah[3], bl[2], bl[3]);
-                mma_f16(s[2 * jj + 1], ah[0], ah[1], ah[2], ah[3], bh[2], bh[3]);
+                ldsm4(bh[jj], sKh + boff);
+                ldsm4(bl[jj], sKl + boff);
             }
+#pragma unroll
+            for (int j = 0; j < 4; j++) mma_f16(s[j], al[0], al[1], al[2], al[3], bh[j >> 1][2 * (j & 1)], bh[j >> 1][2 * (j & 1) + 1]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) mma_f16(s[j], ah[0], ah[1], ah[2], ah[3], bl[j >> 1][2 * (j & 1)], bl[j >> 1][2 * (j & 1) + 1]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) mma_f16(s[j], ah[0], ah[1], ah[2], ah[3], bh[j >> 1][2 * (j & 1)], bh[j >> 1][2 * (j & 1) + 1]);
         }
         // ---- online softmax: thread holds keys k0 + 8j + {2t, 2t+1} of rows r0 (s[j][0..1]) and r1 (s[j][2..3]) ----
         float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -1085,17 +1087,21 @@ __global__ void __launch_bounds__(128, 2) k_pf_attention_h(const float *__restri
             }
             const int key = 16 * kk + v_key;
 #pragma unroll
-            for (int nn = 0; nn < 8; nn++) { // 16 dims per ldmatrix.x4.trans: n-tiles 2nn, 2nn+1
-                const uint32_t voff = key * 256 + (((2 * nn + v_cg) ^ (key & 7)) << 4);
-                uint32_t vh[4], vl[4];
-                ldsm4t(vh, sVh + voff);
-                ldsm4t(vl, sVl + voff);
-                mma_f16(o[2 * nn], pl[0], pl[1], pl[2], pl[3], vh[0], vh[1]);
-                mma_f16(o[2 * nn], ph[0], ph[1], ph[2], ph[3], vl[0], vl[1]);
-                mma_f16(o[2 * nn], ph[0], ph[1], ph[2], ph[3], vh[0], vh[1]);
-                mma_f16(o[2 * nn + 1], pl[0], pl[1], pl[2], pl[3], vh[2], vh[3]);
-                mma_f16(o[2 * nn + 1], ph[0], ph[1], ph[2], ph[3], vl[2], vl[3]);
-                mma_f16(o[2 * nn + 1], ph[0], ph[1], ph[2], ph[3], vh[2], vh[3]);
+            for (int n4 = 0; n4 < 4; n4++) { // 32 dims = four output tiles per round, the three product terms go round them
+                uint32_t vh[2][4], vl[2][4];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; h2++) { // 16 dims per ldmatrix.x4.trans: n-tiles 2nn, 2nn+1
+                    const int nn = 2 * n4 + h2;
+                    const uint32_t voff = key * 256 + (((2 * nn + v_cg) ^ (key & 7)) << 4);
+                    ldsm4t(vh[h2], sVh + voff);
+                    ldsm4t(vl[h2], sVl + voff);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) mma_f16(o[4 * n4 + j], pl[0], pl[1], pl[2], pl[3], vh[j >> 1][2 * (j & 1)], vh[j >> 1][2 * (j & 1) + 1]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) mma_f16(o[4 * n4 + j], ph[0], ph[1], ph[2], ph[3], vl[j >> 1][2 * (j & 1)], vl[j >> 1][2 * (j & 1) + 1]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) mma_f16(o[4 * n4 + j], ph[0], ph[1], ph[2], ph[3], vh[j >> 1][2 * (j & 1)], vh[j >> 1][2 * (j & 1) + 1]);
             }
         }
         __syncthreads(); // everybody is done with stage `st` before the next iteration's loads overwrite it
