@@ -115,6 +115,11 @@ struct q3_handle {
     // [part o_proj | part down | argmax candidates | barrier flags | logits]
     uint8_t *xchg = nullptr;
     size_t xchg_bytes = 0, off_part[2] = {0, 0}, off_best = 0, off_flags = 0, off_logits = 0;
+    // batched prefill under TP: two partial blocks [pf_tp_cap][dim] f32 + an arrival counter inside the exchange buffer
+    size_t off_pf_part[2] = {0, 0}, off_pf_ctr = 0;
+    int pf_tp_cap = 0;                     // tokens per prefill chunk under TP (longer prompts go through in chunks)
+    PfPeers pf_peers[2]{};                 // peer views of the two partial blocks (+ counters), filled by q3_tp_connect
+    unsigned long long pf_xbar_count = 0;  // cross-GPU prefill barriers passed so far (same sequence on every rank)
     bool tp_connected = false;
     std::vector<void *> peer_maps;
     size_t mega_smem = 0;
@@ -697,7 +702,7 @@ static int mega_check(q3_handle *h, bool queued = false) {
             if (h->att_cnt) cudaMemset(h->att_cnt, 0, (size_t)h->cfg.n_layers * h->n_kv_l * 4);
         }
         return fail(Q3_ECUDA, "persistent decode kernel: a wait timed out (status %d: 1 grid barrier, 2 stage ring, 3 cross-GPU barrier, 4 producer order, "
-                              "6-10 flagged exchange: 6 o/down rows, 7 attention output, 8 SwiGLU outputs, 9 qkv rows, 10 TP partials)%s", code,
+                              "6-10 flagged exchange: 6 o/down rows, 7 attention output, 8 SwiGLU outputs, 9 qkv rows, 10 TP partials; 11 prefill cross-GPU barrier)%s", code,
                     h->tp_size > 1 ? "; tensor-parallel handle poisoned" : "");
     }
     return 0;
@@ -845,7 +850,6 @@ static int prefill_prepare_tensor(q3_handle *h, DevQT &t) {
 static int prefill_init(q3_handle *h) {
     const q3_config &c = h->cfg;
     h->pf_ok = false;
-    if (h->tp_size != 1) { h->pf_why = "batched prefill is single-GPU for now"; return 0; }
     if (c.dim % 128 || h->AH_l % 128 || h->H_l % 128 || h->layers[0].qkv.rows % 128 || (2 * h->H_l) % 128) {
         h->pf_why = "matrix dimensions must be multiples of 128";
         return 0;
@@ -922,6 +926,32 @@ static int prefill_reserve(q3_handle *h, int T) {
     return 0;
 }
 
+// Row-parallel GEMM under tensor parallelism (o_proj: which = 0, down_proj: which = 1): partial block -> exchange buffer, cross-GPU
+// barrier, rank-ordered sum of the tp partials over NVLink folded into the residual stream (q3_prefill.cuh).  All ranks issue the
+// same sequence, so the barrier count is the same everywhere.
+static int prefill_tp_rowparallel(q3_handle *h, int which, const CUtensorMap &mx, const CUtensorMap &mw, PrefillGemmArgs g, int T) {
+    int rc;
+    g.out = const_cast<float *>(h->pf_peers[which].part[h->tp_rank]);
+    if ((rc = launch_gemm_q8<PF_EPI_STORE>(h->cfg.group_size, mx, mw, g, h->stream))) return rc;
+    h->pf_xbar_count++;
+    k_pf_xbarrier<<<1, 32, 0, h->stream>>>(h->pf_peers[which], h->tp_size, h->tp_rank, h->pf_xbar_count * (unsigned long long)h->tp_size, h->d_status);
+    const size_t n4 = (size_t)T * h->cfg.dim / 4;
+    k_pf_allreduce_resid<<<h->num_sms * 4, 256, 0, h->stream>>>(h->pf_x, h->pf_peers[which], h->tp_size, n4);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int prefill_run(q3_handle *h, const int *tokens_host, int T, int pos0);
+// prompts longer than the tensor-parallel partial blocks go through in chunks (causal attention reads the earlier chunks' cache rows)
+static int prefill_chunks(q3_handle *h, const int *tokens_host, int n, int pos0) {
+    const int cap = h->tp_size > 1 ? h->pf_tp_cap : n;
+    for (int off = 0; off < n; off += cap) {
+        int rc = prefill_run(h, tokens_host + off, n - off < cap ? n - off : cap, pos0 + off);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 // the whole batched forward for tokens at positions pos0..pos0+T-1; leaves x of the last token in h->x
 static int prefill_run(q3_handle *h, const int *tokens_host, int T, int pos0) {
     const q3_config &c = h->cfg;
@@ -994,7 +1024,9 @@ static int prefill_run(q3_handle *h, const int *tokens_host, int T, int pos0) {
         GS_DISPATCH(gs, (k_pf_quantize<GS><<<T, 256, 0, s>>>(h->pf_att, h->pf_xq, h->pf_xsT, AH, Tpad)));
         PrefillGemmArgs o{};
         o.T = T; o.Tpad = Tpad; o.K = AH; o.N = dim; o.wsT = W.wo.sT; o.xsT = h->pf_xsT; o.out = h->pf_x; o.ld_out = dim;
-        if ((rc = launch_gemm_q8<PF_EPI_RESID>(gs, mx_ah, W.wo.map, o, s))) return rc;
+        if (h->tp_size == 1) {
+            if ((rc = launch_gemm_q8<PF_EPI_RESID>(gs, mx_ah, W.wo.map, o, s))) return rc;
+        } else if ((rc = prefill_tp_rowparallel(h, 0, mx_ah, W.wo.map, o, T))) return rc;
         GS_DISPATCH(gs, (k_pf_norm_quant<GS><<<T, 256, 0, s>>>(h->pf_x, W.rms_ffn, h->pf_xq, h->pf_xsT, dim, Tpad, nullptr, nullptr,
                                                               nullptr, 0)));
         PrefillGemmArgs gu{};
@@ -1003,7 +1035,9 @@ static int prefill_run(q3_handle *h, const int *tokens_host, int T, int pos0) {
         GS_DISPATCH(gs, (k_pf_quantize<GS><<<T, 256, 0, s>>>(h->pf_hb, h->pf_hq, h->pf_hsT, H, Tpad)));
         PrefillGemmArgs dn{};
         dn.T = T; dn.Tpad = Tpad; dn.K = H; dn.N = dim; dn.wsT = W.w2.sT; dn.xsT = h->pf_hsT; dn.out = h->pf_x; dn.ld_out = dim;
-        if ((rc = launch_gemm_q8<PF_EPI_RESID>(gs, mx_h, W.w2.map, dn, s))) return rc;
+        if (h->tp_size == 1) {
+            if ((rc = launch_gemm_q8<PF_EPI_RESID>(gs, mx_h, W.w2.map, dn, s))) return rc;
+        } else if ((rc = prefill_tp_rowparallel(h, 1, mx_h, W.w2.map, dn, T))) return rc;
     }
     CK(cudaMemcpyAsync(h->x, h->pf_x + (size_t)(T - 1) * dim, (size_t)dim * 4, cudaMemcpyDeviceToDevice, s));
     CK(cudaGetLastError());
@@ -1126,6 +1160,11 @@ static int create_impl(const char *path, int ctx_len, int device, int tp_rank, i
         h->off_best = o; o = al(o + (size_t)tp_size * h->num_sms * 8);
         h->off_flags = o; o = al(o + 64 * 4);
         h->off_logits = o; o = al(o + (size_t)c.vocab_size * 4);
+        if (tp_size > 1) { // batched prefill: partial blocks of the row-parallel GEMMs (chunks of up to 2048 tokens)
+            h->pf_tp_cap = c.seq_len < 2048 ? (c.seq_len + 127) / 128 * 128 : 2048;
+            h->off_pf_ctr = o; o = al(o + 64);
+            for (int i = 0; i < 2; i++) { h->off_pf_part[i] = o; o = al(o + (size_t)h->pf_tp_cap * dim * 4); }
+        }
         h->xchg_bytes = o;
         TRY(dmalloc(h, (void **)&h->xchg, o));
         CKH(cudaMemset(h->xchg, 0, o));
@@ -1241,6 +1280,10 @@ extern "C" int q3_tp_connect(q3_handle *h, const void *blobs) {
         a.best[r] = (unsigned long long *)(base + h->off_best);
         a.xbar[r] = (unsigned long long *)(base + h->off_flags);
         a.logits[r] = (float *)(base + h->off_logits);
+        for (int i = 0; i < 2; i++) {
+            h->pf_peers[i].part[r] = (const float *)(base + h->off_pf_part[i]);
+            h->pf_peers[i].ctr[r] = (unsigned long long *)(base + h->off_pf_ctr);
+        }
     }
     h->tp_connected = true;
     return Q3_OK;
@@ -1594,7 +1637,8 @@ extern "C" int q3_prefill(q3_handle *h, const int *tokens, int n, int pos0, floa
         return Q3_OK;
     }
     int rc;
-    if ((rc = prefill_run(h, tokens, n, pos0))) return rc;
+    if (h->tp_size > 1 && !h->tp_connected) return fail(Q3_ECOMM, "tensor-parallel handle used before q3_tp_connect");
+    if ((rc = prefill_chunks(h, tokens, n, pos0))) return rc;
     // final norm + quantize + lm_head on the last token only (qwen3.rs:72-76)
     if ((rc = set_tok_pos(h, tokens[n - 1], pos0 + n - 1))) return rc;
     if (use_mega(h)) {
@@ -1619,13 +1663,14 @@ extern "C" int q3_bench_prefill(q3_handle *h, const int *tokens, int n, int pos0
     if (pos0 < 0 || pos0 + n > h->cfg.seq_len) return fail(Q3_EINVAL, "index out of bounds");
     CK(cudaSetDevice(h->device));
     int rc;
-    if ((rc = prefill_run(h, tokens, n, pos0))) return rc; // warm-up (also sizes the buffers)
+    if (h->tp_size > 1 && !h->tp_connected) return fail(Q3_ECOMM, "tensor-parallel handle used before q3_tp_connect");
+    if ((rc = prefill_chunks(h, tokens, n, pos0))) return rc; // warm-up (also sizes the buffers)
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaEventRecord(e0, h->stream));
-    if ((rc = prefill_run(h, tokens, n, pos0))) return rc;
+    if ((rc = prefill_chunks(h, tokens, n, pos0))) return rc;
     CK(cudaEventRecord(e1, h->stream));
     CK(cudaEventSynchronize(e1));
     CK(cudaGetLastError());
@@ -1634,7 +1679,7 @@ extern "C" int q3_bench_prefill(q3_handle *h, const int *tokens, int n, int pos0
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (ms_out) *ms_out = ms;
-    return Q3_OK;
+    return h->tp_size > 1 ? mega_check(h) : Q3_OK;
 }
 
 extern "C" int q3_reset(q3_handle *h) {

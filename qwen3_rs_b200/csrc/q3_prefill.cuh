@@ -1122,6 +1122,53 @@ __global__ void __launch_bounds__(128, 2) k_pf_attention_h(const float *__restri
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Batched prefill under tensor parallelism: the row-parallel GEMMs (o_proj, down_proj) leave a PARTIAL [T][dim] f32 block in
+// this rank's part of the exchange buffer; after a cross-GPU barrier every rank adds the tp partials in RANK ORDER (so all
+// ranks hold bit-identical residual streams, the same order as the decode path's exchange) over NVLink peer loads and folds
+// them into its residual stream: T * dim * 4 bytes per sub-block and peer -- the bandwidth-bound exchange of SURVEY 8(e).
+// Two partial buffers alternate (o_proj / down), so one barrier per exchange is enough: a buffer is rewritten only after
+// the NEXT exchange's barrier, which a rank reaches after it has finished reading.
+// ------------------------------------------------------------------------------------------
+struct PfPeers {
+    const float *part[MEGA_MAX_TP];        // every rank's partial block [Tcap][dim] (peer memory)
+    unsigned long long *ctr[MEGA_MAX_TP];  // every rank's arrival counter (peer memory)
+};
+// one thread: tell every rank (this one included) that this rank's partial block is complete, wait until all tp ranks have said so
+__global__ void k_pf_xbarrier(PfPeers p, int tp, int rank, unsigned long long target, int *status) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __threadfence_system(); // the GEMM that wrote the block ran before this kernel on the same stream
+    for (int r = 0; r < tp; r++) asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p.ctr[r]), "l"(1ULL) : "memory");
+    const long long t0 = clock64();
+    unsigned long long v;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p.ctr[rank]) : "memory");
+        if (v < target && clock64() - t0 > 6000000000LL) { // ~3 s: a peer is gone; never hang the GPU
+            atomicExch(status, 11);
+            return;
+        }
+    } while (v < target);
+}
+// x[t][c] += sum over ranks (in rank order) of part_r[t][c]      n4 = T * dim / 4
+__global__ void __launch_bounds__(256) k_pf_allreduce_resid(float *x, PfPeers p, int tp, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 s = __ldcg(reinterpret_cast<const float4 *>(p.part[0]) + i);
+        for (int r = 1; r < tp; r++) {
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(p.part[r]) + i);
+            s.x = __fadd_rn(s.x, v.x);
+            s.y = __fadd_rn(s.y, v.y);
+            s.z = __fadd_rn(s.z, v.z);
+            s.w = __fadd_rn(s.w, v.w);
+        }
+        float4 o = reinterpret_cast<float4 *>(x)[i];
+        o.x = __fadd_rn(o.x, s.x);
+        o.y = __fadd_rn(o.y, s.y);
+        o.z = __fadd_rn(o.z, s.z);
+        o.w = __fadd_rn(o.w, s.w);
+        reinterpret_cast<float4 *>(x)[i] = o;
+    }
+}
+
 // [rows][ng] -> [ng][rows] (weight scales, once at load)
 __global__ void k_transpose_f32(const float *__restrict__ in, float *out, int rows, int cols) {
     __shared__ float tile[32][33];

@@ -117,6 +117,26 @@ def _run(rank, world, path, steps, q, dist):
     out["sampled"] = m.decode_sample(9, 0, 8)
     ms = m.bench_decode(9, 1, 16)
     out["ms_per_tok"] = ms / 16
+    # batched prefill under TP: tcgen05 GEMMs on this rank's shards, the row-parallel partial blocks ([T][dim] f32 per sub-block)
+    # summed in rank order over NVLink peer loads (q3_prefill.cuh: k_pf_xbarrier / k_pf_allreduce_resid)
+    Tp = min(40, c["seq_len"] - 2)
+    ptoks = np.random.default_rng(5).integers(0, c["vocab_size"], Tp).tolist()
+    o.reset()
+    for p_, t_ in enumerate(ptoks):
+        plo = o.forward(t_, p_)
+    pko, pvo = o.kv_cache()
+    m.reset()
+    plg = m.prefill(ptoks, 0)
+    out["pf_logits"], out["pf_ologits"] = plg, (plo if rank == 0 else None)
+    kverr = 0.0
+    h0 = rank * (nkv // world)
+    for l in range(c["n_layers"]):
+        k, v = m.kv_read(l, 0, Tp)
+        kr = pko[l, :Tp, h0:h0 + nkv // world].reshape(Tp, kv_l)
+        vr = pvo[l, :Tp, h0:h0 + nkv // world].reshape(Tp, kv_l)
+        kverr = max(kverr, float(np.abs(k - kr).max()) / max(1.0, float(np.abs(kr).max())), float(np.abs(v - vr).max()) / max(1.0, float(np.abs(vr).max())))
+    out["pf_kv_err"] = kverr
+    out["pf_ms"] = m.bench_prefill(ptoks, 0)
     q.put((rank, out))
     dist.barrier()
     m.close()
@@ -157,6 +177,7 @@ def test_tensor_parallel_matches_oracle(ckpt, name, gs, seed, world):
         assert got[r]["rooted"] == got[0]["rooted"]
         assert got[r]["sampled"] == got[0]["sampled"]
         assert np.array_equal(got[r]["layer_errs"], got[0]["layer_errs"])
+        assert np.array_equal(got[r]["pf_logits"], got[0]["pf_logits"])
     g = got[0]
     ol = g["ologits"]
     # layer by layer against the oracle
@@ -181,6 +202,12 @@ def test_tensor_parallel_matches_oracle(ckpt, name, gs, seed, world):
             assert argmax_last(g["logits"][pos]) == argmax_last(ol[pos])
     assert g["argmax"][0] == argmax_last(g["logits"][0])
     assert g["rooted"][0] == g["argmax"][0]
+    # batched prefill under TP against the oracle's sequential forwards: last-token logits and this rank's K / V rows of every layer
+    pferr = float(np.abs(g["pf_logits"] - g["pf_ologits"]).max())
+    print(f"{name} gs{gs} tp{world}: prefill (40 tokens) max|dlogit| {pferr:.2e} (|logit| max {np.abs(g['pf_ologits']).max():.1f}), "
+          f"K/V rows worst {max(got[r]['pf_kv_err'] for r in range(world)):.2e} of their scale; {g['pf_ms'] * 1e3:.0f} us")
+    assert pferr <= 0.05 * float(np.abs(g["pf_ologits"]).max()) + 1e-2
+    assert all(got[r]["pf_kv_err"] <= 0.05 for r in range(world))
     # greedy tokens: identical to the oracle's up to the first step whose margin is inside the fast-mode noise
     worst = float(err.max())
     for i, (a, b) in enumerate(zip(g["greedy"], g["ogreedy"])):
