@@ -445,6 +445,22 @@ def main():
         if lo.item() != hi.item():
             raise SystemExit("bench.py: tensor-parallel ranks diverged in the end-to-end loop")
 
+    # ---- batched prefill, timed here because every rank of a tensor-parallel group takes part (partial blocks reduced over NVLink) ----
+    pms, prefill_err = None, None
+    if not args.no_prefill:
+        try:
+            Tn = min(2048, args.ctx)
+            ptoks = np.random.default_rng(0).integers(0, shape.vocab_size, Tn).tolist()
+            m.reset()
+            pms = m.bench_prefill(ptoks, 0)
+        except Exception as e:  # noqa: BLE001
+            prefill_err = str(e)
+            pms = float("nan")
+        if world > 1:
+            tms = torch.tensor([pms], device="cuda")
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            pms = float(tms.item())
+
     if rank != 0:
         m.close()
         if world > 1:
@@ -491,20 +507,20 @@ def main():
 
     # ---- batched prefill (tcgen05 int8 GEMM path), secondary metric of BASELINE.json ----
     prefill = None
-    if world == 1 and not args.no_prefill:
+    if pms is not None and pms == pms:
         try:
             Tn = min(2048, args.ctx)
-            ptoks = np.random.default_rng(0).integers(0, shape.vocab_size, Tn).tolist()
-            m.reset()
-            pms = m.bench_prefill(ptoks, 0)
             ah, kvd = shape.n_heads * shape.head_dim, shape.n_kv_heads * shape.head_dim
             ops = 2.0 * Tn * shape.n_layers * (2 * shape.dim * ah + 2 * shape.dim * kvd + 3 * shape.dim * shape.hidden_dim)
             prefill = {"tokens": Tn, "ms": pms, "value": Tn / pms * 1e3, "unit": "tok/s", "gemm_int8_TOPS": ops / pms / 1e9,
                        "frac_of_int8_peak_4500_TOPS_spec": ops / pms / 1e9 / 4500.0,
-                       "note": "whole prefill (norm/quantize, tcgen05 GEMMs with per-group TMEM drains, f32 causal attention); "
-                               "GEMM TOPS counts the int8 MACs only; peak is the datasheet figure (no measured int8 peak available)"}
+                       "note": "whole prefill (norm/quantize, tcgen05 GEMMs with per-group TMEM drains, tensor-core causal attention on an FP16 hi/lo "
+                               "split; under tensor parallelism the row-parallel partial blocks are summed over NVLink peer loads); GEMM TOPS counts "
+                               "the int8 MACs only; peak is the datasheet figure (the same tiling as a dense int8 GEMM: profiles/r02_gemm_q8_ceilings.txt)"}
         except Exception as e:  # noqa: BLE001
             log(f"[bench] prefill measurement failed: {e}")
+    elif prefill_err:
+        log(f"[bench] prefill measurement failed: {prefill_err}")
 
     cpu, parity = None, None
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
