@@ -83,6 +83,10 @@ constexpr int MEGA_EDGES = 6;                       // epochs per layer: one per
 #define MEGA_LAZY_SYNC 0    // 1: no CTA-wide sync at the end of the o_proj / gate-up / down steps (the next prologue syncs before it rewrites the
                             // activation; down_proj's activation lives in a second buffer so that gate/up stragglers may still read the first)
 #endif
+#ifndef MEGA_ATTN_V2
+#define MEGA_ATTN_V2 1      // 1: position loop with lane = cached position (skewed dot products, one softmax update per 32 positions);
+                            // 0: the round-1 loop (lane = 4 dims, online softmax per position in every lane)
+#endif
 #ifndef MEGA_EARLY_W
 #define MEGA_EARLY_W 1      // issue the norm-weight loads BEFORE polling for the activation (one loaded round trip instead of two)
 #endif
@@ -134,7 +138,8 @@ struct MegaArgs {
     unsigned ll_base;                // epoch counter before this launch, already reduced mod 2^32 - 1 (host-tracked, same on every TP rank)
     unsigned long long *prof;        // optional [grid][MEGA_PROF_EVENTS] clock64 stamps (thread 0 of each CTA)
     int dbg;                         // timing experiments only (env Q3_MEGA_DBG; results are garbage): 1 = every bulk copy reads the
-                                     // same L2-resident bytes (no HBM traffic), 2 = grid barrier skipped, 4 = prologues / polls skipped
+                                     // same L2-resident bytes (no HBM traffic), 2 = grid barrier skipped, 4 = prologues / polls skipped,
+                                     // 8 = attention position loop without arithmetic (the K / V stream alone)
 };
 // In-kernel profiler: thread 0 of every CTA appends (clock64 << 8 | tag).  Tags: 0 start; 1 + 3*kind + {0 prologue done,
 // 1 GEMV done, 2 step-end sync done} for step kinds 0..5; >= 32 finer marks inside the prologues and the grid barrier.
@@ -703,8 +708,11 @@ struct RingPos {
 // warps that take part in the position loop: all 16 when their partials fit the scratch area, else one group
 template <int KVMUL>
 struct AttnWarps {
-    static constexpr int N = (KVMUL * MEGA_NCW * 512 + 8192 <= MEGA_SCRATCH) ? MEGA_NCW : MEGA_GW;
+    static constexpr int N = MEGA_ATTN_V2 ? MEGA_NCW : ((KVMUL * MEGA_NCW * 512 + 8192 <= MEGA_SCRATCH) ? MEGA_NCW : MEGA_GW);
 };
+__device__ __forceinline__ void gsync(int grp) { // the 8 warps of one consumer group
+    asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(MEGA_GW * 32) : "memory");
+}
 
 template <int GS, int KVMUL>
 __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int pos, int kvh, int split, int nsplit,
@@ -718,7 +726,9 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
     float *sm_m = reinterpret_cast<float *>(sv + 32);                 // [NATT][KVMUL]
     float *sm_l = sm_m + NATT * KVMUL;                                // [NATT][KVMUL]
     float4 *sm_acc = reinterpret_cast<float4 *>(sm_l + NATT * KVMUL); // [NATT][KVMUL][32]
-    static_assert((KVMUL * 32 + 64) * 16 + 2 * NATT * KVMUL * 4 + NATT * KVMUL * 512 <= MEGA_SCRATCH, "attention scratch");
+    static_assert(MEGA_ATTN_V2 ? ((KVMUL * 32 + 64) * 16 + (2 * MEGA_GW * 32 + 16 + 8 * HEAD_DIM) * 4 <= MEGA_SCRATCH)
+                               : ((KVMUL * 32 + 64) * 16 + 2 * NATT * KVMUL * 4 + NATT * KVMUL * 512 <= MEGA_SCRATCH),
+                  "attention scratch");
     static_assert(KVMUL + 2 <= MEGA_NCW, "one warp per gathered row");
     const int n = pos + 1;
     const int per = (n + nsplit - 1) / nsplit;
@@ -754,6 +764,170 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
     csync();
     prof_mark(pr, 35); // q / k normalised + rotated
     const float scale = __fdiv_rn(1.0f, sqrtf((float)HEAD_DIM));
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+    float M = -INFINITY, L = 0.0f;
+#if MEGA_ATTN_V2
+    {
+        // The cache rows t0 .. t1 of this kv head arrive through the weight ring: stages of MEGA_KV_ROWS = 32 positions (K tile, then
+        // V tile, 16 KB each, [position][128] f32), issued by the producers behind the QKV weights; stages alternate between the two
+        // consumer groups like weight stages.  Inside a group, warp w works for query head w % KVMUL on the dims of part w / KVMUL
+        // (PARTS = 8 / KVMUL parts of DPP dims):
+        //   scores : LANE = cached position.  Each lane walks its K row in 16-byte chunks, starting `lane` chunks in (the rows are
+        //            512 B apart, so the same chunk index in every lane would be a 32-way bank conflict; skewed, a quarter warp
+        //            touches 8 distinct bank groups, and the matching q chunks are consecutive addresses); the PARTS partial sums
+        //            of a head are exchanged through shared memory;
+        //   softmax: ONE update per 32 positions -- a warp maximum, one exp per lane, a warp sum (the round-1 loop redid the whole
+        //            online update, 2 exps, in all 32 lanes for every single position);
+        //   P V    : lane = dims; the weight of position j comes from lane j by shuffle.
+        // Row `pos` itself is not in the cache yet when its tile is fetched: that lane / iteration reads sk / sv instead.
+        constexpr int PARTS = MEGA_GW / KVMUL, DPP = HEAD_DIM / PARTS, CPP = DPP / 4; // dims / 16-byte chunks per part
+        constexpr int VPL = DPP >= 32 ? DPP / 32 : 1;                                  // output dims per lane (KVMUL 1: lanes >= DPP idle)
+        static_assert(MEGA_GW % KVMUL == 0 && (CPP & (CPP - 1)) == 0, "head / part split");
+        const int grp = warp / MEGA_GW, wl = warp % MEGA_GW;
+        const int head = wl % KVMUL, part = wl / KVMUL;
+        float *sbase = reinterpret_cast<float *>(sv + 32);                              // behind q / k / v
+        float *sS = sbase + grp * (MEGA_GW * 32);                                       // [grp][part][head][32] partial scores
+        const uint32_t sq_s = smem_u32(sq) + head * 512, sk_s = smem_u32(sk), sv_s = smem_u32(sv);
+        float m = -INFINITY, l = 0.0f;
+        float acc[VPL];
+#pragma unroll
+        for (int j = 0; j < VPL; j++) acc[j] = 0.0f;
+        const int nst = (t1 - t0 + MEGA_KV_ROWS - 1) / MEGA_KV_ROWS;
+        for (int st = 0; st < nst; st++) {
+            if ((st & 1) == grp) {
+                const int slot = rp.it % MEGA_NSTAGE;
+                mbar_wait(&myfull[slot], (rp.fullp >> slot) & 1, a.status);
+                rp.fullp ^= 1u << slot;
+                const uint32_t kt = ring_s + slot * slot_bytes, vt = kt + MEGA_KV_ROWS * HEAD_DIM * 4;
+                const int tb = t0 + st * MEGA_KV_ROWS, t = tb + lane; // first position of the stage, this lane's position
+                if (a.dbg & 8) { // timing experiment: the K / V stream through the ring without the arithmetic
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[slot]);
+                    rp.it++;
+                    continue;
+                }
+                const uint32_t krow = (t == pos ? sk_s : kt + lane * (HEAD_DIM * 4)) + part * (DPP * 4);
+                const uint32_t qrow = sq_s + part * (DPP * 4);
+                // four chunks per round: eight 128-bit loads in flight, four independent partial sums
+                float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int i0 = 0; i0 < CPP; i0 += 4) {
+                    int4 ki[4], qi[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int c = ((i0 + u + lane) & (CPP - 1)) * 16;
+                        ki[u] = lds128(krow + c);
+                        qi[u] = lds128(qrow + c);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        s4[u] = fmaf(__int_as_float(qi[u].x), __int_as_float(ki[u].x), s4[u]);
+                        s4[u] = fmaf(__int_as_float(qi[u].y), __int_as_float(ki[u].y), s4[u]);
+                        s4[u] = fmaf(__int_as_float(qi[u].z), __int_as_float(ki[u].z), s4[u]);
+                        s4[u] = fmaf(__int_as_float(qi[u].w), __int_as_float(ki[u].w), s4[u]);
+                    }
+                }
+                float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                if (PARTS > 1) { // the parts of a head add their partial sums (same order in every part: identical scores)
+                    sS[(part * KVMUL + head) * 32 + lane] = s;
+                    gsync(grp);
+                    s = 0.0f;
+#pragma unroll
+                    for (int pp = 0; pp < PARTS; pp++) s += sS[(pp * KVMUL + head) * 32 + lane];
+                    gsync(grp); // sS is rewritten in this group's next stage
+                }
+                s = t < t1 ? __fmul_rn(s, scale) : -INFINITY;
+                const float mn = fmaxf(m, warp_max(s));
+                const float corr = expf(m - mn), pj = expf(s - mn); // exp(-inf) = 0: first stage / positions past the end
+                l = l * corr + warp_sum(pj);
+                m = mn;
+#pragma unroll
+                for (int j = 0; j < VPL; j++) acc[j] *= corr;
+                // all 32 rows of the stage, four per round (loads and shuffles of a round in flight together): rows past the end carry
+                // weight 0 (their scores were -inf) and finite values (cache rows are zero-initialised, tiles past the cache zero-filled)
+                const uint32_t vcol = (part * DPP + (DPP >= 32 ? lane * VPL : (lane & (DPP - 1)))) * 4;
+                const int jpos = pos - tb; // row of the stage that holds `pos` (taken from sv), if any
+#pragma unroll 2
+                for (int j0 = 0; j0 < MEGA_KV_ROWS; j0 += 4) {
+                    float vv[4][VPL], w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t va = (j0 + u == jpos ? sv_s : vt + (j0 + u) * (HEAD_DIM * 4)) + vcol;
+                        if (VPL == 4) {
+                            const int4 v = lds128(va);
+                            vv[u][0] = __int_as_float(v.x);
+                            vv[u][1 % VPL] = __int_as_float(v.y);
+                            vv[u][2 % VPL] = __int_as_float(v.z);
+                            vv[u][3 % VPL] = __int_as_float(v.w);
+                        } else if (VPL == 2) {
+                            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(vv[u][0]), "=f"(vv[u][1 % VPL]) : "r"(va));
+                        } else {
+                            vv[u][0] = lds_f32(va);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) w[u] = __shfl_sync(0xffffffffu, pj, j0 + u);
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+#pragma unroll
+                        for (int j = 0; j < VPL; j++) acc[j] = fmaf(w[u], vv[u][j], acc[j]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);
+            }
+            rp.it++;
+        }
+        prof_mark(pr, 36); // position loop done
+        // merge the two groups (each holds the stages it owned), head by head: group 1 hands over, group 0 combines and lays the head
+        // out as [128] floats for the warps that publish it
+        float *xm = sbase, *xl = sbase + 2 * MEGA_GW * 32;                      // group 1's m[8] (score area, free now) and l[8]
+        float *xa = xl + 16;                                                   // group 1's accumulators [8 warps][DPP], then the final [KVMUL][128]
+        csync(); // every warp is done with sS
+        if (grp == 1) {
+            if (lane == 0) {
+                xm[wl] = m;
+                xl[wl] = l;
+            }
+            if (DPP >= 32 || lane < DPP) {
+#pragma unroll
+                for (int j = 0; j < VPL; j++) xa[wl * DPP + (DPP >= 32 ? lane * VPL : lane) + j] = acc[j];
+            }
+        }
+        csync();
+        float mt = m, lt = l;
+        if (grp == 0) {
+            const float m1 = xm[wl], l1 = xl[wl];
+            mt = fmaxf(m, m1);
+            const float c0 = m == -INFINITY ? 0.0f : expf(m - mt), c1 = m1 == -INFINITY ? 0.0f : expf(m1 - mt);
+            lt = l * c0 + l1 * c1;
+            if (DPP >= 32 || lane < DPP) {
+#pragma unroll
+                for (int j = 0; j < VPL; j++) {
+                    const int d = (DPP >= 32 ? lane * VPL : lane) + j;
+                    acc[j] = acc[j] * c0 + xa[wl * DPP + d] * c1;
+                }
+            }
+        }
+        csync(); // group 1's hand-over has been read: xa becomes the [KVMUL][128] output layout
+        float *xo = xa, *xs_m = sbase + 16, *xs_l = sbase + 24; // (free part of the score area)
+        if (grp == 0) {
+            if (DPP >= 32 || lane < DPP) {
+#pragma unroll
+                for (int j = 0; j < VPL; j++) xo[head * HEAD_DIM + part * DPP + (DPP >= 32 ? lane * VPL : lane) + j] = acc[j];
+            }
+            if (part == 0 && lane == 0) {
+                xs_m[head] = mt;
+                xs_l[head] = lt;
+            }
+        }
+        csync();
+        if (warp < KVMUL) {
+            A = reinterpret_cast<const float4 *>(xo + warp * HEAD_DIM)[lane];
+            M = xs_m[warp];
+            L = xs_l[warp];
+        }
+    }
+#else
     float4 qv[KVMUL];
     float m[KVMUL], l[KVMUL];
     float4 acc[KVMUL];
@@ -852,8 +1026,6 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
     }
     csync();
     // warp h < KVMUL merges the NATT warp partials of query head h (lane w owns partial w: one exp per lane)
-    float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
-    float M = -INFINITY, L = 0.0f;
     if (warp < KVMUL) {
         const int h = warp;
         const float mw = lane < NATT ? sm_m[lane * KVMUL + h] : -INFINITY;
@@ -870,6 +1042,7 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
             A.w += aw.w * c;
         }
     }
+#endif
     if (nsplit == 1) { // the only split of its kv head: A / L is the attention output
         if (warp < KVMUL) publish_head<GS>(a, kvh * KVMUL + warp, lane, A, L, ep_a);
         return;
