@@ -715,7 +715,7 @@ __device__ __forceinline__ void gsync(int grp) { // the 8 warps of one consumer 
 }
 
 template <int GS, int KVMUL>
-__device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int pos, int kvh, int split, int nsplit,
+__device__ __forceinline__ void attention_item(const MegaArgs &a, int layer, int pos, int kvh, int split, int nsplit,
                                                uint8_t *scratch, unsigned ep_q, unsigned ep_a, Prof &pr, RingPos &rp, uint32_t ring_s, int slot_bytes,
                                                uint64_t *myfull, uint64_t *empty) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -813,12 +813,22 @@ __device__ __noinline__ void attention_item(const MegaArgs &a, int layer, int po
 #pragma unroll
                 for (int i0 = 0; i0 < CPP; i0 += 4) {
                     int4 ki[4], qi[4];
+                    uint32_t cc[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int c = ((i0 + u + lane) & (CPP - 1)) * 16;
-                        ki[u] = lds128(krow + c);
-                        qi[u] = lds128(qrow + c);
-                    }
+                    for (int u = 0; u < 4; u++) cc[u] = ((i0 + u + lane) & (CPP - 1)) * 16;
+                    // one asm statement: left to itself the compiler re-serialises the round into load-load-4 FMAs per chunk (registers),
+                    // which exposes a shared-memory latency per chunk
+                    asm volatile(
+                        "ld.shared.v4.b32 {%0,%1,%2,%3}, [%32];\n\tld.shared.v4.b32 {%4,%5,%6,%7}, [%33];\n\t"
+                        "ld.shared.v4.b32 {%8,%9,%10,%11}, [%34];\n\tld.shared.v4.b32 {%12,%13,%14,%15}, [%35];\n\t"
+                        "ld.shared.v4.b32 {%16,%17,%18,%19}, [%36];\n\tld.shared.v4.b32 {%20,%21,%22,%23}, [%37];\n\t"
+                        "ld.shared.v4.b32 {%24,%25,%26,%27}, [%38];\n\tld.shared.v4.b32 {%28,%29,%30,%31}, [%39];"
+                        : "=r"(ki[0].x), "=r"(ki[0].y), "=r"(ki[0].z), "=r"(ki[0].w), "=r"(ki[1].x), "=r"(ki[1].y), "=r"(ki[1].z), "=r"(ki[1].w),
+                          "=r"(ki[2].x), "=r"(ki[2].y), "=r"(ki[2].z), "=r"(ki[2].w), "=r"(ki[3].x), "=r"(ki[3].y), "=r"(ki[3].z), "=r"(ki[3].w),
+                          "=r"(qi[0].x), "=r"(qi[0].y), "=r"(qi[0].z), "=r"(qi[0].w), "=r"(qi[1].x), "=r"(qi[1].y), "=r"(qi[1].z), "=r"(qi[1].w),
+                          "=r"(qi[2].x), "=r"(qi[2].y), "=r"(qi[2].z), "=r"(qi[2].w), "=r"(qi[3].x), "=r"(qi[3].y), "=r"(qi[3].z), "=r"(qi[3].w)
+                        : "r"(krow + cc[0]), "r"(krow + cc[1]), "r"(krow + cc[2]), "r"(krow + cc[3]), "r"(qrow + cc[0]), "r"(qrow + cc[1]),
+                          "r"(qrow + cc[2]), "r"(qrow + cc[3]));
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         s4[u] = fmaf(__int_as_float(qi[u].x), __int_as_float(ki[u].x), s4[u]);
