@@ -983,8 +983,13 @@ static int prefill_run(q3_handle *h, const int *tokens_host, int T, int pos0) {
         float *kc_l = h->kc + (size_t)l * c.seq_len * KV;
         float *vc_l = h->vc + (size_t)l * c.seq_len * KV;
         // attn_norm + quantize (qwen3.rs:134-136), embedding on layer 0
-        GS_DISPATCH(gs, (k_pf_norm_quant<GS><<<T, 256, 0, s>>>(h->pf_x, W.rms_att, h->pf_xq, h->pf_xsT, dim, Tpad,
-                                                              l == 0 ? h->embed.q : nullptr, h->embed.s, h->pf_tokens, 0)));
+        if (dim <= 4096) {
+            GS_DISPATCH(gs, (k_pf_norm_quant<GS, 4><<<T, 256, 0, s>>>(h->pf_x, W.rms_att, h->pf_xq, h->pf_xsT, dim, Tpad,
+                                                                     l == 0 ? h->embed.q : nullptr, h->embed.s, h->pf_tokens, 0)));
+        } else {
+            GS_DISPATCH(gs, (k_pf_norm_quant<GS><<<T, 256, 0, s>>>(h->pf_x, W.rms_att, h->pf_xq, h->pf_xsT, dim, Tpad,
+                                                                  l == 0 ? h->embed.q : nullptr, h->embed.s, h->pf_tokens, 0)));
+        }
         PrefillGemmArgs g{};
         g.T = T; g.Tpad = Tpad; g.K = dim; g.N = W.qkv.rows; g.wsT = W.qkv.sT; g.xsT = h->pf_xsT;
         g.q = h->pf_q; g.kc = kc_l; g.vc = vc_l; g.AH = AH; g.KV = KV; g.pos0 = pos0;
@@ -1027,8 +1032,11 @@ static int prefill_run(q3_handle *h, const int *tokens_host, int T, int pos0) {
         if (h->tp_size == 1) {
             if ((rc = launch_gemm_q8<PF_EPI_RESID>(gs, mx_ah, W.wo.map, o, s))) return rc;
         } else if ((rc = prefill_tp_rowparallel(h, 0, mx_ah, W.wo.map, o, T))) return rc;
-        GS_DISPATCH(gs, (k_pf_norm_quant<GS><<<T, 256, 0, s>>>(h->pf_x, W.rms_ffn, h->pf_xq, h->pf_xsT, dim, Tpad, nullptr, nullptr,
-                                                              nullptr, 0)));
+        if (dim <= 4096) {
+            GS_DISPATCH(gs, (k_pf_norm_quant<GS, 4><<<T, 256, 0, s>>>(h->pf_x, W.rms_ffn, h->pf_xq, h->pf_xsT, dim, Tpad, nullptr, nullptr, nullptr, 0)));
+        } else {
+            GS_DISPATCH(gs, (k_pf_norm_quant<GS><<<T, 256, 0, s>>>(h->pf_x, W.rms_ffn, h->pf_xq, h->pf_xsT, dim, Tpad, nullptr, nullptr, nullptr, 0)));
+        }
         PrefillGemmArgs gu{};
         gu.T = T; gu.Tpad = Tpad; gu.K = dim; gu.N = W.w13.rows; gu.wsT = W.w13.sT; gu.xsT = h->pf_xsT; gu.out = h->pf_hb; gu.ld_out = H;
         if ((rc = launch_gemm_q8<PF_EPI_SWIGLU>(gs, mx_dim, W.w13.map, gu, s))) return rc;

@@ -87,6 +87,14 @@ constexpr int MEGA_EDGES = 6;                       // epochs per layer: one per
 #define MEGA_ATTN_V2 1      // 1: position loop with lane = cached position (skewed dot products, one softmax update per 32 positions);
                             // 0: the round-1 loop (lane = 4 dims, online softmax per position in every lane)
 #endif
+#ifndef MEGA_INLINE_PRO
+#define MEGA_INLINE_PRO 0   // 1: the three prologues inlined into the step loop (each has a single call site)
+#endif
+#if MEGA_INLINE_PRO
+#define MEGA_PRO_INLINE __forceinline__
+#else
+#define MEGA_PRO_INLINE __noinline__
+#endif
 #ifndef MEGA_EARLY_W
 #define MEGA_EARLY_W 1      // issue the norm-weight loads BEFORE polling for the activation (one loaded round trip instead of two)
 #endif
@@ -434,7 +442,7 @@ constexpr int MEGA_MAXV = (MEGA_MAX_KT + 4 * MEGA_CTHREADS - 1) / (4 * MEGA_CTHR
 // src: 0 = embedding row of tokpos[0], 1 = a.x (teacher-forced entry), 2 = sx (this CTA's copy of the residual stream in
 // shared memory; a thread always owns the same elements).  zone/epoch: pending GEMV rows to add (or null).
 template <int GS>
-__device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, int src, const unsigned long long *zone, unsigned epoch,
+__device__ MEGA_PRO_INLINE void prologue_norm(const MegaArgs &a, const float *w, int src, const unsigned long long *zone, unsigned epoch,
                                               uint8_t *sxq, float *sxs, float *sred, float *sx, int KT, int G, Prof &pr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n4 = a.dim >> 2;
@@ -549,7 +557,7 @@ __device__ __noinline__ void prologue_norm(const MegaArgs &a, const float *w, in
 // o_proj input: the attention output arrives already normalised and quantised (attention_item), packed 4 int8 per word in the
 // chunk order of this phase's shared-memory activation, followed by the group scales -- the prologue is a polled copy.
 template <int GS>
-__device__ __noinline__ void prologue_attn_poll(const MegaArgs &a, unsigned epoch, uint8_t *sxq, float *sxs) {
+__device__ MEGA_PRO_INLINE void prologue_attn_poll(const MegaArgs &a, unsigned epoch, uint8_t *sxq, float *sxs) {
     const int tid = threadIdx.x;
     const int nq = a.AH_l >> 2, ng = a.AH_l / GS; // nq is a multiple of 32
     unsigned spins = 0;
@@ -595,7 +603,7 @@ __device__ __forceinline__ void quant_ll_one(const MegaArgs &a, const unsigned l
     }
 }
 template <int GS>
-__device__ __noinline__ void prologue_quant_ll(const MegaArgs &a, const unsigned long long *z, unsigned epoch, int n, uint8_t *sxq, float *sxs, int KT, int G) {
+__device__ MEGA_PRO_INLINE void prologue_quant_ll(const MegaArgs &a, const unsigned long long *z, unsigned epoch, int n, uint8_t *sxq, float *sxs, int KT, int G) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int n4 = n >> 2;
     unsigned long long wa[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};

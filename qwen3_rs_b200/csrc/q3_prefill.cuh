@@ -506,7 +506,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) // 96 registers: three schedule
 // ------------------------------------------------------------------------------------------
 // per-token RMSNorm (+ embedding gather) + group quantise; scales written group-major [ng][Tpad].
 // grid = T, block = 256.  (layers.rs:72-76, 109-130; tensor.rs:91-119)
-template <int GS>
+// MAXV: float4 per thread held in registers (n <= 1024 * MAXV): 4 covers every dim <= 4096 at 16 registers instead of 64 --
+// 8 resident blocks per SM instead of 3 (the kernel is latency-bound: load -> reduce -> quantise per token).
+template <int GS, int MAXV = 16>
 __global__ void __launch_bounds__(256) k_pf_norm_quant(float *x, const float *w, int8_t *q, float *sT, int n, int Tpad,
                                                        const int8_t *embed_q, const float *embed_s, const int *tokens, int write_normed) {
     __shared__ float red[8];
@@ -514,7 +516,6 @@ __global__ void __launch_bounds__(256) k_pf_norm_quant(float *x, const float *w,
     const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float *xr = x + (size_t)t * n;
     const int n4 = n >> 2;
-    constexpr int MAXV = 16; // n <= 16384
     float4 v[MAXV];
     float ss = 0.0f;
 #pragma unroll
