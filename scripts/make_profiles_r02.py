@@ -150,8 +150,8 @@ def copies():
             "__syncwarp + mbarrier.arrive after its last read; producer: mbarrier.try_wait before issuing the copy) -- the standard TMA pipeline hand-off,\n"
             "which racecheck does not model for asynchronous-proxy writes.  memcheck and synccheck are clean (r02_sanitizer_memcheck.log, _synccheck.log).\n\n")
     kinds = defaultdict(int)
-    for m in re.finditer(r"Read Thread .*? at (\S+?)\+.*?\n=========     Write Thread .*? at (\S+?)\+", race):
-        kinds[(m.group(1), m.group(2))] += 1
+    for m in re.finditer(r"Read Thread \([^)]*\) at (.+?)\+0x[0-9a-f]+ in \S+\n=========     Write Thread \([^)]*\) at (.+?)\+0x", race):
+        kinds[(m.group(1).split("(")[0], m.group(2).split("(")[0])] += 1
     head += "hazard classes in this excerpt (reader function, writer function): " + "; ".join("%s / %s x %d" % (a, b, n) for (a, b), n in kinds.items()) + "\n\n"
     open(os.path.join(P, "r02_sanitizer_racecheck.log"), "w").write(head + race[:40000] + "\n...\n" + race[-400:])
 
