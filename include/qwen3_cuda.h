@@ -127,6 +127,11 @@ int q3_reset(q3_handle *h);
 /* Device pointer to the logits of the last forward (vocab_size f32, valid until the next call). */
 const float *q3_logits_device(const q3_handle *h);
 
+/* The handle's own page-locked host buffer (vocab_size f32).  Passed as `logits_host` to q3_forward / q3_prefill, the logits are
+ * DMA-ed straight into it and no second host copy is made -- the reference's `forward` returns a borrow of the transformer's own
+ * logits buffer in the same way (models/qwen3.rs:78); valid until the next call on this handle. */
+float *q3_logits_host(q3_handle *h);
+
 /* Copy KV cache rows [pos0, pos0+n) of one layer to the host, layout [n][n_kv_heads*head_dim]
  * (the reference's cache layout, layers.rs:329-331), or overwrite them from the host.  A tensor-parallel handle holds
  * only its own kv heads: rows are [n][(n_kv_heads / tp_size) * head_dim], heads tp_rank * n_kv_heads / tp_size ... */

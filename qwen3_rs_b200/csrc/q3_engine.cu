@@ -1323,6 +1323,7 @@ extern "C" void q3_destroy(q3_handle *h) {
 
 extern "C" const q3_config *q3_get_config(const q3_handle *h) { return h ? &h->cfg : nullptr; }
 extern "C" const float *q3_logits_device(const q3_handle *h) { return h ? h->logits : nullptr; }
+extern "C" float *q3_logits_host(q3_handle *h) { return h ? h->h_logits : nullptr; }
 extern "C" int q3_launches_per_step(const q3_handle *h) { return h ? h->launches_per_step : 0; }
 extern "C" int q3_set_decode_path(q3_handle *h, int path) {
     if (!h) return fail(Q3_EINVAL, "null handle");
@@ -1382,7 +1383,7 @@ extern "C" int q3_forward(q3_handle *h, int token, int pos, float *logits_host) 
     if (logits_host) {
         CK(cudaMemcpyAsync(h->h_logits, h->logits, (size_t)h->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        memcpy(logits_host, h->h_logits, (size_t)h->cfg.vocab_size * 4);
+        if (logits_host != h->h_logits) memcpy(logits_host, h->h_logits, (size_t)h->cfg.vocab_size * 4);
     } else {
         CK(cudaStreamSynchronize(h->stream));
     }
@@ -1657,7 +1658,7 @@ extern "C" int q3_prefill(q3_handle *h, const int *tokens, int n, int pos0, floa
     if (last_logits_host) {
         CK(cudaMemcpyAsync(h->h_logits, h->logits, (size_t)h->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        memcpy(last_logits_host, h->h_logits, (size_t)h->cfg.vocab_size * 4);
+        if (last_logits_host != h->h_logits) memcpy(last_logits_host, h->h_logits, (size_t)h->cfg.vocab_size * 4);
     } else {
         CK(cudaStreamSynchronize(h->stream));
     }

@@ -77,6 +77,7 @@ ABI = {
     "q3_bench_prefill": (_i, [_vp, _vp, _i, _i, C.POINTER(_f)]),
     "q3_reset": (_i, [_vp]),
     "q3_logits_device": (_vp, [_vp]),
+    "q3_logits_host": (_vp, [_vp]),
     "q3_kv_read": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "q3_kv_write": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "q3_forward_layers": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
@@ -146,13 +147,17 @@ class Transformer:
         c = load_library().q3_get_config(handle).contents
         self._config = ModelConfig(**{n: (bool(getattr(c, n)) if n == "shared_classifier" else int(getattr(c, n)))
                                       for n, _ in _Cfg._fields_})
-        self._logits = np.empty(self._config.vocab_size, np.float32)
+        # the handle's own page-locked logits buffer, wrapped without a copy (q3_logits_host): forward() DMA-s into it
+        hp = load_library().q3_logits_host(self._h)
+        self._logits = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_float)), shape=(self._config.vocab_size,)) if hp else \
+            np.empty(self._config.vocab_size, np.float32)
 
     # -- the reference trait --------------------------------------------------------------
-    def forward(self, token: int, pos: int) -> np.ndarray:
-        """Transformer::forward.  Out-of-range token/pos raises (the reference panics)."""
+    def forward(self, token: int, pos: int, copy: bool = True) -> np.ndarray:
+        """Transformer::forward.  Out-of-range token/pos raises (the reference panics).  copy=False returns a view of the
+        transformer's own logits buffer, valid until the next call -- what the reference's `forward(..) -> &[f32]` hands out."""
         _check(load_library().q3_forward(self._h, int(token), int(pos), _ptr(self._logits)))
-        return self._logits.copy()
+        return self._logits.copy() if copy else self._logits
 
     def get_config(self) -> ModelConfig:
         return self._config
@@ -290,6 +295,7 @@ class Transformer:
 
     def close(self) -> None:
         if getattr(self, "_h", None):
+            self._logits = np.array(self._logits, np.float32)  # detach from the handle's page-locked buffer before it is freed
             load_library().q3_destroy(self._h)
             self._h = None
 

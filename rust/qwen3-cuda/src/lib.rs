@@ -26,6 +26,7 @@ extern "C" {
     fn q3_decode_greedy(h: *mut Q3Handle, first_token: c_int, pos0: c_int, n: c_int, tokens_out: *mut c_int) -> c_int;
     fn q3_prefill(h: *mut Q3Handle, tokens: *const c_int, n: c_int, pos0: c_int, last_logits_host: *mut c_float) -> c_int;
     fn q3_reset(h: *mut Q3Handle) -> c_int;
+    fn q3_logits_host(h: *mut Q3Handle) -> *mut c_float;
 }
 
 fn last_error() -> String {
@@ -36,7 +37,9 @@ fn last_error() -> String {
 pub struct CudaTransformer {
     handle: *mut Q3Handle,
     config: ModelConfig,
-    logits: Vec<f32>,
+    /// the handle's own page-locked logits buffer (q3_logits_host): `forward` DMA-s into it and lends it out, like the
+    /// reference's `&self.buffers.logits` (models/qwen3.rs:78) -- no second host copy
+    logits: *mut c_float,
 }
 
 impl CudaTransformer {
@@ -55,7 +58,7 @@ impl CudaTransformer {
             head_dim: c.head_dim as usize, seq_len: c.seq_len as usize, vocab_size: c.vocab_size as usize,
             group_size: c.group_size as usize, shared_classifier: c.shared_classifier != 0,
         };
-        let logits = vec![0.0; config.vocab_size];
+        let logits = unsafe { q3_logits_host(handle) };
         Ok(Self { handle, config, logits })
     }
 
@@ -85,11 +88,11 @@ impl CudaTransformer {
     /// `tokens.len() - 1` draws when temperature > 0, then sample once.
     pub fn prefill(&mut self, tokens: &[usize], pos0: usize) -> &[f32] {
         let ids: Vec<c_int> = tokens.iter().map(|&t| t as c_int).collect();
-        let rc = unsafe { q3_prefill(self.handle, ids.as_ptr(), ids.len() as c_int, pos0 as c_int, self.logits.as_mut_ptr()) };
+        let rc = unsafe { q3_prefill(self.handle, ids.as_ptr(), ids.len() as c_int, pos0 as c_int, self.logits) };
         if rc != 0 {
             panic!("{}", last_error());
         }
-        &self.logits
+        unsafe { std::slice::from_raw_parts(self.logits, self.config.vocab_size) }
     }
 
     /// Zero the KV cache (a fresh `TransformerBlockBuffers`, qwen3.rs:439-440).
@@ -100,11 +103,11 @@ impl CudaTransformer {
 
 impl Transformer for CudaTransformer {
     fn forward(&mut self, token: usize, pos: usize) -> &[f32] {
-        let rc = unsafe { q3_forward(self.handle, token as c_int, pos as c_int, self.logits.as_mut_ptr()) };
+        let rc = unsafe { q3_forward(self.handle, token as c_int, pos as c_int, self.logits) };
         if rc != 0 {
             panic!("{}", last_error()); // the reference panics on out-of-range token/pos (slice index)
         }
-        &self.logits
+        unsafe { std::slice::from_raw_parts(self.logits, self.config.vocab_size) }
     }
     fn get_config(&self) -> &ModelConfig {
         &self.config
