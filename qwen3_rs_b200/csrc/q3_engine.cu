@@ -936,7 +936,15 @@ static int prefill_tp_rowparallel(q3_handle *h, int which, const CUtensorMap &mx
     h->pf_xbar_count++;
     k_pf_xbarrier<<<1, 32, 0, h->stream>>>(h->pf_peers[which], h->tp_size, h->tp_rank, h->pf_xbar_count * (unsigned long long)h->tp_size, h->d_status);
     const size_t n4 = (size_t)T * h->cfg.dim / 4;
-    k_pf_allreduce_resid<<<h->num_sms * 4, 256, 0, h->stream>>>(h->pf_x, h->pf_peers[which], h->tp_size, n4);
+    static const int rsag = getenv("Q3_PF_TP_RSAG") ? atoi(getenv("Q3_PF_TP_RSAG")) : -1; // -1: by group size; 0 / 1: forced (tests)
+    if (rsag == 1 || (rsag < 0 && h->tp_size > 2)) { // reduce-scatter, barrier, all-gather: 2 (tp-1)/tp blocks over NVLink instead of tp-1
+        k_pf_reduce_scatter<<<h->num_sms * 2, 256, 0, h->stream>>>(h->pf_peers[which], g.out, h->tp_size, h->tp_rank, n4);
+        h->pf_xbar_count++;
+        k_pf_xbarrier<<<1, 32, 0, h->stream>>>(h->pf_peers[which], h->tp_size, h->tp_rank, h->pf_xbar_count * (unsigned long long)h->tp_size, h->d_status);
+        k_pf_allgather_resid<<<dim3(h->num_sms / 2, h->tp_size), 256, 0, h->stream>>>(h->pf_x, h->pf_peers[which], h->tp_size, n4);
+    } else {
+        k_pf_allreduce_resid<<<h->num_sms * 4, 256, 0, h->stream>>>(h->pf_x, h->pf_peers[which], h->tp_size, n4);
+    }
     CK(cudaGetLastError());
     return 0;
 }

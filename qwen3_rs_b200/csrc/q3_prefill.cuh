@@ -1150,6 +1150,37 @@ __global__ void k_pf_xbarrier(PfPeers p, int tp, int rank, unsigned long long ta
         }
     } while (v < target);
 }
+// For tp > 2 the same sum as a reduce-scatter + all-gather over the same peer mappings (2 (tp-1)/tp blocks over NVLink per rank instead
+// of tp-1): rank r sums slice r of all tp partial blocks in rank order and writes it back into ITS OWN block (nobody else reads that
+// slice of it), a second barrier, then every rank adds slice r of rank r's block to its residual stream.  Same values as the direct form.
+__global__ void __launch_bounds__(256) k_pf_reduce_scatter(PfPeers p, float *own, int tp, int rank, size_t n4) {
+    const size_t lo = n4 * rank / tp, hi = n4 * (rank + 1) / tp;
+    for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
+        float4 s = __ldcg(reinterpret_cast<const float4 *>(p.part[0]) + i);
+        for (int r = 1; r < tp; r++) {
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(p.part[r]) + i);
+            s.x = __fadd_rn(s.x, v.x);
+            s.y = __fadd_rn(s.y, v.y);
+            s.z = __fadd_rn(s.z, v.z);
+            s.w = __fadd_rn(s.w, v.w);
+        }
+        reinterpret_cast<float4 *>(own)[i] = s;
+    }
+}
+// grid.y = owner rank of the slice
+__global__ void __launch_bounds__(256) k_pf_allgather_resid(float *x, PfPeers p, int tp, size_t n4) {
+    const int r = blockIdx.y;
+    const size_t lo = n4 * r / tp, hi = n4 * (r + 1) / tp;
+    for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 s = __ldcg(reinterpret_cast<const float4 *>(p.part[r]) + i);
+        float4 o = reinterpret_cast<float4 *>(x)[i];
+        o.x = __fadd_rn(o.x, s.x);
+        o.y = __fadd_rn(o.y, s.y);
+        o.z = __fadd_rn(o.z, s.z);
+        o.w = __fadd_rn(o.w, s.w);
+        reinterpret_cast<float4 *>(x)[i] = o;
+    }
+}
 // x[t][c] += sum over ranks (in rank order) of part_r[t][c]      n4 = T * dim / 4
 __global__ void __launch_bounds__(256) k_pf_allreduce_resid(float *x, PfPeers p, int tp, size_t n4) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
