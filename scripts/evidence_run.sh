@@ -1,5 +1,5 @@
 # Round-2 evidence captures (one B200): sanitizer logs, ncu full capture of the decode kernel (exported to CSV pages here: the
-# .ncu-rep files are too large to travel), launch list.  (The prefill captures: scripts/call12.sh-style, see profiles/r02_ncu_prefill_4b.txt.)
+# .ncu-rep files are too large to travel), launch list.  (The prefill captures: scripts/evidence_prefill.sh.)
 set -x
 export PYTHONUNBUFFERED=1
 mkdir -p /tmp/ev gpurun_out
