@@ -49,7 +49,11 @@ constexpr int MEGA_CTHREADS = MEGA_NCW * 32;        // 512 consumer threads
 // + one producer warp per consumer group.  (A producer warpgroup that hands its registers to the consumers with
 // setmaxnreg was tried: ptxas cannot allocate this kernel's consumer path in 112-120 registers without spilling and
 // refuses -- see DESIGN.md.)
-constexpr int MEGA_THREADS = MEGA_CTHREADS + 32 * MEGA_GROUPS;
+#ifndef MEGA_HELPER
+#define MEGA_HELPER 0
+#endif
+constexpr int MEGA_NHELP = MEGA_HELPER ? 2 : 0;       // helper warps (see MEGA_HELPER below)
+constexpr int MEGA_THREADS = MEGA_CTHREADS + 32 * MEGA_GROUPS + 32 * MEGA_NHELP;
 #ifndef MEGA_NSTAGE_
 #define MEGA_NSTAGE_ 4
 #endif
@@ -86,6 +90,10 @@ constexpr int MEGA_EDGES = 6;                       // epochs per layer: one per
 #ifndef MEGA_ATTN_V2
 #define MEGA_ATTN_V2 1      // 1: position loop with lane = cached position (skewed dot products, one softmax update per 32 positions);
                             // 0: the round-1 loop (lane = 4 dims, online softmax per position in every lane)
+#endif
+#ifndef MEGA_HELPER
+#define MEGA_HELPER 0       // 1: two helper warps poll + quantise the SwiGLU outputs (the down_proj activation, 96 KB of flagged words per CTA) in the
+                            // background WHILE the consumers are still streaming gate/up rows; the down prologue then only waits for them
 #endif
 #ifndef MEGA_INLINE_PRO
 #define MEGA_INLINE_PRO 0   // 1: the three prologues inlined into the step loop (each has a single call site)
@@ -1277,8 +1285,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
     float *sxs = reinterpret_cast<float *>(scratch + 16384);         // up to 512 groups
     float *sred = reinterpret_cast<float *>(scratch + 16384 + 2048); // 16 floats (+ argmax scratch at +32)
     // down_proj's activation: its own buffer under MEGA_LAZY_SYNC (written while gate/up stragglers may still be reading sxq)
-    uint8_t *sxq_dn = MEGA_LAZY_SYNC ? scratch + 20480 : sxq;
-    float *sxs_dn = MEGA_LAZY_SYNC ? reinterpret_cast<float *>(scratch + 20480 + 16384) : sxs;
+    uint8_t *sxq_dn = (MEGA_LAZY_SYNC || MEGA_HELPER) ? scratch + 20480 : sxq;
+    float *sxs_dn = (MEGA_LAZY_SYNC || MEGA_HELPER) ? reinterpret_cast<float *>(scratch + 20480 + 16384) : sxs;
     static_assert(20480 + 16384 + 2048 <= MEGA_SCRATCH, "second activation buffer");
     // full barriers are per (consumer group, slot): a waiter can only tell adjacent mbarrier phases
     // apart, and with ownership alternating between the groups a group would otherwise skip the
@@ -1320,6 +1328,76 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
 
     const int L0 = a.layer0, L1 = a.layer1;
 
+#if MEGA_HELPER
+    if (warp >= MEGA_NCW + MEGA_GROUPS) {
+        // =============================== HELPERS ===============================
+        // Per layer: wait until the consumers have entered the gate/up step (barrier 4: the down activation buffer of the previous layer
+        // is free), then quantise the SwiGLU outputs group by group as their flagged words arrive -- a half-warp per group of GS values
+        // (lane = one float4, exactly prologue_quant_ll's grouping, so the int8 / scales are the same bits) -- and report (barrier 5).
+        if (a.dbg & 4) return;
+        const int hw = warp - MEGA_NCW - MEGA_GROUPS;
+        constexpr int LPG = GS / 4;                       // lanes per group
+        constexpr int GPW = 32 / LPG;                     // groups a warp handles at once
+        const int ngroups = a.H_l / GS, nunits = (ngroups + GPW - 1) / GPW; // units of GPW groups
+        const int KT = a.g[PH_DN].KT, G = a.g[PH_DN].G;
+        for (int l = L0; l < L1; l++) {
+            asm volatile("bar.sync 4, %0;" ::"n"(MEGA_CTHREADS + 64) : "memory");
+            const unsigned ep = ll_epoch(a.ll_base, (unsigned)(MEGA_EDGES * (l - L0) + 3));
+            // units hw, hw + 2, ...; a unit that is not complete yet is skipped and revisited (pending bits), with a short sleep per
+            // fruitless round so that the spinning does not take issue slots from the consumers
+            unsigned pend[8];
+#pragma unroll
+            for (int w = 0; w < 8; w++) pend[w] = 0;
+            int left = 0;
+            for (int u = hw; u < nunits; u += 2) {
+                pend[(u >> 1) >> 5] |= 1u << ((u >> 1) & 31);
+                left++;
+            }
+            unsigned spins = 0;
+            bool dead = false;
+            while (left > 0 && !dead) {
+                int progressed = 0;
+                for (int u = hw; u < nunits; u += 2) {
+                    const int bit = u >> 1;
+                    if (!((pend[bit >> 5] >> (bit & 31)) & 1u)) continue;
+                    const int i4 = u * 32 + lane; // float4 index into the H_l vector
+                    const bool in = i4 * 4 < a.H_l;
+                    unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                    if (in) {
+                        ll_load2(a.zh + (size_t)i4 * 4, w0, w1);
+                        ll_load2(a.zh + (size_t)i4 * 4 + 2, w2, w3);
+                    }
+                    const bool ok = !in || (ll_ok(w0, ep) && ll_ok(w1, ep) && ll_ok(w2, ep) && ll_ok(w3, ep));
+                    if (!__all_sync(0xffffffffu, ok)) continue;
+                    float4 y = make_float4(__uint_as_float((unsigned)w0), __uint_as_float((unsigned)w1), __uint_as_float((unsigned)w2), __uint_as_float((unsigned)w3));
+                    uint32_t packed;
+                    float scale;
+                    quantize_group4<GS>(y, packed, scale);
+                    if (in) {
+                        xq_store<GS>(sxq_dn, i4, packed, KT, G);
+                        if ((i4 % (GS / 4)) == 0) sxs_dn[i4 / (GS / 4)] = scale;
+                    }
+                    pend[bit >> 5] &= ~(1u << (bit & 31));
+                    left--;
+                    progressed++;
+                }
+                if (!progressed) {
+                    __nanosleep(200);
+                    if ((++spins & 63u) == 0) {
+                        if (*(volatile int *)a.status) dead = true;
+                        else if (spins > (1u << 22)) {
+                            atomicExch(a.status, 8);
+                            dead = true;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            asm volatile("bar.sync 5, %0;" ::"n"(MEGA_CTHREADS + 64) : "memory");
+        }
+        return;
+    }
+#endif
     if (warp >= MEGA_NCW) {
         // =============================== PRODUCERS ===============================
         // One producer thread per consumer group: the serial wait -> expect_tx -> bulk-copy loop of a single
@@ -1493,10 +1571,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_decode(const __grid_co
             prologue_attn_poll<GS>(a, ep_prev, sxq, sxs);
             ph = PH_O;
         } else {
+#if MEGA_HELPER
+            asm volatile("bar.sync 5, %0;" ::"n"(MEGA_CTHREADS + 64) : "memory"); // the helper warps have built the down activation
+#else
             prologue_quant_ll<GS>(a, a.zh, ep_prev, a.H_l, sxq_dn, sxs_dn, a.g[PH_DN].KT, a.g[PH_DN].G); // quantize(hb), layers.rs:478
+#endif
             ph = PH_DN;
         }
         prof_mark(pr, 1 + 3 * kind);
+#if MEGA_HELPER
+        if (kind == 3 && !(a.dbg & 4)) asm volatile("bar.arrive 4, %0;" ::"n"(MEGA_CTHREADS + 64) : "memory"); // gate/up starts: helpers may build this layer's down activation
+#endif
         // ------------------------------ GEMV ------------------------------
         if (kind != 1) {
             const MegaGemv &g = a.g[ph];
