@@ -38,3 +38,10 @@ def shard_plan(cfg, rank: int, size: int) -> ShardPlan:
     return ShardPlan(rank, size, range(rank * ah_l, (rank + 1) * ah_l), range(rank * kv_l, (rank + 1) * kv_l),
                      range(rank * h_l, (rank + 1) * h_l), range(rank * ah_l, (rank + 1) * ah_l),
                      range(rank * v_l, (rank + 1) * v_l))
+
+
+def prefill_exchange_slices(n4: int, size: int):
+    """The batched prefill's row-parallel exchange under TP for size > 2 (csrc/q3_prefill.cuh: k_pf_reduce_scatter /
+    k_pf_allgather_resid): rank r sums float4 elements [n4 * r // size, n4 * (r + 1) // size) of all `size` partial blocks in
+    rank order, and every rank then takes slice r from rank r.  Returns the slices (they tile [0, n4) without gaps)."""
+    return [range(n4 * r // size, n4 * (r + 1) // size) for r in range(size)]

@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 
 from oracle import binding as orc
 from oracle import np_forward as npf
-from qwen3_rs_b200.tp_plan import shard_plan
+from qwen3_rs_b200.tp_plan import prefill_exchange_slices, shard_plan
 
 
 def test_plan_covers_everything_once():
@@ -24,6 +24,26 @@ def test_plan_covers_everything_once():
         for p in plans:  # GQA groups intact, quantisation groups never straddle a shard
             assert len(p.q_rows) // len(p.kv_rows) == 4
             assert p.hidden_rows.start % 64 == 0 and p.attn_cols.start % 128 == 0
+
+
+def test_prefill_exchange_slices_tile_the_block_and_give_the_direct_sum():
+    """Reduce-scatter + all-gather form of the prefill exchange: the slices tile the block, and summing slice r on rank r in rank
+    order then gathering gives bit for bit what every rank would get by adding all partial blocks itself (the tp <= 2 form)."""
+    rng = np.random.default_rng(0)
+    for tp, n4 in ((3, 10), (4, 37 * 640 // 4), (8, 2048 * 4096 // 4 // 64), (8, 7)):
+        sl = prefill_exchange_slices(n4, tp)
+        assert sorted(i for s_ in sl for i in s_) == list(range(n4))
+        parts = rng.standard_normal((tp, n4, 4)).astype(np.float32)
+        direct = parts[0].copy()
+        for r in range(1, tp):
+            direct = (direct + parts[r]).astype(np.float32)
+        gathered = np.empty_like(direct)
+        for r, s_ in enumerate(sl):  # rank r reduces its slice ...
+            acc = parts[0][s_.start:s_.stop].copy()
+            for q in range(1, tp):
+                acc = (acc + parts[q][s_.start:s_.stop]).astype(np.float32)
+            gathered[s_.start:s_.stop] = acc  # ... and everybody gathers it
+        assert np.array_equal(gathered, direct)
 
 
 def test_plan_rejects_bad_splits():
