@@ -1974,6 +1974,7 @@ extern "C" int q3_bench_gemm_q8(int device, int T, int N, int K, int gs, int mod
     if ((rc = launch_gemm_q8<PF_EPI_STORE>(gs, mx, mw, a, 0, mode))) return rc; // warm-up
     CK(cudaDeviceSynchronize());
     if (getenv("Q3_PF_TRACE")) { // one extra launch with the in-kernel stamps of CTA 0 switched on; dumped to stderr (cycles, relative)
+#if PF_TRACE
         DevBuf dtr;
         if ((rc = dtr.alloc((size_t)4 * PF_TRACE_N * 8))) return rc;
         CK(cudaMemset(dtr.p, 0, (size_t)4 * PF_TRACE_N * 8));
@@ -1984,10 +1985,11 @@ extern "C" int q3_bench_gemm_q8(int device, int T, int N, int K, int gs, int mod
         std::vector<long long> tr((size_t)4 * PF_TRACE_N);
         CK(cudaMemcpy(tr.data(), dtr.p, tr.size() * 8, cudaMemcpyDeviceToHost));
         const long long t0 = tr[PF_TRACE_N]; // first commit
-        fprintf(stderr, "pair  mma:slot_free  mma:committed  epi:complete_seen  epi:released   (cycles after the first commit; T %d N %d K %d mode %d)\n", T, N, K, mode);
-        for (int i = 0; i < 48; i++)
-            fprintf(stderr, "%4d %14lld %14lld %18lld %14lld\n", i, tr[i] ? tr[i] - t0 : -1, tr[PF_TRACE_N + i] - t0, tr[2 * PF_TRACE_N + i] ? tr[2 * PF_TRACE_N + i] - t0 : -1,
-                    tr[3 * PF_TRACE_N + i] - t0);
+        fprintf(stderr, "pair  mma:slot_free  mma:committed   (MMA warp of CTA 0, cycles after the first commit; T %d N %d K %d mode %d)\n", T, N, K, mode);
+        for (int i = 0; i < 48; i++) fprintf(stderr, "%4d %14lld %14lld\n", i, tr[i] ? tr[i] - t0 : -1, tr[PF_TRACE_N + i] - t0);
+#else
+        fprintf(stderr, "Q3_PF_TRACE: this library was built without -DPF_TRACE=1 (python scripts/ab_variants.py build trace:PF_TRACE=1, then Q3_LIB=...)\n");
+#endif
     }
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));

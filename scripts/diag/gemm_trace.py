@@ -1,4 +1,6 @@
-"""In-kernel pipeline trace of the prefill GEMM (CTA 0): Q3_PF_TRACE=1 python scripts/diag/gemm_trace.py [mode]"""
+"""In-kernel pipeline trace of the prefill GEMM (MMA warp of CTA 0): needs a library built with -DPF_TRACE=1
+(python scripts/ab_variants.py build trace:PF_TRACE=1; Q3_LIB=qwen3_rs_b200/lib/variant_trace.so python scripts/diag/gemm_trace.py [mode]).
+The epilogue-side stamps used for profiles/r02_gemm_q8_ceilings.txt were removed again with the drain-loop rewrite."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 os.environ["Q3_PF_TRACE"] = "1"
